@@ -1,0 +1,369 @@
+// hb_gemm.cu — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   out[M,N] = epilogue( A[M,K] x W[N,K]^T ),  A and W bf16 with K contiguous, fp32 accumulate in TMEM.
+//
+// Structure (one CTA per SM, or one CTA pair per TPC when CG == 2):
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> SWIZZLE_128B smem ring, mbarrier complete_tx)
+//   warp 1      : MMA issuer     (one thread, tcgen05.mma kind::f16, 128xN (CG=1) or 256xN (CG=2) tiles)
+//   warp 2      : TMEM allocator (512 columns = two 256-column accumulator buffers)
+//   warps 4..11 : epilogue       (tcgen05.ld -> bias / GELU / residual -> vectorised st.global)
+// The accumulator is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Reference call sites replaced: every F.linear on the hot path, e.g. EVA_clip/vit_model.py:57-61
+// (fc1 -> GELU -> fc2), :124-126 (qkv with cat(q_bias, 0, v_bias)), :148 (proj), :198 (patch conv as
+// GEMM), :350 (head); EVA_clip/eva_model.py:132,143-150,249 (text tower).
+#include "hb_gemm.cuh"
+#include "hb_ptx.cuh"
+
+#include <cstdio>
+#include <mutex>
+
+namespace hb {
+
+namespace {
+
+constexpr int BM = 128;   // rows per CTA
+constexpr int BN = 256;   // max columns per tile (one UMMA N)
+constexpr int BK = 64;    // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;  // 384
+constexpr int TMEM_COLS = 512;
+
+template <int CG>
+struct Cfg {
+  static constexpr int W_ROWS = BN / CG;              // rows of W this CTA stages per k-block
+  static constexpr int A_BYTES = BM * BK * 2;         // 16 KiB
+  static constexpr int W_BYTES = W_ROWS * BK * 2;     // 32 / 16 KiB
+  static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
+  static constexpr int STAGES = (CG == 1) ? 4 : 6;    // 192 KiB either way
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TileCoord {
+  int m_blk, n_blk;
+};
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const uint32_t (&r)[32], long long row_out,
+                                                     int row_in, int col0, int n_valid) {
+  // r: 32 consecutive fp32 accumulator columns [col0, col0+32) of one row. n_valid = #columns < N in this chunk.
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (g * 4 < n_valid) {
+        const float4 b = __ldg(b4 + g);
+        v[4 * g + 0] += b.x;
+        v[4 * g + 1] += b.y;
+        v[4 * g + 2] += b.z;
+        v[4 * g + 3] += b.w;
+      }
+    }
+  }
+  if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
+    if constexpr (EPI == EPI_GELU_BF16) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    } else {
+      if (col0 < p.qcols) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.qcols) ? v[j] * p.qscale : v[j];
+      }
+    }
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_out * p.ldo + col0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (g * 8 < n_valid) {
+        uint4 q;
+        q.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
+        q.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+        q.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+        q.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+        *reinterpret_cast<uint4*>(o + 8 * g) = q;
+      }
+    }
+  } else {
+    if (p.rowadd != nullptr) {
+      const float4* a4 = reinterpret_cast<const float4*>(p.rowadd + static_cast<long long>(row_in % p.remap_in) * p.N + col0);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (g * 4 < n_valid) {
+          const float4 a = __ldg(a4 + g);
+          v[4 * g + 0] += a.x;
+          v[4 * g + 1] += a.y;
+          v[4 * g + 2] += a.z;
+          v[4 * g + 3] += a.w;
+        }
+      }
+    }
+    if (p.resid != nullptr) {
+      const float4* x4 = reinterpret_cast<const float4*>(p.resid + row_out * p.ldo + col0);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (g * 4 < n_valid) {
+          const float4 a = x4[g];
+          v[4 * g + 0] += a.x;
+          v[4 * g + 1] += a.y;
+          v[4 * g + 2] += a.z;
+          v[4 * g + 3] += a.w;
+        }
+      }
+    }
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row_out * p.ldo + col0);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (g * 4 < n_valid) o4[g] = make_float4(v[4 * g + 0], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    }
+  }
+}
+
+template <int CG, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+  using C = Cfg<CG>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + C::STAGES;          // [STAGES]
+  uint64_t* tmem_full_bar = bars + 2 * C::STAGES;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
+
+  const int tile_m = BM * CG;
+  const int m_tiles = (p.M + tile_m - 1) / tile_m;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int k_blocks = (p.K + BK - 1) / BK;
+  const int worker = blockIdx.x / CG;
+  const int num_workers = gridDim.x / CG;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS * CG);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<CG>(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+   if (lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = worker; t < total_tiles; t += num_workers) {
+      const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+      const int n0 = n_blk * BN;
+      const int n_eff = min(BN, p.N - n0);
+      const int row_a = m_blk * tile_m + static_cast<int>(cta_rank) * BM;
+      const int row_w = n0 + static_cast<int>(cta_rank) * (n_eff / CG);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = smem + stage * C::STAGE_BYTES;
+        uint8_t* sw = sa + C::A_BYTES;
+        if constexpr (CG == 1) {
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, row_a);
+          tma_load_2d(sw, &tmW, &full_bar[stage], kb * BK, row_w);
+        } else {
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, row_a);
+          tma_load_2d_pair(sw, &tmW, &full_bar[stage], kb * BK, row_w);
+        }
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+   }
+   __syncwarp();
+  } else if (warp == 1) {
+   if (lane == 0 && leader) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = worker; t < total_tiles; t += num_workers) {
+      const int n_blk = t % n_tiles;
+      const int n_eff = min(BN, p.N - n_blk * BN);
+      const uint32_t idesc = umma_idesc_bf16(BM * CG, static_cast<uint32_t>(n_eff));
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+        const uint32_t w_addr = a_addr + C::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t adesc = umma_desc_sw128(a_addr + k * UMMA_K * 2);
+          const uint64_t wdesc = umma_desc_sw128(w_addr + k * UMMA_K * 2);
+          umma_bf16<CG>(d_tmem, adesc, wdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit<CG>(&empty_bar[stage]);  // smem slot free once these MMAs retire
+        if (kb == k_blocks - 1) umma_commit<CG>(&tmem_full_bar[acc]);
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+   }
+   __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;     // column half of the tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = worker; t < total_tiles; t += num_workers) {
+      const int m_blk = t / n_tiles, n_blk = t % n_tiles;
+      const int n0 = n_blk * BN;
+      const int n_eff = min(BN, p.N - n0);
+      const int row_in = m_blk * tile_m + static_cast<int>(cta_rank) * BM + q * 32 + lane;
+      long long row_out = row_in;
+      if (p.remap_in > 0) row_out = static_cast<long long>(row_in / p.remap_in) * p.remap_out + (row_in % p.remap_in) + p.remap_off;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int c_end = min(n_eff, (half + 1) * (BN / 2));
+      for (int c = half * (BN / 2); c < c_end; c += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c);
+        tmem_ld_32x32(taddr, r);
+        tmem_ld_wait();
+        if (row_in < p.M) epilogue_store_chunk<EPI>(p, r, row_out, row_in, n0 + c, n_eff - c);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 1) mbar_arrive(&tmem_empty_bar[acc]);
+        else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  // ===================== teardown =====================
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+}
+
+// -------------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled g_encode = nullptr;
+std::once_flag g_encode_once;
+int g_encode_status = -1;
+
+template <int CG, int EPI>
+int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  using C = Cfg<CG>;
+  static bool attr_set = false;
+  auto kern = gemm_kernel<CG, EPI>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  const int tile_m = BM * CG;
+  const int m_tiles = (p.M + tile_m - 1) / tile_m;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles;
+  int workers = num_sms / CG;
+  if (workers > total) workers = total;
+  if (workers < 1) workers = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(workers * CG));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, p));
+}
+
+}  // namespace
+
+int tmap_init() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn != nullptr) {
+      g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+      g_encode_status = 0;
+    } else {
+      g_encode_status = -1;
+    }
+  });
+  return g_encode_status;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  if (tmap_init() != 0) return -1;
+  if ((ld * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(ptr) % 16) != 0) return -2;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -(1000 + static_cast<int>(r));
+}
+
+int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int epi, int cg, int num_sms,
+                cudaStream_t stream) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return -3;
+  if (p.N % 16 != 0) return -4;           // UMMA N granularity at M = 128/256 (and 16-byte stores)
+  if (cg == 2 && p.N % 32 != 0) return -4;
+  if (cg == 1) {
+    switch (epi) {
+      case EPI_BF16: return launch_impl<1, EPI_BF16>(tmA, tmW, p, num_sms, stream);
+      case EPI_GELU_BF16: return launch_impl<1, EPI_GELU_BF16>(tmA, tmW, p, num_sms, stream);
+      case EPI_F32: return launch_impl<1, EPI_F32>(tmA, tmW, p, num_sms, stream);
+    }
+  } else if (cg == 2) {
+    switch (epi) {
+      case EPI_BF16: return launch_impl<2, EPI_BF16>(tmA, tmW, p, num_sms, stream);
+      case EPI_GELU_BF16: return launch_impl<2, EPI_GELU_BF16>(tmA, tmW, p, num_sms, stream);
+      case EPI_F32: return launch_impl<2, EPI_F32>(tmA, tmW, p, num_sms, stream);
+    }
+  }
+  return -5;
+}
+
+}  // namespace hb

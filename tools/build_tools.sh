@@ -1,0 +1,7 @@
+#!/bin/bash
+# Build the standalone GPU probes (no torch dependency). Output: tools/_build/ (git-ignored, travels with gpurun).
+set -e
+cd "$(dirname "$0")/.."
+mkdir -p tools/_build
+NVCC_FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17"
+nvcc $NVCC_FLAGS -o tools/_build/gemm_selftest tools/gemm_selftest.cu hirest_b200/csrc/hb_gemm.cu
