@@ -1,0 +1,125 @@
+"""ctypes binding of libhirest_b200.so (C ABI declared in include/hirest_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or the device is not sm_100 every call
+raises.  The library is built in-tree by ``build.sh`` / ``__graft_entry__.build()``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhirest_b200.so")
+_lib = None
+_lock = threading.Lock()
+_inited_device = None
+
+c_float_p = C.POINTER(C.c_float)
+c_float_pp = C.POINTER(c_float_p)
+
+
+class HbVitConfig(C.Structure):
+    _fields_ = [("image_size", C.c_int), ("patch_size", C.c_int), ("width", C.c_int), ("layers", C.c_int),
+                ("heads", C.c_int), ("mlp_hidden", C.c_int), ("embed_dim", C.c_int), ("ln_eps", C.c_float)]
+
+
+class HbVitWeights(C.Structure):
+    _fields_ = [("cls_token", C.c_void_p), ("pos_embed", C.c_void_p), ("patch_w", C.c_void_p), ("patch_b", C.c_void_p),
+                ("norm1_w", C.c_void_p), ("norm1_b", C.c_void_p), ("q_bias", C.c_void_p), ("v_bias", C.c_void_p),
+                ("qkv_w", C.c_void_p), ("proj_w", C.c_void_p), ("proj_b", C.c_void_p), ("norm2_w", C.c_void_p),
+                ("norm2_b", C.c_void_p), ("fc1_w", C.c_void_p), ("fc1_b", C.c_void_p), ("fc2_w", C.c_void_p),
+                ("fc2_b", C.c_void_p), ("norm_w", C.c_void_p), ("norm_b", C.c_void_p), ("head_w", C.c_void_p),
+                ("head_b", C.c_void_p)]
+
+
+class HbTextConfig(C.Structure):
+    _fields_ = [("context_length", C.c_int), ("vocab_size", C.c_int), ("width", C.c_int), ("heads", C.c_int),
+                ("layers", C.c_int), ("embed_dim", C.c_int), ("ln_eps", C.c_float)]
+
+
+class HbTextWeights(C.Structure):
+    _fields_ = [("token_embedding", C.c_void_p), ("positional_embedding", C.c_void_p), ("ln1_w", C.c_void_p),
+                ("ln1_b", C.c_void_p), ("in_proj_w", C.c_void_p), ("in_proj_b", C.c_void_p), ("out_proj_w", C.c_void_p),
+                ("out_proj_b", C.c_void_p), ("ln2_w", C.c_void_p), ("ln2_b", C.c_void_p), ("fc_w", C.c_void_p),
+                ("fc_b", C.c_void_p), ("cproj_w", C.c_void_p), ("cproj_b", C.c_void_p), ("ln_final_w", C.c_void_p),
+                ("ln_final_b", C.c_void_p), ("text_projection", C.c_void_p)]
+
+
+# name -> (restype, argtypes); must list every symbol include/hirest_b200.h declares (tests check this).
+SIGNATURES = {
+    "hb_init": (C.c_int, [C.c_int]),
+    "hb_last_error": (C.c_char_p, []),
+    "hb_strerror": (C.c_char_p, [C.c_int]),
+    "hb_launch_count": (C.c_int64, []),
+    "hb_set_gemm_cta_group": (C.c_int, [C.c_int]),
+    "hb_vit_create": (C.c_int, [C.POINTER(HbVitConfig), C.POINTER(HbVitWeights), C.c_int, C.c_void_p,
+                                C.POINTER(C.c_void_p)]),
+    "hb_vit_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "hb_vit_set_tap": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "hb_vit_destroy": (None, [C.c_void_p]),
+    "hb_text_create": (C.c_int, [C.POINTER(HbTextConfig), C.POINTER(HbTextWeights), C.c_int, C.c_void_p,
+                                 C.POINTER(C.c_void_p)]),
+    "hb_text_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "hb_text_destroy": (None, [C.c_void_p]),
+    "hb_pool_normalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "hb_similarity": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int,
+                                C.c_void_p]),
+    "hb_linear": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                            C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_void_p]),
+    "hb_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int64, C.c_int, C.c_void_p, C.c_int,
+                               C.c_void_p]),
+    "hb_vit_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "hb_small_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                     C.c_float, C.c_int, C.c_float, C.c_int, C.c_void_p]),
+}
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load():
+    """dlopen the library (no device needed) and attach signatures."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(_LIB_PATH):
+                raise RuntimeError(
+                    f"{_LIB_PATH} not found: build it with ./build.sh (nvcc, sm_100a). hirest_b200 has no CPU fallback.")
+            lib = C.CDLL(_LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        lib = load()
+        msg = lib.hb_last_error().decode(errors="replace")
+        raise RuntimeError(f"hirest_b200: {what} failed with {rc} ({lib.hb_strerror(rc).decode()}): {msg}")
+
+
+def init(device: int = 0):
+    """hb_init once per process/device. Raises if the device is not a B200-class (sm_100) GPU."""
+    global _inited_device
+    lib = load()
+    if _inited_device != device:
+        check(lib.hb_init(int(device)), "hb_init")
+        _inited_device = device
+    return lib
+
+
+def stream_ptr(device=None) -> int:
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def ptr_array(tensors):
+    """Host array of device pointers (HbVitWeights per-layer members). Keeps no reference to the tensors."""
+    arr = (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr

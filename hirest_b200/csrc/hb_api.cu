@@ -1,0 +1,548 @@
+// hb_api.cu — the C ABI (include/hirest_b200.h): model handles (weights repacked to bf16 once, workspace,
+// TMA tensor maps) and the per-call kernel sequences for encode_image / encode_text / retrieval scoring.
+#include "../../include/hirest_b200.h"
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "hb_attn.cuh"
+#include "hb_elem.cuh"
+#include "hb_gemm.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+int g_cg = 2;
+int g_num_sms = 148;
+bool g_inited = false;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define HB_CUDA(x)                                                                                   \
+  do {                                                                                               \
+    cudaError_t e_ = (x);                                                                            \
+    if (e_ != cudaSuccess) return fail(HB_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define HB_LAUNCH(x)                                                                                 \
+  do {                                                                                               \
+    int r_ = (x);                                                                                    \
+    if (r_ != 0) {                                                                                   \
+      if (r_ > 0) return fail(HB_ERR_CUDA, "%s: %s (%s:%d)", #x, cudaGetErrorString((cudaError_t)r_), __FILE__, __LINE__); \
+      return fail(HB_ERR_INVALID, "%s: invalid argument code %d (%s:%d)", #x, r_, __FILE__, __LINE__); \
+    }                                                                                                \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                              \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t n) {
+    if (p) { cudaFree(p); p = nullptr; }
+    bytes = n;
+    if (n == 0) return 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) { p = nullptr; return fail(HB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e)); }
+    return 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// fp32 [N,K] (optionally transposed source [K,N]) -> bf16 [N,Kpad], zero padded.
+__global__ void repack_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int K, int Kpad,
+                                     int transposed) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(N) * Kpad) return;
+  const int n = static_cast<int>(t / Kpad), k = static_cast<int>(t % Kpad);
+  float v = 0.f;
+  if (k < K) v = transposed ? src[static_cast<long long>(k) * N + n] : src[static_cast<long long>(n) * K + k];
+  dst[t] = __float2bfloat16(v);
+}
+
+// A Linear layer held by a handle: bf16 weight [N,Kpad] + fp32 bias + TMA map.
+struct Linear {
+  DevBuf w, b;
+  CUtensorMap tm;
+  int N = 0, K = 0, Kpad = 0, cg = 2;
+  bool has_bias = false;
+  // bias may be assembled from up to three pieces (q_bias | zeros | v_bias), each of length N/3.
+  int init(const float* w_src, int N_, int K_, const float* bias, bool transposed, cudaStream_t s, const float* bias_q = nullptr,
+           const float* bias_v = nullptr) {
+    N = N_; K = K_; cg = g_cg;
+    Kpad = (K + 7) / 8 * 8;
+    if (int r = w.alloc(static_cast<size_t>(N) * Kpad * 2)) return r;
+    const long long total = static_cast<long long>(N) * Kpad;
+    repack_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w_src, w.as<__nv_bfloat16>(), N, K, Kpad,
+                                                                                     transposed ? 1 : 0);
+    HB_CUDA(cudaGetLastError());
+    if (bias != nullptr || bias_q != nullptr) {
+      has_bias = true;
+      if (int r = b.alloc(static_cast<size_t>(N) * 4)) return r;
+      if (bias != nullptr) {
+        HB_CUDA(cudaMemcpyAsync(b.p, bias, static_cast<size_t>(N) * 4, cudaMemcpyDeviceToDevice, s));
+      } else {
+        const int D = N / 3;
+        HB_CUDA(cudaMemsetAsync(b.p, 0, static_cast<size_t>(N) * 4, s));
+        HB_CUDA(cudaMemcpyAsync(b.p, bias_q, static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice, s));
+        HB_CUDA(cudaMemcpyAsync(b.as<float>() + 2 * D, bias_v, static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice, s));
+      }
+    }
+    int r = hb::make_tmap_bf16(&tm, w.p, N, Kpad, Kpad, hb::gemm_w_box_rows(cg));
+    if (r) return fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled(weight %dx%d) failed: %d", N, Kpad, r);
+    return 0;
+  }
+  const float* bias() const { return has_bias ? b.as<float>() : nullptr; }
+};
+
+// bf16 activation buffer usable as a GEMM A operand.
+struct Act {
+  DevBuf buf;
+  CUtensorMap tm;
+  long long rows = 0;
+  int cols = 0;
+  int init(long long rows_, int cols_) {
+    rows = rows_; cols = cols_;
+    if (int r = buf.alloc(static_cast<size_t>(rows) * cols * 2)) return r;
+    int r = hb::make_tmap_bf16(&tm, buf.p, rows, cols, cols, hb::gemm_a_box_rows());
+    if (r) return fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled(act %lldx%d) failed: %d", rows, cols, r);
+    return 0;
+  }
+  __nv_bfloat16* ptr() const { return buf.as<__nv_bfloat16>(); }
+};
+
+struct F32Vec {
+  DevBuf d;
+  int init(const float* src, size_t n, cudaStream_t s) {
+    if (int r = d.alloc(n * 4)) return r;
+    HB_CUDA(cudaMemcpyAsync(d.p, src, n * 4, cudaMemcpyDeviceToDevice, s));
+    return 0;
+  }
+  const float* ptr() const { return d.as<float>(); }
+};
+
+int run_gemm(const CUtensorMap& tmA, const Linear& L, long long M, void* out, int ldo, int epi, cudaStream_t s,
+             const float* resid = nullptr, float qscale = 1.f, int qcols = 0, const float* rowadd = nullptr, int remap_in = 0,
+             int remap_out = 0, int remap_off = 0) {
+  hb::GemmParams p;
+  p.M = static_cast<int>(M); p.N = L.N; p.K = L.Kpad;
+  p.bias = L.bias(); p.out = out; p.ldo = ldo; p.resid = resid;
+  p.qscale = qscale; p.qcols = qcols;
+  p.rowadd = rowadd; p.remap_in = remap_in; p.remap_out = remap_out; p.remap_off = remap_off;
+  HB_LAUNCH(hb::gemm_launch(tmA, L.tm, p, epi, L.cg, g_num_sms, s));
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// ViT
+// =================================================================================================
+struct HbVit {
+  HbVitConfig cfg;
+  int T = 0, Kpatch = 0, max_batch = 0;
+  F32Vec cls, pos;
+  Linear patch;
+  struct Layer {
+    F32Vec n1w, n1b, n2w, n2b;
+    Linear qkv, proj, fc1, fc2;
+  };
+  std::vector<std::unique_ptr<Layer>> layers;
+  F32Vec nw, nb;
+  Linear head;
+  Act col, h, hid, clsn;
+  DevBuf x, qkv, cls_idx;
+  int tap_layer = -1;
+  float* tap_dst = nullptr;
+};
+
+extern "C" {
+
+int hb_init(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return fail(HB_ERR_NODEVICE, "no CUDA device visible");
+  if (device < 0 || device >= n) return fail(HB_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+  HB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  HB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(HB_ERR_NODEVICE, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
+  g_num_sms = prop.multiProcessorCount;
+  if (hb::tmap_init() != 0) return fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  g_inited = true;
+  return HB_OK;
+}
+
+const char* hb_last_error(void) { return g_err; }
+
+const char* hb_strerror(int code) {
+  switch (code) {
+    case HB_OK: return "ok";
+    case HB_ERR_INVALID: return "invalid argument or unsupported shape";
+    case HB_ERR_NOMEM: return "out of device memory";
+    case HB_ERR_CUDA: return "CUDA error";
+    case HB_ERR_NODEVICE: return "no sm_100 device";
+    default: return "unknown error";
+  }
+}
+
+int64_t hb_launch_count(void) { return g_launches.load(); }
+
+int hb_set_gemm_cta_group(int cg) {
+  if (cg != 1 && cg != 2) return fail(HB_ERR_INVALID, "cta group must be 1 or 2");
+  g_cg = cg;
+  return HB_OK;
+}
+
+int hb_vit_create(const HbVitConfig* cfg, const HbVitWeights* w, int max_batch, void* stream, HbVit** out) {
+  if (!g_inited) return fail(HB_ERR_INVALID, "hb_init() not called");
+  if (!cfg || !w || !out || max_batch <= 0) return fail(HB_ERR_INVALID, "null argument");
+  const int D = cfg->width, H = cfg->heads, F = cfg->mlp_hidden, E = cfg->embed_dim, P = cfg->patch_size, S = cfg->image_size;
+  if (D != H * 88) return fail(HB_ERR_INVALID, "head_dim must be 88 (width %d, heads %d)", D, H);
+  if (S != 224 || P != 14) return fail(HB_ERR_INVALID, "only 224x224 / patch 14 (257 tokens) is supported");  // vit_model.py:203-204
+  if (D % 16 || F % 16 || E % 16) return fail(HB_ERR_INVALID, "width/mlp_hidden/embed_dim must be multiples of 16");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::unique_ptr<HbVit> m(new (std::nothrow) HbVit);
+  if (!m) return fail(HB_ERR_NOMEM, "host allocation failed");
+  m->cfg = *cfg;
+  m->T = (S / P) * (S / P) + 1;
+  m->Kpatch = 3 * P * P;
+  m->max_batch = max_batch;
+  int r;
+  if ((r = m->cls.init(w->cls_token, D, s))) return r;
+  if ((r = m->pos.init(w->pos_embed, static_cast<size_t>(m->T) * D, s))) return r;
+  if ((r = m->patch.init(w->patch_w, D, m->Kpatch, w->patch_b, false, s))) return r;
+  for (int i = 0; i < cfg->layers; ++i) {
+    std::unique_ptr<HbVit::Layer> L(new HbVit::Layer);
+    if ((r = L->n1w.init(w->norm1_w[i], D, s))) return r;
+    if ((r = L->n1b.init(w->norm1_b[i], D, s))) return r;
+    if ((r = L->n2w.init(w->norm2_w[i], D, s))) return r;
+    if ((r = L->n2b.init(w->norm2_b[i], D, s))) return r;
+    // qkv bias = cat(q_bias, zeros, v_bias), built once instead of every forward (vit_model.py:124)
+    if ((r = L->qkv.init(w->qkv_w[i], 3 * D, D, nullptr, false, s, w->q_bias[i], w->v_bias[i]))) return r;
+    if ((r = L->proj.init(w->proj_w[i], D, D, w->proj_b[i], false, s))) return r;
+    if ((r = L->fc1.init(w->fc1_w[i], F, D, w->fc1_b[i], false, s))) return r;
+    if ((r = L->fc2.init(w->fc2_w[i], D, F, w->fc2_b[i], false, s))) return r;
+    m->layers.push_back(std::move(L));
+  }
+  if ((r = m->nw.init(w->norm_w, D, s))) return r;
+  if ((r = m->nb.init(w->norm_b, D, s))) return r;
+  if ((r = m->head.init(w->head_w, E, D, w->head_b, false, s))) return r;
+  const long long rows = static_cast<long long>(max_batch) * m->T;
+  if ((r = m->col.init(static_cast<long long>(max_batch) * (m->T - 1), m->patch.Kpad))) return r;
+  if ((r = m->h.init(rows, D))) return r;
+  if ((r = m->hid.init(rows, F))) return r;
+  if ((r = m->clsn.init(max_batch, D))) return r;
+  if ((r = m->x.alloc(static_cast<size_t>(rows) * D * 4))) return r;
+  if ((r = m->qkv.alloc(static_cast<size_t>(rows) * 3 * D * 2))) return r;
+  if ((r = m->cls_idx.alloc(static_cast<size_t>(max_batch) * 4))) return r;
+  {
+    std::vector<int> idx(max_batch);
+    for (int i = 0; i < max_batch; ++i) idx[i] = i * m->T;
+    HB_CUDA(cudaMemcpyAsync(m->cls_idx.p, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, s));
+    HB_CUDA(cudaStreamSynchronize(s));  // idx is a host temporary; also surfaces repack errors at create time
+  }
+  *out = m.release();
+  return HB_OK;
+}
+
+int hb_vit_set_tap(HbVit* m, int layer, float* dst) {
+  if (!m) return fail(HB_ERR_INVALID, "null handle");
+  m->tap_layer = dst ? layer : -1;
+  m->tap_dst = dst;
+  return HB_OK;
+}
+
+static int vit_encode_chunk(HbVit* m, const float* frames, int B, float* out, cudaStream_t s) {
+  const HbVitConfig& c = m->cfg;
+  const int D = c.width, T = m->T, F = c.mlp_hidden, E = c.embed_dim;
+  const long long M = static_cast<long long>(B) * T;
+  float* x = m->x.as<float>();
+  __nv_bfloat16* qkv = m->qkv.as<__nv_bfloat16>();
+  int r;
+  // patch embed: gather -> GEMM (+bias +pos, rows remapped past the cls slot); cls row separately
+  HB_LAUNCH(hb::im2col_patch_launch(frames, m->col.ptr(), B, c.image_size, c.patch_size, m->patch.Kpad, s));
+  if ((r = run_gemm(m->col.tm, m->patch, static_cast<long long>(B) * (T - 1), x, D, hb::EPI_F32, s, nullptr, 1.f, 0,
+                    m->pos.ptr() + D, T - 1, T, 1)))
+    return r;
+  HB_LAUNCH(hb::cls_row_launch(x, m->cls.ptr(), m->pos.ptr(), B, T, D, s));
+  if (m->tap_layer == 0 && m->tap_dst)
+    HB_CUDA(cudaMemcpyAsync(m->tap_dst, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, s));
+  const float qscale = 1.0f / sqrtf(88.0f);
+  for (int i = 0; i < c.layers; ++i) {
+    HbVit::Layer& L = *m->layers[i];
+    hb::LayerNormParams ln;
+    ln.x = x; ln.ldx = D; ln.y = m->h.ptr(); ln.ldy = D; ln.w = L.n1w.ptr(); ln.b = L.n1b.ptr();
+    ln.eps = c.ln_eps; ln.rows = static_cast<int>(M); ln.D = D;
+    HB_LAUNCH(hb::layernorm_launch(ln, true, s));
+    if ((r = run_gemm(m->h.tm, L.qkv, M, qkv, 3 * D, hb::EPI_BF16, s, nullptr, qscale, D))) return r;
+    hb::AttnParams ap;
+    ap.qkv = qkv; ap.out = m->h.ptr(); ap.B = B; ap.H = c.heads;
+    HB_LAUNCH(hb::vit_attn_launch(ap, s));
+    if ((r = run_gemm(m->h.tm, L.proj, M, x, D, hb::EPI_F32, s, x))) return r;
+    ln.w = L.n2w.ptr(); ln.b = L.n2b.ptr();
+    HB_LAUNCH(hb::layernorm_launch(ln, true, s));
+    if ((r = run_gemm(m->h.tm, L.fc1, M, m->hid.ptr(), F, hb::EPI_GELU_BF16, s))) return r;
+    if ((r = run_gemm(m->hid.tm, L.fc2, M, x, D, hb::EPI_F32, s, x))) return r;
+    if (m->tap_layer == i + 1 && m->tap_dst)
+      HB_CUDA(cudaMemcpyAsync(m->tap_dst, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  // final norm on the cls rows only (LayerNorm is row-wise; rows 1..256 are never read, vit_model.py:340-346)
+  hb::LayerNormParams ln;
+  ln.x = x; ln.ldx = D; ln.row_idx = m->cls_idx.as<int>(); ln.y = m->clsn.ptr(); ln.ldy = D;
+  ln.w = m->nw.ptr(); ln.b = m->nb.ptr(); ln.eps = c.ln_eps; ln.rows = B; ln.D = D;
+  HB_LAUNCH(hb::layernorm_launch(ln, true, s));
+  if ((r = run_gemm(m->clsn.tm, m->head, B, out, E, hb::EPI_F32, s))) return r;
+  return HB_OK;
+}
+
+int hb_vit_encode(HbVit* m, const float* frames, int64_t B, float* out, void* stream) {
+  if (!m || !frames || !out) return fail(HB_ERR_INVALID, "null argument");
+  if (B < 0) return fail(HB_ERR_INVALID, "negative batch");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t frame_elems = static_cast<size_t>(3) * m->cfg.image_size * m->cfg.image_size;
+  for (int64_t b0 = 0; b0 < B; b0 += m->max_batch) {
+    const int nb = static_cast<int>(std::min<int64_t>(m->max_batch, B - b0));
+    int r = vit_encode_chunk(m, frames + b0 * frame_elems, nb, out + b0 * m->cfg.embed_dim, s);
+    if (r) return r;
+  }
+  return HB_OK;
+}
+
+void hb_vit_destroy(HbVit* m) { delete m; }
+
+}  // extern "C"
+
+// =================================================================================================
+// Text tower
+// =================================================================================================
+struct HbText {
+  HbTextConfig cfg;
+  int max_batch = 0;
+  F32Vec tok, pos;
+  struct Layer {
+    F32Vec l1w, l1b, l2w, l2b;
+    Linear qkv, out, fc, cproj;
+  };
+  std::vector<std::unique_ptr<Layer>> layers;
+  F32Vec lfw, lfb;
+  Linear proj;
+  Act h, hid, eot;
+  DevBuf x, qkv, eot_row;
+};
+
+extern "C" {
+
+int hb_text_create(const HbTextConfig* cfg, const HbTextWeights* w, int max_batch, void* stream, HbText** out) {
+  if (!g_inited) return fail(HB_ERR_INVALID, "hb_init() not called");
+  if (!cfg || !w || !out || max_batch <= 0) return fail(HB_ERR_INVALID, "null argument");
+  const int W = cfg->width, C = cfg->context_length, E = cfg->embed_dim;
+  if (W != cfg->heads * 64) return fail(HB_ERR_INVALID, "text head_dim must be 64 (width %d, heads %d)", W, cfg->heads);
+  if (W % 16 || E % 16) return fail(HB_ERR_INVALID, "width/embed_dim must be multiples of 16");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::unique_ptr<HbText> m(new (std::nothrow) HbText);
+  if (!m) return fail(HB_ERR_NOMEM, "host allocation failed");
+  m->cfg = *cfg;
+  m->max_batch = max_batch;
+  int r;
+  if ((r = m->tok.init(w->token_embedding, static_cast<size_t>(cfg->vocab_size) * W, s))) return r;
+  if ((r = m->pos.init(w->positional_embedding, static_cast<size_t>(C) * W, s))) return r;
+  for (int i = 0; i < cfg->layers; ++i) {
+    std::unique_ptr<HbText::Layer> L(new HbText::Layer);
+    if ((r = L->l1w.init(w->ln1_w[i], W, s))) return r;
+    if ((r = L->l1b.init(w->ln1_b[i], W, s))) return r;
+    if ((r = L->l2w.init(w->ln2_w[i], W, s))) return r;
+    if ((r = L->l2b.init(w->ln2_b[i], W, s))) return r;
+    if ((r = L->qkv.init(w->in_proj_w[i], 3 * W, W, w->in_proj_b[i], false, s))) return r;
+    if ((r = L->out.init(w->out_proj_w[i], W, W, w->out_proj_b[i], false, s))) return r;
+    if ((r = L->fc.init(w->fc_w[i], 4 * W, W, w->fc_b[i], false, s))) return r;
+    if ((r = L->cproj.init(w->cproj_w[i], W, 4 * W, w->cproj_b[i], false, s))) return r;
+    m->layers.push_back(std::move(L));
+  }
+  if ((r = m->lfw.init(w->ln_final_w, W, s))) return r;
+  if ((r = m->lfb.init(w->ln_final_b, W, s))) return r;
+  if ((r = m->proj.init(w->text_projection, E, W, nullptr, /*transposed=*/true, s))) return r;  // x @ P == x P'^T, P' = P^T
+  const long long rows = static_cast<long long>(max_batch) * C;
+  if ((r = m->h.init(rows, W))) return r;
+  if ((r = m->hid.init(rows, 4 * W))) return r;
+  if ((r = m->eot.init(max_batch, W))) return r;
+  if ((r = m->x.alloc(static_cast<size_t>(rows) * W * 4))) return r;
+  if ((r = m->qkv.alloc(static_cast<size_t>(rows) * 3 * W * 2))) return r;
+  if ((r = m->eot_row.alloc(static_cast<size_t>(max_batch) * 4))) return r;
+  HB_CUDA(cudaStreamSynchronize(s));
+  *out = m.release();
+  return HB_OK;
+}
+
+static int text_encode_chunk(HbText* m, const int64_t* ids, int Q, float* out, cudaStream_t s) {
+  const HbTextConfig& c = m->cfg;
+  const int W = c.width, C = c.context_length, E = c.embed_dim;
+  const long long M = static_cast<long long>(Q) * C;
+  float* x = m->x.as<float>();
+  __nv_bfloat16* qkv = m->qkv.as<__nv_bfloat16>();
+  int r;
+  HB_LAUNCH(hb::text_embed_launch(reinterpret_cast<const long long*>(ids), m->tok.ptr(), m->pos.ptr(), x,
+                                  m->eot_row.as<int>(), Q, C, W, c.vocab_size, s));
+  for (int i = 0; i < c.layers; ++i) {
+    HbText::Layer& L = *m->layers[i];
+    hb::LayerNormParams ln;
+    ln.x = x; ln.ldx = W; ln.y = m->h.ptr(); ln.ldy = W; ln.w = L.l1w.ptr(); ln.b = L.l1b.ptr();
+    ln.eps = c.ln_eps; ln.rows = static_cast<int>(M); ln.D = W;
+    HB_LAUNCH(hb::layernorm_launch(ln, true, s));
+    if ((r = run_gemm(m->h.tm, L.qkv, M, qkv, 3 * W, hb::EPI_BF16, s))) return r;
+    hb::SmallAttnParams ap;
+    ap.q = qkv; ap.k = qkv + W; ap.v = qkv + 2 * W; ap.out = m->h.ptr();
+    ap.B = Q; ap.H = c.heads; ap.Tq = C; ap.Tk = C;
+    ap.ldq = ap.ldk = ap.ldv = 3 * W; ap.ldo = W;
+    ap.bsq = ap.bsk = ap.bsv = static_cast<long long>(C) * 3 * W; ap.bso = static_cast<long long>(C) * W;
+    ap.scale = 0.125f;   // head_dim^-0.5, nn.MultiheadAttention
+    ap.mask_mode = 1;    // causal, eva_model.py:224-230
+    HB_LAUNCH(hb::small_attn_launch(ap, s));
+    if ((r = run_gemm(m->h.tm, L.out, M, x, W, hb::EPI_F32, s, x))) return r;
+    ln.w = L.l2w.ptr(); ln.b = L.l2b.ptr();
+    HB_LAUNCH(hb::layernorm_launch(ln, true, s));
+    if ((r = run_gemm(m->h.tm, L.fc, M, m->hid.ptr(), 4 * W, hb::EPI_GELU_BF16, s))) return r;
+    if ((r = run_gemm(m->hid.tm, L.cproj, M, x, W, hb::EPI_F32, s, x))) return r;
+  }
+  // ln_final on the EOT rows only (row-wise op; eva_model.py:239-243), then @ text_projection (:249)
+  hb::LayerNormParams ln;
+  ln.x = x; ln.ldx = W; ln.row_idx = m->eot_row.as<int>(); ln.y = m->eot.ptr(); ln.ldy = W;
+  ln.w = m->lfw.ptr(); ln.b = m->lfb.ptr(); ln.eps = c.ln_eps; ln.rows = Q; ln.D = W;
+  HB_LAUNCH(hb::layernorm_launch(ln, true, s));
+  if ((r = run_gemm(m->eot.tm, m->proj, Q, out, E, hb::EPI_F32, s))) return r;
+  return HB_OK;
+}
+
+int hb_text_encode(HbText* m, const int64_t* ids, int64_t Q, float* out, void* stream) {
+  if (!m || !ids || !out) return fail(HB_ERR_INVALID, "null argument");
+  if (Q < 0) return fail(HB_ERR_INVALID, "negative batch");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int64_t q0 = 0; q0 < Q; q0 += m->max_batch) {
+    const int nq = static_cast<int>(std::min<int64_t>(m->max_batch, Q - q0));
+    int r = text_encode_chunk(m, ids + q0 * m->cfg.context_length, nq, out + q0 * m->cfg.embed_dim, s);
+    if (r) return r;
+  }
+  return HB_OK;
+}
+
+void hb_text_destroy(HbText* m) { delete m; }
+
+// =================================================================================================
+// retrieval scoring + generic ops
+// =================================================================================================
+int hb_pool_normalize(const float* emb, int64_t V, int F, int E, float* out, void* stream) {
+  if (!emb || !out) return fail(HB_ERR_INVALID, "null argument");
+  if (V == 0) return HB_OK;
+  HB_LAUNCH(hb::pool_normalize_launch(emb, out, V, F, E, true, false, static_cast<cudaStream_t>(stream)));
+  return HB_OK;
+}
+
+int hb_similarity(const float* text, int64_t Q, const float* video, int64_t V, int E, float* scores, int64_t ld_scores,
+                  int exact, void* stream) {
+  if (!g_inited) return fail(HB_ERR_INVALID, "hb_init() not called");
+  if (!text || !video || !scores) return fail(HB_ERR_INVALID, "null argument");
+  if (Q == 0 || V == 0) return HB_OK;
+  if (E % 8 != 0 || V % 16 != 0 || ld_scores % 4 != 0 || ld_scores < V)
+    return fail(HB_ERR_INVALID, "hb_similarity needs E %% 8 == 0, V %% 16 == 0 (pad the gallery), ld_scores %% 4 == 0");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int Kx = exact ? 3 * E : E;
+  // scratch is allocated on the stream (cudaMallocAsync): no hidden sync, freed in stream order
+  __nv_bfloat16 *tb = nullptr, *vb = nullptr;
+  HB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tb), static_cast<size_t>(Q) * Kx * 2, s));
+  HB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&vb), static_cast<size_t>(V) * Kx * 2, s));
+  int rc = HB_OK;
+  do {
+    if (exact) {
+      int r1 = hb::split_bf16_launch(text, tb, Q, E, 0, s), r2 = hb::split_bf16_launch(video, vb, V, E, 1, s);
+      if (r1 || r2) { rc = fail(HB_ERR_CUDA, "split_bf16 launch failed"); break; }
+    } else {
+      int r1 = hb::f32_to_bf16_launch(text, tb, Q * E, s), r2 = hb::f32_to_bf16_launch(video, vb, V * E, s);
+      if (r1 || r2) { rc = fail(HB_ERR_CUDA, "f32_to_bf16 launch failed"); break; }
+    }
+    g_launches.fetch_add(2);
+    CUtensorMap tmT, tmV;
+    if (hb::make_tmap_bf16(&tmT, tb, Q, Kx, Kx, hb::gemm_a_box_rows()) ||
+        hb::make_tmap_bf16(&tmV, vb, V, Kx, Kx, hb::gemm_w_box_rows(g_cg))) {
+      rc = fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled failed for similarity operands");
+      break;
+    }
+    hb::GemmParams p;
+    p.M = static_cast<int>(Q); p.N = static_cast<int>(V); p.K = Kx; p.out = scores; p.ldo = static_cast<int>(ld_scores);
+    int r = hb::gemm_launch(tmT, tmV, p, hb::EPI_F32, g_cg, g_num_sms, s);
+    if (r) { rc = fail(HB_ERR_CUDA, "similarity GEMM launch failed: %d", r); break; }
+    g_launches.fetch_add(1);
+  } while (0);
+  cudaFreeAsync(tb, s);
+  cudaFreeAsync(vb, s);
+  return rc;
+}
+
+int hb_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const float* resid, void* out,
+              int64_t ldo, int64_t M, int64_t N, int64_t K, int epilogue, void* stream) {
+  if (!g_inited) return fail(HB_ERR_INVALID, "hb_init() not called");
+  if (!x || !w || !out) return fail(HB_ERR_INVALID, "null argument");
+  if (M == 0) return HB_OK;
+  if (K % 8 || N % 16 || ldx % 8 || ldw % 8) return fail(HB_ERR_INVALID, "hb_linear needs K %% 8 == 0, N %% 16 == 0, ld %% 8 == 0");
+  if (epilogue < 0 || epilogue > 2) return fail(HB_ERR_INVALID, "bad epilogue %d", epilogue);
+  if (resid && epilogue != HB_EPI_F32) return fail(HB_ERR_INVALID, "residual needs HB_EPI_F32");
+  CUtensorMap tmA, tmW;
+  if (hb::make_tmap_bf16(&tmA, x, M, K, ldx, hb::gemm_a_box_rows()) || hb::make_tmap_bf16(&tmW, w, N, K, ldw, hb::gemm_w_box_rows(g_cg)))
+    return fail(HB_ERR_INVALID, "cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)");
+  hb::GemmParams p;
+  p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
+  p.bias = bias; p.out = out; p.ldo = static_cast<int>(ldo); p.resid = resid;
+  HB_LAUNCH(hb::gemm_launch(tmA, tmW, p, epilogue, g_cg, g_num_sms, static_cast<cudaStream_t>(stream)));
+  return HB_OK;
+}
+
+int hb_layernorm(const float* x, const float* w, const float* b, float eps, int64_t rows, int D, void* y, int out_bf16,
+                 void* stream) {
+  if (!x || !w || !b || !y) return fail(HB_ERR_INVALID, "null argument");
+  hb::LayerNormParams ln;
+  ln.x = x; ln.ldx = D; ln.y = y; ln.ldy = D; ln.w = w; ln.b = b; ln.eps = eps; ln.rows = static_cast<int>(rows); ln.D = D;
+  HB_LAUNCH(hb::layernorm_launch(ln, out_bf16 != 0, static_cast<cudaStream_t>(stream)));
+  return HB_OK;
+}
+
+int hb_vit_attention(const void* qkv, void* out, int64_t B, int H, void* stream) {
+  if (!qkv || !out) return fail(HB_ERR_INVALID, "null argument");
+  if (B == 0) return HB_OK;
+  hb::AttnParams ap;
+  ap.qkv = static_cast<const __nv_bfloat16*>(qkv); ap.out = static_cast<__nv_bfloat16*>(out);
+  ap.B = static_cast<int>(B); ap.H = H;
+  HB_LAUNCH(hb::vit_attn_launch(ap, static_cast<cudaStream_t>(stream)));
+  return HB_OK;
+}
+
+int hb_small_attention(const void* q, const void* k, const void* v, void* out, int B, int H, int Tq, int Tk, int ldq, int ldk,
+                       int ldv, int ldo, int64_t bsq, int64_t bsk, int64_t bsv, int64_t bso, float scale, int mask_mode,
+                       float mask_const, int causal_soft, void* stream) {
+  if (!q || !k || !v || !out) return fail(HB_ERR_INVALID, "null argument");
+  hb::SmallAttnParams ap;
+  ap.q = static_cast<const __nv_bfloat16*>(q); ap.k = static_cast<const __nv_bfloat16*>(k);
+  ap.v = static_cast<const __nv_bfloat16*>(v); ap.out = static_cast<__nv_bfloat16*>(out);
+  ap.B = B; ap.H = H; ap.Tq = Tq; ap.Tk = Tk; ap.ldq = ldq; ap.ldk = ldk; ap.ldv = ldv; ap.ldo = ldo;
+  ap.bsq = bsq; ap.bsk = bsk; ap.bsv = bsv; ap.bso = bso; ap.scale = scale; ap.mask_mode = mask_mode;
+  ap.mask_const = mask_const; ap.causal_soft = causal_soft;
+  HB_LAUNCH(hb::small_attn_launch(ap, static_cast<cudaStream_t>(stream)));
+  return HB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,354 @@
+// hb_attn.cu — fused multi-head attention for the EVA ViT-g/14 block on sm_100a (tcgen05 + TMEM).
+//
+// Replaces EVA_clip/vit_model.py:127-147: reshape/permute of qkv, q*scale, q@k^T, softmax, @v,
+// transpose/reshape — without materialising the [B,16,257,257] score tensor.
+//
+// One CTA per (frame, head).  257 tokens = 2 x 128 query rows + 1: tokens 0..255 run on the tensor
+// cores (S = Q K^T as two 128x256 UMMA tiles in TMEM, O = P V as two 128x96 tiles), token 256 is the
+// "extra" token: its key/value column is folded into the softmax / output by the softmax threads
+// (rank-1 update), and its query row is computed by one CUDA-core warp.  head_dim 88 is padded to 96
+// (zero chunk) for the K=16 UMMA steps.
+//
+//   warps 0-3 : loaders, then softmax + output for query tile 0 (one thread per row)
+//   warps 4-7 : loaders, then softmax + output for query tile 1
+//   warp  8   : TMEM allocation + single-thread MMA issue
+//   warp  9   : query row 256 on CUDA cores (reads K/V straight from L2)
+//
+// Shared memory (SWIZZLE_128B slabs, 128 B per row, 8-row groups 1024 B apart):
+//   Q region 64 KiB: tile g, slab s (d 0..63 | d 64..95)           -> later overwritten by P tile 1
+//   K region 64 KiB: slab s, 256 key rows                           -> later overwritten by P tile 0
+//   V region 64 KiB: slab s, 256 key rows (MN-major B operand of P·V)
+// q arrives pre-scaled by head_dim^-0.5 (QKV GEMM epilogue).
+#include "hb_attn.cuh"
+#include "hb_ptx.cuh"
+
+namespace hb {
+namespace {
+
+constexpr int T_TOK = 257;
+constexpr int TQ = 256;       // tokens handled on tensor cores (queries and keys)
+constexpr int DH = 88;
+constexpr int NCHUNK = 11;    // 16-byte chunks per head row
+constexpr int ATT_THREADS = 320;
+constexpr uint32_t Q_OFF = 0, K_OFF = 65536, V_OFF = 131072, MISC_OFF = 196608;
+constexpr uint32_t ATT_SMEM = MISC_OFF + 2048 + 1024;
+constexpr float LOG2E = 1.4426950408889634f;
+
+// MN-major SWIZZLE_128B descriptor (B operand = V[key][d], d contiguous): 64-element (128 B) rows along N,
+// 8-key groups 1024 B apart (SBO), 64-wide d slabs `lbo_bytes` apart (LBO).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ uint4 ldg16(const void* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ void sts16(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+// Copy 256 rows x 88 bf16 (row stride ld elements) into two SW128 slabs; chunk 11 (d 88..95) is zeroed.
+// rows_per_tile: 128 for Q (tile-major: [tile][slab]), 256 for K/V ([slab]).
+__device__ __forceinline__ void load_rows(uint32_t base, const __nv_bfloat16* __restrict__ src, int ld, int tid,
+                                          int rows_per_tile) {
+  const uint32_t slab_bytes = static_cast<uint32_t>(rows_per_tile) * 128u;
+#pragma unroll 4
+  for (int c = tid; c < TQ * 12; c += 256) {
+    const int row = c / 12, ch = c - row * 12;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (ch < NCHUNK) v = ldg16(src + static_cast<size_t>(row) * ld + ch * 8);
+    const int tile = row / rows_per_tile, r = row - tile * rows_per_tile;
+    const int slab = ch >> 3, cs = ch & 7;
+    const uint32_t addr = base + static_cast<uint32_t>(tile * 2 + slab) * slab_bytes + static_cast<uint32_t>(r >> 3) * 1024u +
+                          static_cast<uint32_t>(r & 7) * 128u + (static_cast<uint32_t>(cs ^ (r & 7)) << 4);
+    sts16(addr, v);
+  }
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  float* kx = reinterpret_cast<float*>(smem + MISC_OFF);        // [96] key of token 256
+  float* vx = kx + 96;                                          // [96] value of token 256
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MISC_OFF + 1024);
+  uint64_t* bar_load = bars;       // count 256
+  uint64_t* bar_s = bars + 1;      // [2] count 1 (commit)
+  uint64_t* bar_p = bars + 3;      // [2] count 128
+  uint64_t* bar_o = bars + 5;      // [2] count 1 (commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
+  const int ldq = 3 * p.H * DH;
+  const __nv_bfloat16* qg = p.qkv + static_cast<size_t>(b) * T_TOK * ldq + h * DH;
+  const __nv_bfloat16* kg = qg + p.H * DH;
+  const __nv_bfloat16* vg = kg + p.H * DH;
+  __nv_bfloat16* og = p.out + static_cast<size_t>(b) * T_TOK * (p.H * DH) + h * DH;
+  const int ldo = p.H * DH;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_init(bar_load, 256);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bar_s[i], 1);
+        mbar_init(&bar_p[i], 128);
+        mbar_init(&bar_o[i], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<1>(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------------ load phase
+    const int tid = threadIdx.x;
+    load_rows(sbase + Q_OFF, qg, ldq, tid, 128);
+    load_rows(sbase + K_OFF, kg, ldq, tid, 256);
+    load_rows(sbase + V_OFF, vg, ldq, tid, 256);
+    if (tid < 96) {
+      kx[tid] = (tid < DH) ? __bfloat162float(kg[static_cast<size_t>(TQ) * ldq + tid]) : 0.f;
+    } else if (tid >= 128 && tid < 224) {
+      const int d = tid - 128;
+      vx[d] = (d < DH) ? __bfloat162float(vg[static_cast<size_t>(TQ) * ldq + d]) : 0.f;
+    }
+    fence_proxy_async_smem();
+    mbar_arrive(bar_load);
+    // all 256 threads must see kx/vx and the Q tile before the extra-key dot product
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+
+    const int g = warp >> 2;           // query tile
+    const int wq = warp & 3;           // TMEM lane quarter
+    const int r = wq * 32 + lane;      // row within the tile
+    // score against the extra key (token 256): s_x = q_row . k_x  (q is pre-scaled)
+    float s_x = 0.f;
+    {
+      const uint32_t qrow = sbase + Q_OFF + static_cast<uint32_t>(g * 2) * 16384u + static_cast<uint32_t>(r >> 3) * 1024u +
+                            static_cast<uint32_t>(r & 7) * 128u;
+#pragma unroll
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int slab = ch >> 3, cs = ch & 7;
+        const uint4 v = lds16(qrow + static_cast<uint32_t>(slab) * 16384u + (static_cast<uint32_t>(cs ^ (r & 7)) << 4));
+        const float* kk = kx + ch * 8;
+        s_x += bf_lo(v.x) * kk[0] + bf_hi(v.x) * kk[1] + bf_lo(v.y) * kk[2] + bf_hi(v.y) * kk[3] +
+               bf_lo(v.z) * kk[4] + bf_hi(v.z) * kk[5] + bf_lo(v.w) * kk[6] + bf_hi(v.w) * kk[7];
+      }
+    }
+    // Both S tiles must be complete (K and Q smem dead) and every thread done reading Q before P overwrites them.
+    mbar_wait(&bar_s[0], 0);
+    mbar_wait(&bar_s[1], 0);
+    tc_fence_after();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+
+    const uint32_t t_s = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(g * 256);
+    float m = s_x;
+    {
+      uint32_t v[32];
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        tmem_ld_32x32(t_s + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+      }
+    }
+    const float m2 = m * LOG2E;
+    float sum = 0.f;
+    const uint32_t prow = sbase + (g == 0 ? K_OFF : Q_OFF) + static_cast<uint32_t>(r >> 3) * 1024u +
+                          static_cast<uint32_t>(r & 7) * 128u;
+    {
+      uint32_t v[32];
+#pragma unroll 1
+      for (int c = 0; c < 8; ++c) {
+        tmem_ld_32x32(t_s + c * 32, v);
+        tmem_ld_wait();
+        float e[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          e[j] = exp2f(__uint_as_float(v[j]) * LOG2E - m2);
+          sum += e[j];
+        }
+        const uint32_t slab_addr = prow + static_cast<uint32_t>(c >> 1) * 16384u;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint4 q;
+          q.x = pack_bf16x2(e[8 * jj + 0], e[8 * jj + 1]);
+          q.y = pack_bf16x2(e[8 * jj + 2], e[8 * jj + 3]);
+          q.z = pack_bf16x2(e[8 * jj + 4], e[8 * jj + 5]);
+          q.w = pack_bf16x2(e[8 * jj + 6], e[8 * jj + 7]);
+          const int cs = (c & 1) * 4 + jj;
+          sts16(slab_addr + (static_cast<uint32_t>(cs ^ (r & 7)) << 4), q);
+        }
+      }
+    }
+    const float p_x = exp2f(s_x * LOG2E - m2);
+    sum += p_x;
+    const float inv = 1.0f / sum;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(&bar_p[g]);
+
+    // ------------------------------------------------------------------ output
+    mbar_wait(&bar_o[g], 0);
+    tc_fence_after();
+    __nv_bfloat16* orow = og + static_cast<size_t>(g * 128 + r) * ldo;
+    {
+      uint32_t v[32];
+#pragma unroll 1
+      for (int c = 0; c < 3; ++c) {
+        tmem_ld_32x32(t_s + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int d0 = c * 32 + jj * 8;
+          if (d0 < DH) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (__uint_as_float(v[jj * 8 + j]) + p_x * vx[d0 + j]) * inv;
+            uint4 q;
+            q.x = pack_bf16x2(o[0], o[1]);
+            q.y = pack_bf16x2(o[2], o[3]);
+            q.z = pack_bf16x2(o[4], o[5]);
+            q.w = pack_bf16x2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(orow + d0) = q;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issue
+    if (lane == 0) {
+      mbar_wait(bar_load, 0);
+      tc_fence_after();
+      const uint32_t idesc_s = umma_idesc_bf16(128, 256);
+      for (int g = 0; g < 2; ++g) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int slab = k >> 2, kk = k & 3;
+          const uint64_t ad = umma_desc_sw128(sbase + Q_OFF + static_cast<uint32_t>(g * 2 + slab) * 16384u + kk * 32);
+          const uint64_t bd = umma_desc_sw128(sbase + K_OFF + static_cast<uint32_t>(slab) * 32768u + kk * 32);
+          umma_bf16<1>(tmem_base + g * 256, ad, bd, idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit<1>(&bar_s[g]);
+      }
+      const uint32_t idesc_o = umma_idesc_bf16(128, 96) | (1u << 16);  // B operand MN-major
+      for (int g = 0; g < 2; ++g) {
+        mbar_wait(&bar_p[g], 0);
+        tc_fence_after();
+        const uint32_t pbase = sbase + (g == 0 ? K_OFF : Q_OFF);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const uint64_t ad = umma_desc_sw128(pbase + static_cast<uint32_t>(k >> 2) * 16384u + (k & 3) * 32);
+          const uint64_t bd = umma_desc_sw128_mn(sbase + V_OFF + static_cast<uint32_t>(k) * 2048u, 32768u);
+          umma_bf16<1>(tmem_base + g * 256, ad, bd, idesc_o, k > 0 ? 1u : 0u);
+        }
+        umma_commit<1>(&bar_o[g]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ query row 256 on CUDA cores
+    // lanes over keys for q.k, then lanes over d for p.v; K/V are read from global (L2-resident).
+    float q[DH];
+    {
+      const __nv_bfloat16* qx = qg + static_cast<size_t>(TQ) * ldq;
+#pragma unroll
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        const uint4 v = ldg16(qx + ch * 8);
+        q[ch * 8 + 0] = bf_lo(v.x); q[ch * 8 + 1] = bf_hi(v.x);
+        q[ch * 8 + 2] = bf_lo(v.y); q[ch * 8 + 3] = bf_hi(v.y);
+        q[ch * 8 + 4] = bf_lo(v.z); q[ch * 8 + 5] = bf_hi(v.z);
+        q[ch * 8 + 6] = bf_lo(v.w); q[ch * 8 + 7] = bf_hi(v.w);
+      }
+    }
+    float s[9];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int key = i * 32 + lane;
+      float acc = -INFINITY;
+      if (key < T_TOK) {
+        acc = 0.f;
+        const __nv_bfloat16* kr = kg + static_cast<size_t>(key) * ldq;
+#pragma unroll
+        for (int ch = 0; ch < NCHUNK; ++ch) {
+          const uint4 v = ldg16(kr + ch * 8);
+          acc += q[ch * 8 + 0] * bf_lo(v.x) + q[ch * 8 + 1] * bf_hi(v.x) + q[ch * 8 + 2] * bf_lo(v.y) +
+                 q[ch * 8 + 3] * bf_hi(v.y) + q[ch * 8 + 4] * bf_lo(v.z) + q[ch * 8 + 5] * bf_hi(v.z) +
+                 q[ch * 8 + 6] * bf_lo(v.w) + q[ch * 8 + 7] * bf_hi(v.w);
+        }
+      }
+      s[i] = acc;
+      m = fmaxf(m, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      s[i] = exp2f((s[i] - m) * LOG2E);  // exp2f(-inf) = 0 for padded keys
+      sum += s[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+    const bool has2 = (lane + 64) < DH;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const int nk = (i < 8) ? 32 : (T_TOK - 256);
+#pragma unroll 8
+      for (int j = 0; j < nk; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, s[i], j);
+        const __nv_bfloat16* vr = vg + static_cast<size_t>(i * 32 + j) * ldq;
+        o0 += pj * __bfloat162float(vr[lane]);
+        o1 += pj * __bfloat162float(vr[lane + 32]);
+        if (has2) o2 += pj * __bfloat162float(vr[lane + 64]);
+      }
+    }
+    __nv_bfloat16* orow = og + static_cast<size_t>(TQ) * ldo;
+    orow[lane] = __float2bfloat16(o0 * inv);
+    orow[lane + 32] = __float2bfloat16(o1 * inv);
+    if (has2) orow[lane + 64] = __float2bfloat16(o2 * inv);
+  }
+
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 8) tmem_dealloc<1>(tmem_base, 512);
+}
+
+}  // namespace
+
+int vit_attn_launch(const AttnParams& p, cudaStream_t stream) {
+  if (p.B <= 0 || p.H <= 0) return -3;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(vit_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  vit_attn_kernel<<<p.B * p.H, ATT_THREADS, ATT_SMEM, stream>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace hb

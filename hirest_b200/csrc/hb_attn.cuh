@@ -1,0 +1,40 @@
+// hb_attn.cuh — attention kernels (implementation in hb_attn.cu / hb_attn_small.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace hb {
+
+// EVA ViT-g/14 attention (EVA_clip/vit_model.py:127-147): 257 tokens, head_dim 88.
+// qkv: bf16 [B*257, 3*H*88] with feature index = which*H*88 + head*88 + d (vit_model.py:127), q pre-scaled.
+// out: bf16 [B*257, H*88]  (== (attn @ v).transpose(1,2).reshape(B,N,C), vit_model.py:147).
+struct AttnParams {
+  const __nv_bfloat16* qkv = nullptr;
+  __nv_bfloat16* out = nullptr;
+  int B = 0;
+  int H = 0;
+};
+int vit_attn_launch(const AttnParams& p, cudaStream_t stream);
+
+// Generic small-sequence attention on CUDA cores (text tower, MomentModel encoder, caption decoder):
+//   q: bf16 [B, Tq, ldq] (+ head*64), k/v: bf16 [B, Tk, ldk], head_dim 64, scores = q.k * scale
+//   mask_mode 0: none; 1: causal (key > query masked with -inf, EVA_clip/eva_model.py:224-230);
+//   2: additive constant `mask_const` on every logit, then causal -10000 if causal_soft != 0
+//      (clip4caption/modules/module_visual.py:406-414, module_decoder.py:385-396).
+struct SmallAttnParams {
+  const __nv_bfloat16* q = nullptr;
+  const __nv_bfloat16* k = nullptr;
+  const __nv_bfloat16* v = nullptr;
+  __nv_bfloat16* out = nullptr;  // [B, Tq, ldo] (+ head*64)
+  int B = 0, H = 0, Tq = 0, Tk = 0;
+  int ldq = 0, ldk = 0, ldv = 0, ldo = 0;  // row strides in elements
+  long long bsq = 0, bsk = 0, bsv = 0, bso = 0;  // batch strides in elements
+  float scale = 1.f;
+  int mask_mode = 0;
+  float mask_const = 0.f;
+  int causal_soft = 0;
+};
+int small_attn_launch(const SmallAttnParams& p, cudaStream_t stream);
+
+}  // namespace hb

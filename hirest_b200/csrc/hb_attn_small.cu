@@ -1,0 +1,135 @@
+// hb_attn_small.cu — head_dim-64 attention for the small sequence models on the hot path:
+//   * EVA-CLIP text tower, causal, 77 tokens            (EVA_clip/eva_model.py:132,146,224-230)
+//   * MomentModel temporal encoder, T ~ 300 frames       (clip4caption/modules/module_visual.py:154-180)
+//   * caption decoder self / cross attention             (clip4caption/modules/module_decoder.py:220-247)
+// One CTA per (batch, head); K and V of that head live in shared memory, one warp per query row,
+// lanes over keys for q.k and over d for p.v.  These models are launch/latency bound, so
+// this kernel is CUDA-core work; the 97 % of FLOPs that matter go through hb_gemm.cu / hb_attn.cu.
+#include "hb_attn.cuh"
+
+#include <cmath>
+
+namespace hb {
+namespace {
+
+constexpr int DH = 64;
+constexpr int K_STRIDE = 144;   // bytes per K row in smem (128 + 16 pad -> conflict-free 16-byte reads)
+constexpr int V_STRIDE = 128;   // bytes per V row
+constexpr int MAX_TK = 768;
+constexpr int MAXJ = MAX_TK / 32;
+constexpr int SA_THREADS = 256;
+
+__device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+__global__ void __launch_bounds__(SA_THREADS) small_attn_kernel(const SmallAttnParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* sk = smem;
+  uint8_t* sv = smem + static_cast<size_t>(p.Tk) * K_STRIDE;
+  const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __nv_bfloat16* qg = p.q + b * p.bsq + h * DH;
+  const __nv_bfloat16* kg = p.k + b * p.bsk + h * DH;
+  const __nv_bfloat16* vg = p.v + b * p.bsv + h * DH;
+  __nv_bfloat16* og = p.out + b * p.bso + h * DH;
+
+  // stage K and V (8 x 16-byte chunks per row)
+  for (int c = threadIdx.x; c < p.Tk * 8; c += SA_THREADS) {
+    const int row = c >> 3, ch = c & 7;
+    const uint4 kv = __ldg(reinterpret_cast<const uint4*>(kg + static_cast<size_t>(row) * p.ldk + ch * 8));
+    const uint4 vv = __ldg(reinterpret_cast<const uint4*>(vg + static_cast<size_t>(row) * p.ldv + ch * 8));
+    *reinterpret_cast<uint4*>(sk + row * K_STRIDE + ch * 16) = kv;
+    *reinterpret_cast<uint4*>(sv + row * V_STRIDE + ch * 16) = vv;
+  }
+  __syncthreads();
+
+  for (int i = warp; i < p.Tq; i += SA_THREADS / 32) {
+    float q[DH];
+    {
+      const uint4* q4 = reinterpret_cast<const uint4*>(qg + static_cast<size_t>(i) * p.ldq);
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint4 v = __ldg(q4 + ch);
+        q[ch * 8 + 0] = bf_lo(v.x); q[ch * 8 + 1] = bf_hi(v.x);
+        q[ch * 8 + 2] = bf_lo(v.y); q[ch * 8 + 3] = bf_hi(v.y);
+        q[ch * 8 + 4] = bf_lo(v.z); q[ch * 8 + 5] = bf_hi(v.z);
+        q[ch * 8 + 6] = bf_lo(v.w); q[ch * 8 + 7] = bf_hi(v.w);
+      }
+    }
+    const int tk_eff = (p.mask_mode == 1) ? min(p.Tk, i + 1) : p.Tk;  // hard causal: keys <= query only
+    float s[MAXJ];
+    float m = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < MAXJ; ++jj) {
+      s[jj] = -INFINITY;
+      if (jj * 32 < tk_eff) {
+        const int key = jj * 32 + lane;
+        if (key < tk_eff) {
+          const uint8_t* kr = sk + key * K_STRIDE;
+          float acc = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint4 v = *reinterpret_cast<const uint4*>(kr + ch * 16);
+            acc += q[ch * 8 + 0] * bf_lo(v.x) + q[ch * 8 + 1] * bf_hi(v.x) + q[ch * 8 + 2] * bf_lo(v.y) +
+                   q[ch * 8 + 3] * bf_hi(v.y) + q[ch * 8 + 4] * bf_lo(v.z) + q[ch * 8 + 5] * bf_hi(v.z) +
+                   q[ch * 8 + 6] * bf_lo(v.w) + q[ch * 8 + 7] * bf_hi(v.w);
+          }
+          acc *= p.scale;
+          if (p.mask_mode == 2) {
+            acc = acc + p.mask_const;                       // fp32 add, as the reference does (quantises the logit)
+            if (p.causal_soft && key > i) acc = acc + (-10000.0f);
+          }
+          s[jj] = acc;
+          m = fmaxf(m, acc);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < MAXJ; ++jj) {
+      if (jj * 32 < tk_eff) {
+        s[jj] = __expf(s[jj] - m);  // exp(-inf) = 0 for keys past tk_eff
+        sum += s[jj];
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < MAXJ; ++jj) {
+      if (jj * 32 < tk_eff) {
+        const int nk = min(32, tk_eff - jj * 32);
+        for (int j = 0; j < nk; ++j) {
+          const float pj = __shfl_sync(0xffffffffu, s[jj], j);
+          const uint32_t vv = *reinterpret_cast<const uint32_t*>(sv + (jj * 32 + j) * V_STRIDE + lane * 4);
+          o0 += pj * bf_lo(vv);
+          o1 += pj * bf_hi(vv);
+        }
+      }
+    }
+    __nv_bfloat162 r = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+    *reinterpret_cast<__nv_bfloat162*>(og + static_cast<size_t>(i) * p.ldo + lane * 2) = r;
+  }
+}
+
+}  // namespace
+
+int small_attn_launch(const SmallAttnParams& p, cudaStream_t stream) {
+  if (p.B <= 0 || p.H <= 0 || p.Tq <= 0 || p.Tk <= 0) return -3;
+  if (p.Tk > MAX_TK) return -6;
+  const size_t smem = static_cast<size_t>(p.Tk) * (K_STRIDE + V_STRIDE);
+  static size_t attr_set = 0;
+  if (smem > 48 * 1024 && smem > attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(small_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         MAX_TK * (K_STRIDE + V_STRIDE));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = MAX_TK * (K_STRIDE + V_STRIDE);
+  }
+  small_attn_kernel<<<p.B * p.H, SA_THREADS, smem, stream>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace hb

@@ -1,0 +1,30 @@
+// hb_elem.cuh — HBM-bound row kernels (implementation in hb_elem.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace hb {
+
+struct LayerNormParams {
+  const float* x = nullptr;      // fp32 rows, leading dim ldx
+  long long ldx = 0;
+  const int* row_idx = nullptr;  // optional gather: output row r reads input row row_idx[r]
+  void* y = nullptr;             // bf16 or fp32 rows, leading dim ldy
+  long long ldy = 0;
+  const float* w = nullptr;
+  const float* b = nullptr;
+  float eps = 1e-5f;
+  int rows = 0;
+  int D = 0;
+};
+int layernorm_launch(const LayerNormParams& p, bool out_bf16, cudaStream_t s);
+int im2col_patch_launch(const float* img, __nv_bfloat16* out, int B, int S, int P, int ldo, cudaStream_t s);
+int cls_row_launch(float* x, const float* cls, const float* pos, int B, int T, int D, cudaStream_t s);
+int text_embed_launch(const long long* ids, const float* tok, const float* pos, float* x, int* eot_row, int Q, int C, int W,
+                      int V, cudaStream_t s);
+int pool_normalize_launch(const float* emb, void* out, long long V, int F, int E, bool normalize, bool out_bf16,
+                          cudaStream_t s);
+int split_bf16_launch(const float* x, __nv_bfloat16* out, long long rows, int E, int mode, cudaStream_t s);
+int f32_to_bf16_launch(const float* x, __nv_bfloat16* y, long long n, cudaStream_t s);
+
+}  // namespace hb

@@ -1,0 +1,154 @@
+/* hirest_b200.h — C ABI of libhirest_b200.so (B200 / sm_100a only).
+ *
+ * The reference (j-min/HiREST) has no FFI layer: its hot path is reached through Python methods.  This
+ * header is the boundary a maintainer binds underneath those methods (ctypes stub in INTEGRATION.md):
+ *
+ *   EVA_CLIP.encode_image   EVA_clip/eva_model.py:317-318 -> vit_model.py:326-351   => hb_vit_encode
+ *   EVA_CLIP.encode_text    EVA_clip/eva_model.py:320-321 -> :232-250               => hb_text_encode
+ *   mean-pool + L2 norm     inference_video_retrieval.py:210-212, 283-285, 323-326  => hb_pool_normalize
+ *   T @ V.T scoring         inference_video_retrieval.py:334                        => hb_similarity
+ *   nn.Linear / F.linear    (any site listed in SURVEY.md §8(a))                    => hb_linear
+ *
+ * Conventions: every function returns 0 on success or a negative code (hb_strerror); nothing throws across
+ * the ABI.  All data pointers are DEVICE pointers owned by the caller (e.g. torch tensors' data_ptr());
+ * `stream` is a cudaStream_t passed as void*.  Handles own only repacked bf16 weights + workspace.  No hidden
+ * synchronisation: results are ready when `stream` reaches the call's last kernel.  A handle is not
+ * thread-safe; use one handle per stream / rank (one process per GPU, as run.py:846-856 does).
+ */
+#ifndef HIREST_B200_H_
+#define HIREST_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define HB_API __attribute__((visibility("default")))
+#else
+#define HB_API
+#endif
+
+#define HB_OK 0
+#define HB_ERR_INVALID (-22)   /* bad argument / unsupported shape */
+#define HB_ERR_NOMEM (-12)     /* cudaMalloc failed */
+#define HB_ERR_CUDA (-5)       /* CUDA runtime / driver error, see hb_last_error() */
+#define HB_ERR_NODEVICE (-19)  /* no sm_100 device */
+
+/* ---- library ------------------------------------------------------------------------------- */
+/* Binds the calling thread to `device`, checks it is compute capability 10.x, resolves the driver
+ * entry points.  Must be called once per process before anything else. */
+HB_API int hb_init(int device);
+HB_API const char* hb_last_error(void);
+HB_API const char* hb_strerror(int code);
+/* Number of kernels launched by this library since process start (bench.py's gpu_launches). */
+HB_API int64_t hb_launch_count(void);
+/* cta_group used by the GEMMs: 2 (CTA pairs, default) or 1. */
+HB_API int hb_set_gemm_cta_group(int cg);
+
+/* ---- EVA ViT frame encoder (EVA_clip/vit_model.py) -------------------------------------------- */
+typedef struct {
+  int image_size;   /* 224 */
+  int patch_size;   /* 14  */
+  int width;        /* 1408 */
+  int layers;       /* 40  */
+  int heads;        /* 16 (head_dim must be 88) */
+  int mlp_hidden;   /* 6144 = int(width * 4.3637) */
+  int embed_dim;    /* 1024 */
+  float ln_eps;     /* 1e-6 (eva_model.py:304) */
+} HbVitConfig;
+
+/* fp32 device pointers in the reference state_dict layout.  Per-layer members are
+ * HOST arrays of `layers` device pointers.  Borrowed only during hb_vit_create (weights are repacked). */
+typedef struct {
+  const float* cls_token;      /* [1,1,D] */
+  const float* pos_embed;      /* [1,T,D] */
+  const float* patch_w;        /* patch_embed.proj.weight [D,3,P,P] */
+  const float* patch_b;        /* [D] */
+  const float* const* norm1_w; const float* const* norm1_b;
+  const float* const* q_bias;  const float* const* v_bias;   /* attn.q_bias / attn.v_bias [D] */
+  const float* const* qkv_w;   /* attn.qkv.weight [3D, D] */
+  const float* const* proj_w;  const float* const* proj_b;
+  const float* const* norm2_w; const float* const* norm2_b;
+  const float* const* fc1_w;   const float* const* fc1_b;    /* [F,D], [F] */
+  const float* const* fc2_w;   const float* const* fc2_b;    /* [D,F], [D] */
+  const float* norm_w; const float* norm_b;                  /* final norm */
+  const float* head_w; const float* head_b;                  /* [E,D], [E] */
+} HbVitWeights;
+
+typedef struct HbVit HbVit;
+HB_API int hb_vit_create(const HbVitConfig* cfg, const HbVitWeights* w, int max_batch, void* stream, HbVit** out);
+/* frames: fp32 [B,3,S,S] NCHW; out: fp32 [B, embed_dim] (un-normalised, like encode_image). */
+HB_API int hb_vit_encode(HbVit* m, const float* frames, int64_t B, float* out, void* stream);
+/* Debug / parity taps: copy the fp32 residual stream [B*T, D] after `layer` blocks (0 = after patch embed)
+ * of the most recent chunk into `dst`.  Must be requested before encode via hb_vit_set_tap(layer, dst). */
+HB_API int hb_vit_set_tap(HbVit* m, int layer, float* dst);
+HB_API void hb_vit_destroy(HbVit* m);
+
+/* ---- EVA-CLIP text tower (EVA_clip/eva_model.py:177-250) -------------------------------------- */
+typedef struct {
+  int context_length; /* 77 */
+  int vocab_size;     /* 49408 */
+  int width;          /* 768 */
+  int heads;          /* 12 (head_dim must be 64) */
+  int layers;         /* 12 */
+  int embed_dim;      /* 1024 */
+  float ln_eps;       /* 1e-5 */
+} HbTextConfig;
+
+typedef struct {
+  const float* token_embedding;       /* [V, W] */
+  const float* positional_embedding;  /* [C, W] */
+  const float* const* ln1_w; const float* const* ln1_b;
+  const float* const* in_proj_w;      /* attn.in_proj_weight [3W, W] */
+  const float* const* in_proj_b;      /* [3W] */
+  const float* const* out_proj_w; const float* const* out_proj_b;
+  const float* const* ln2_w; const float* const* ln2_b;
+  const float* const* fc_w;  const float* const* fc_b;      /* mlp.c_fc   [4W, W] */
+  const float* const* cproj_w; const float* const* cproj_b; /* mlp.c_proj [W, 4W] */
+  const float* ln_final_w; const float* ln_final_b;
+  const float* text_projection;       /* [W, E] */
+} HbTextWeights;
+
+typedef struct HbText HbText;
+HB_API int hb_text_create(const HbTextConfig* cfg, const HbTextWeights* w, int max_batch, void* stream, HbText** out);
+/* ids: int64 [Q, context_length]; out: fp32 [Q, embed_dim] (un-normalised, like encode_text). */
+HB_API int hb_text_encode(HbText* m, const int64_t* ids, int64_t Q, float* out, void* stream);
+HB_API void hb_text_destroy(HbText* m);
+
+/* ---- retrieval scoring ------------------------------------------------------------------------ */
+/* out[v,:] = l2norm(mean_f emb[v,f,:]); emb fp32 [V,F,E]; out fp32 [V,E].  F = 1 gives plain L2 normalise. */
+HB_API int hb_pool_normalize(const float* emb, int64_t V, int F, int E, float* out, void* stream);
+/* scores[q,v] = <text[q,:], video[v,:]>; text fp32 [Q,E], video fp32 [V,E], scores fp32 [Q, ld_scores].
+ * exact != 0: split-bf16 (hi/lo) GEMM, ~fp32 accuracy (for bit-stable top-k); exact == 0: single bf16 GEMM. */
+HB_API int hb_similarity(const float* text, int64_t Q, const float* video, int64_t V, int E, float* scores,
+                  int64_t ld_scores, int exact, void* stream);
+
+/* ---- generic fused linear (tcgen05 GEMM) ------------------------------------------------------ */
+#define HB_EPI_BF16 0       /* out bf16 = x W^T + b                      */
+#define HB_EPI_GELU_BF16 1  /* out bf16 = gelu_erf(x W^T + b)            */
+#define HB_EPI_F32 2        /* out f32  = x W^T + b (+ resid)            */
+/* x: bf16 [M, ldx]; w: bf16 [N, ldw] (K contiguous, nn.Linear layout); bias fp32 [N] or NULL;
+ * resid fp32 [M, ldo] or NULL (HB_EPI_F32 only, may alias out).  K % 8 == 0, N % 16 == 0, 16-byte aligned. */
+HB_API int hb_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, const float* resid,
+              void* out, int64_t ldo, int64_t M, int64_t N, int64_t K, int epilogue, void* stream);
+
+/* LayerNorm over the last dim: x fp32 [rows, D] -> y (bf16 if out_bf16 else fp32) [rows, D]. */
+HB_API int hb_layernorm(const float* x, const float* w, const float* b, float eps, int64_t rows, int D, void* y, int out_bf16,
+                 void* stream);
+
+/* ViT attention (vit_model.py:127-147): qkv bf16 [B*257, 3*H*88] (q pre-scaled) -> out bf16 [B*257, H*88]. */
+HB_API int hb_vit_attention(const void* qkv, void* out, int64_t B, int H, void* stream);
+
+/* head_dim-64 attention (text tower / MomentModel / decoder), see hb_attn.cuh SmallAttnParams.
+ * q [B,Tq,*], k/v [B,Tk,*] bf16 with row strides ld* and batch strides bs* (elements); mask_mode 0 none,
+ * 1 causal (-inf), 2 additive constant (+ soft causal -10000 if causal_soft). */
+HB_API int hb_small_attention(const void* q, const void* k, const void* v, void* out, int B, int H, int Tq, int Tk, int ldq,
+                       int ldk, int ldv, int ldo, int64_t bsq, int64_t bsk, int64_t bsv, int64_t bso, float scale,
+                       int mask_mode, float mask_const, int causal_soft, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIREST_B200_H_ */
