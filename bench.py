@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — frames/sec encoded+scored (EVA-CLIP-g/14, 224 px) on N B200s of one node.
+
+A "step" is one pass of the hot path over one batch of synthetic input per rank:
+  encode_image on 1024 frames (32 videos x 32 frames, BASELINE.json configs[1]) -> per-video mean-pool + L2 norm ->
+  [N > 1: one NCCL all-gather of the normalised video embeddings] -> cosine scores against 512 text queries
+  (4 of them re-encoded by the text tower each step: BASELINE configs[2]'s 512 queries : 131072 frames ratio).
+
+`value`  : whole-job frames/s, inputs already resident in HBM, CUDA-event timed, max over ranks.
+`e2e`    : same metric through the public Python API with HOST (pinned) buffers — H2D of the frames and D2H of the
+           score matrix inside the timed region.
+`roofline`: aggregate of this library's tcgen05 GEMM launches (97 % of the FLOPs), per-launch CUDA events.
+`cpu_baseline`: the CPU oracle port (oracle/eva_oracle.py, torch fp32) on the box's host cores, bounded sample.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec encoded+scored (EVA-CLIP-g/14 224px)"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=1024, help="frames per rank per step")
+    ap.add_argument("--frames-per-video", type=int, default=32)
+    ap.add_argument("--queries", type=int, default=512)
+    ap.add_argument("--cpu-frames", type=int, default=8, help="frames in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tiny", action="store_true", help="debug: tiny config instead of EVA-CLIP-g/14")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_tflops": p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1590.0)), "hbm_gbs": p.get("hbm_gbs", 6650.0),
+                "source": "measured (MEASURED_PEAKS.json, sustained cuBLAS bf16)"}
+    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md, sustained)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm_sorted = sorted(sm)
+        return {"sm_mhz": sm_sorted[len(sm_sorted) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(cfg, n_frames, steps, warmup, frames_per_video, n_queries):
+    """Times the CPU oracle port of the path (torch fp32, all host threads) on `n_frames` frames per step."""
+    import torch
+    from hirest_b200 import synthetic
+    from oracle import eva_oracle
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = synthetic.make_eva_state_dict(cfg, seed=0)
+    frames = synthetic.make_frames(n_frames, cfg["vision_cfg"]["image_size"], seed=1)
+    fpv = min(frames_per_video, n_frames)
+    text_hat = torch.nn.functional.normalize(torch.randn(n_queries, cfg["embed_dim"]), dim=-1)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            emb = eva_oracle.encode_image(sd, frames, cfg)
+            v_hat = eva_oracle.pool_normalize_video(emb[: (n_frames // fpv) * fpv], fpv)
+            _ = eva_oracle.similarity(text_hat, v_hat)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    total = sum(times)
+    return {"frames_per_s": n_frames * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": threads,
+            "sample": f"{n_frames} frames/step x {len(times)} steps (+{warmup} warm-up), encode_image + pool + scores, torch fp32 CPU"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import torch
+    from hirest_b200 import synthetic
+
+    cfg = synthetic.EVA_TINY if args.tiny else synthetic.EVA_G14
+    model_name = "EVA-TINY(debug)" if args.tiny else "EVA-CLIP-g/14"
+
+    # ------------------------------------------------------------------ reference arm: CPU oracle port
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        warm = args.warmup
+        r = cpu_reference_run(cfg, args.cpu_frames, args.steps, warm, args.frames_per_video, args.queries)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": r["frames_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{model_name} frame encoder + retrieval scoring; CPU sample of {args.cpu_frames} frames/step",
+                       "frames_per_step": args.cpu_frames, "frames_per_video": args.frames_per_video, "queries": args.queries},
+            "cpu_baseline": {"value": r["frames_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["frames_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ B200 arm
+    import torch.distributed as dist
+    from hirest_b200 import _lib, eva_clip, retrieval
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200 (no CPU fallback); use --impl reference for the CPU oracle timing")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.init(local_rank)
+
+    sd = synthetic.make_eva_state_dict(cfg, seed=0, device=dev)
+    model = eva_clip.EVA_CLIP(**cfg, max_image_batch=args.frames, max_text_batch=max(args.queries, 8))
+    model.load_state_dict(sd, strict=True)
+    del sd
+    model = model.to(dev).eval()
+
+    S = cfg["vision_cfg"]["image_size"]
+    B, Fv, Q, E = args.frames, args.frames_per_video, args.queries, cfg["embed_dim"]
+    assert B % Fv == 0
+    new_q = max(1, round(Q * B / (4096 * 32)))  # queries re-encoded per step, keeping cfg3's 512 : 131072 ratio
+    frames_dev = synthetic.make_frames(B, S, seed=100 + rank, device=dev)
+    tokens_all = synthetic.make_tokens(Q, cfg, seed=2).to(dev)
+    with torch.no_grad():
+        text_hat = retrieval.normalize(model.encode_text(tokens_all))
+    tokens_step = tokens_all[:new_q].contiguous()
+
+    def step_device():
+        t_new = retrieval.normalize(model.encode_text(tokens_step))
+        text_hat[:new_q].copy_(t_new)
+        scores, _ = retrieval.encode_and_score(model, frames_dev, Fv, text_hat, exact=True)
+        return scores
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step_device()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = lib.hb_launch_count()
+        lib.hb_profile_start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            scores = step_device()
+        e1.record()
+        barrier()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        prof = _lib.HbProfileSummary()
+        _lib.check(lib.hb_profile_stop(prof), "hb_profile_stop")
+        launches = lib.hb_launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        value = world * B * args.steps / (ms_total * 1e-3)
+
+        # ---------------- e2e through the public API with host buffers
+        e2e = None
+        if not args.no_e2e:
+            frames_host = torch.empty((B, 3, S, S), dtype=torch.float32).pin_memory()
+            frames_host.copy_(frames_dev)
+            tokens_host = tokens_step.cpu().pin_memory()
+            scores_host = torch.empty((Q, world * (B // Fv)), dtype=torch.float32).pin_memory()
+
+            def step_e2e():
+                f = frames_host.to(dev, non_blocking=True)
+                tk = tokens_host.to(dev, non_blocking=True)
+                t_new = retrieval.normalize(model.encode_text(tk))
+                text_hat[:new_q].copy_(t_new)
+                sc, _ = retrieval.encode_and_score(model, f, Fv, text_hat, exact=True)
+                scores_host.copy_(sc, non_blocking=True)
+                torch.cuda.current_stream().synchronize()  # the caller holds the scores on the host after every step
+                return scores_host
+
+            for _ in range(max(1, min(args.warmup, 2))):
+                step_e2e()
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                step_e2e()
+            e1.record()
+            barrier()
+            ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+            e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_step": frames_host.numel() * 4 + tokens_host.numel() * 8,
+                   "d2h_bytes_per_step": scores_host.numel() * 4, "ms_per_step": ms_e2e / args.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = load_peaks()
+    cats = _lib.PROF_CATEGORIES
+    per = {c: {"ms_per_step": prof.ms[i] / args.steps, "launches_per_step": prof.launches[i] / args.steps,
+               "tflops": (prof.flops[i] / (prof.ms[i] * 1e-3) / 1e12) if prof.ms[i] > 0 and prof.flops[i] > 0 else None}
+           for i, c in enumerate(cats)}
+    gemm_ms = sum(prof.ms[i] for i in range(3))
+    gemm_flops = sum(prof.flops[i] for i in range(3))
+    gemm_launches = sum(prof.launches[i] for i in range(3))
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    kernel_ms_total = sum(prof.ms[i] for i in range(len(cats)))
+    flops_frame = synthetic.encode_image_flops(cfg)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{model_name} frame encoder, {B}-frame batch per GPU ({B // Fv} videos x {Fv} frames) + mean-pool/L2-norm"
+                               f" + {'NCCL all-gather + ' if world > 1 else ''}cosine scores vs {Q} text queries ({new_q} re-encoded per step)",
+                   "frames_per_gpu_per_step": B, "frames_per_video": Fv, "queries": Q, "weights": "seeded random init (synthetic.py)",
+                   "residual_stream": "fp32", "gemm_operands": "bf16, fp32 accumulate", "l2": "inputs_larger_than_l2",
+                   "parallelism": f"frame-shard dp{world}" if world > 1 else "single GPU"},
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                     "kernel": "hb::gemm_kernel<CG=2,*> (all tcgen05 GEMM launches)", "launches_per_step": gemm_launches / args.steps,
+                     "gemm_share_of_kernel_time": gemm_ms / kernel_ms_total if kernel_ms_total else None,
+                     "whole_step_tflops": flops_frame * B / (ms_total / args.steps * 1e-3) / 1e12,
+                     "whole_step_frac": flops_frame * B / (ms_total / args.steps * 1e-3) / 1e12 / peaks["bf16_tflops"]},
+        "kernels": per,
+        "e2e": e2e,
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(cfg, args.cpu_frames, 2, 1, Fv, Q)
+        line["cpu_baseline"] = {"value": r["frames_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -45,6 +45,12 @@ class HbTextWeights(C.Structure):
                 ("ln_final_b", C.c_void_p), ("text_projection", C.c_void_p)]
 
 
+class HbProfileSummary(C.Structure):
+    _fields_ = [("ms", C.c_double * 6), ("flops", C.c_double * 6), ("launches", C.c_int64 * 6)]
+
+
+PROF_CATEGORIES = ("gemm_bf16", "gemm_gelu", "gemm_f32", "vit_attention", "layernorm", "other")
+
 # name -> (restype, argtypes); must list every symbol include/hirest_b200.h declares (tests check this).
 SIGNATURES = {
     "hb_init": (C.c_int, [C.c_int]),
@@ -52,6 +58,8 @@ SIGNATURES = {
     "hb_strerror": (C.c_char_p, [C.c_int]),
     "hb_launch_count": (C.c_int64, []),
     "hb_set_gemm_cta_group": (C.c_int, [C.c_int]),
+    "hb_profile_start": (C.c_int, []),
+    "hb_profile_stop": (C.c_int, [C.POINTER(HbProfileSummary)]),
     "hb_vit_create": (C.c_int, [C.POINTER(HbVitConfig), C.POINTER(HbVitWeights), C.c_int, C.c_void_p,
                                 C.POINTER(C.c_void_p)]),
     "hb_vit_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),

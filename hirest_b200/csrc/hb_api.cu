@@ -49,6 +49,25 @@ int fail(int code, const char* fmt, ...) {
     g_launches.fetch_add(1, std::memory_order_relaxed);                                              \
   } while (0)
 
+// ---- optional per-launch timing (bench.py roofline): CUDA events around every launch, on its own stream ----
+enum ProfCat { CAT_GEMM_BF16 = 0, CAT_GEMM_GELU = 1, CAT_GEMM_F32 = 2, CAT_VIT_ATTN = 3, CAT_LAYERNORM = 4, CAT_OTHER = 5, CAT_COUNT = 6 };
+struct ProfRec { cudaEvent_t e0, e1; int cat; double flops; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t prof_event() {
+  if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ProfScope {
+  bool on; ProfRec rec; cudaStream_t s;
+  ProfScope(int cat, double flops, cudaStream_t s_) : on(g_prof_on), s(s_) {
+    if (on) { rec.cat = cat; rec.flops = flops; rec.e0 = prof_event(); rec.e1 = prof_event(); cudaEventRecord(rec.e0, s); }
+  }
+  ~ProfScope() { if (on) { cudaEventRecord(rec.e1, s); g_prof.push_back(rec); } }
+};
+#define HB_LAUNCH_P(cat, flops, stream, x) do { ProfScope ps_((cat), (flops), (stream)); HB_LAUNCH(x); } while (0)
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -87,7 +106,7 @@ struct Linear {
   // bias may be assembled from up to three pieces (q_bias | zeros | v_bias), each of length N/3.
   int init(const float* w_src, int N_, int K_, const float* bias, bool transposed, cudaStream_t s, const float* bias_q = nullptr,
            const float* bias_v = nullptr) {
-    N = N_; K = K_; cg = g_cg;
+    N = N_; K = K_; cg = (N_ % 32 == 0) ? g_cg : 1;  // CTA pairs need N % 32 == 0
     Kpad = (K + 7) / 8 * 8;
     if (int r = w.alloc(static_cast<size_t>(N) * Kpad * 2)) return r;
     const long long total = static_cast<long long>(N) * Kpad;
@@ -147,7 +166,8 @@ int run_gemm(const CUtensorMap& tmA, const Linear& L, long long M, void* out, in
   p.bias = L.bias(); p.out = out; p.ldo = ldo; p.resid = resid;
   p.qscale = qscale; p.qcols = qcols;
   p.rowadd = rowadd; p.remap_in = remap_in; p.remap_out = remap_out; p.remap_off = remap_off;
-  HB_LAUNCH(hb::gemm_launch(tmA, L.tm, p, epi, L.cg, g_num_sms, s));
+  HB_LAUNCH_P(epi == hb::EPI_BF16 ? CAT_GEMM_BF16 : (epi == hb::EPI_GELU_BF16 ? CAT_GEMM_GELU : CAT_GEMM_F32),
+              2.0 * static_cast<double>(M) * L.N * L.K, s, hb::gemm_launch(tmA, L.tm, p, epi, L.cg, g_num_sms, s));
   return 0;
 }
 
@@ -208,6 +228,32 @@ int64_t hb_launch_count(void) { return g_launches.load(); }
 int hb_set_gemm_cta_group(int cg) {
   if (cg != 1 && cg != 2) return fail(HB_ERR_INVALID, "cta group must be 1 or 2");
   g_cg = cg;
+  return HB_OK;
+}
+
+int hb_profile_start(void) {
+  for (auto& r : g_prof) { g_event_pool.push_back(r.e0); g_event_pool.push_back(r.e1); }
+  g_prof.clear();
+  g_prof_on = true;
+  return HB_OK;
+}
+
+int hb_profile_stop(HbProfileSummary* out) {
+  g_prof_on = false;
+  if (!out) return fail(HB_ERR_INVALID, "null argument");
+  HB_CUDA(cudaDeviceSynchronize());
+  std::memset(out, 0, sizeof(*out));
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess && r.cat >= 0 && r.cat < HB_PROF_CATS) {
+      out->ms[r.cat] += ms;
+      out->flops[r.cat] += r.flops;
+      out->launches[r.cat] += 1;
+    }
+    g_event_pool.push_back(r.e0);
+    g_event_pool.push_back(r.e1);
+  }
+  g_prof.clear();
   return HB_OK;
 }
 
@@ -278,11 +324,11 @@ static int vit_encode_chunk(HbVit* m, const float* frames, int B, float* out, cu
   __nv_bfloat16* qkv = m->qkv.as<__nv_bfloat16>();
   int r;
   // patch embed: gather -> GEMM (+bias +pos, rows remapped past the cls slot); cls row separately
-  HB_LAUNCH(hb::im2col_patch_launch(frames, m->col.ptr(), B, c.image_size, c.patch_size, m->patch.Kpad, s));
-  if ((r = run_gemm(m->col.tm, m->patch, static_cast<long long>(B) * (T - 1), x, D, hb::EPI_F32, s, nullptr, 1.f, 0,
+  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::im2col_patch_launch(frames, m->col.ptr(), B, c.image_size, c.patch_size, m->patch.Kpad, s));
+  if ((r = run_gemm(m->col.tm, m->patch, static_cast<long long>(B) * (T - 1), x, D, hb::EPI_F32_ROWADD, s, nullptr, 1.f, 0,
                     m->pos.ptr() + D, T - 1, T, 1)))
     return r;
-  HB_LAUNCH(hb::cls_row_launch(x, m->cls.ptr(), m->pos.ptr(), B, T, D, s));
+  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::cls_row_launch(x, m->cls.ptr(), m->pos.ptr(), B, T, D, s));
   if (m->tap_layer == 0 && m->tap_dst)
     HB_CUDA(cudaMemcpyAsync(m->tap_dst, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, s));
   const float qscale = 1.0f / sqrtf(88.0f);
@@ -291,14 +337,14 @@ static int vit_encode_chunk(HbVit* m, const float* frames, int B, float* out, cu
     hb::LayerNormParams ln;
     ln.x = x; ln.ldx = D; ln.y = m->h.ptr(); ln.ldy = D; ln.w = L.n1w.ptr(); ln.b = L.n1b.ptr();
     ln.eps = c.ln_eps; ln.rows = static_cast<int>(M); ln.D = D;
-    HB_LAUNCH(hb::layernorm_launch(ln, true, s));
+    HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, true, s));
     if ((r = run_gemm(m->h.tm, L.qkv, M, qkv, 3 * D, hb::EPI_BF16, s, nullptr, qscale, D))) return r;
     hb::AttnParams ap;
     ap.qkv = qkv; ap.out = m->h.ptr(); ap.B = B; ap.H = c.heads;
-    HB_LAUNCH(hb::vit_attn_launch(ap, s));
+    HB_LAUNCH_P(CAT_VIT_ATTN, 4.0 * B * c.heads * 257.0 * 257.0 * 88.0, s, hb::vit_attn_launch(ap, s));
     if ((r = run_gemm(m->h.tm, L.proj, M, x, D, hb::EPI_F32, s, x))) return r;
     ln.w = L.n2w.ptr(); ln.b = L.n2b.ptr();
-    HB_LAUNCH(hb::layernorm_launch(ln, true, s));
+    HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, true, s));
     if ((r = run_gemm(m->h.tm, L.fc1, M, m->hid.ptr(), F, hb::EPI_GELU_BF16, s))) return r;
     if ((r = run_gemm(m->hid.tm, L.fc2, M, x, D, hb::EPI_F32, s, x))) return r;
     if (m->tap_layer == i + 1 && m->tap_dst)
@@ -308,12 +354,13 @@ static int vit_encode_chunk(HbVit* m, const float* frames, int B, float* out, cu
   hb::LayerNormParams ln;
   ln.x = x; ln.ldx = D; ln.row_idx = m->cls_idx.as<int>(); ln.y = m->clsn.ptr(); ln.ldy = D;
   ln.w = m->nw.ptr(); ln.b = m->nb.ptr(); ln.eps = c.ln_eps; ln.rows = B; ln.D = D;
-  HB_LAUNCH(hb::layernorm_launch(ln, true, s));
+  HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, true, s));
   if ((r = run_gemm(m->clsn.tm, m->head, B, out, E, hb::EPI_F32, s))) return r;
   return HB_OK;
 }
 
 int hb_vit_encode(HbVit* m, const float* frames, int64_t B, float* out, void* stream) {
+  if (B == 0 && m) return HB_OK;  // empty batch: nothing to do (pointers of empty tensors may be null)
   if (!m || !frames || !out) return fail(HB_ERR_INVALID, "null argument");
   if (B < 0) return fail(HB_ERR_INVALID, "negative batch");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -398,14 +445,14 @@ static int text_encode_chunk(HbText* m, const int64_t* ids, int Q, float* out, c
   float* x = m->x.as<float>();
   __nv_bfloat16* qkv = m->qkv.as<__nv_bfloat16>();
   int r;
-  HB_LAUNCH(hb::text_embed_launch(reinterpret_cast<const long long*>(ids), m->tok.ptr(), m->pos.ptr(), x,
+  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::text_embed_launch(reinterpret_cast<const long long*>(ids), m->tok.ptr(), m->pos.ptr(), x,
                                   m->eot_row.as<int>(), Q, C, W, c.vocab_size, s));
   for (int i = 0; i < c.layers; ++i) {
     HbText::Layer& L = *m->layers[i];
     hb::LayerNormParams ln;
     ln.x = x; ln.ldx = W; ln.y = m->h.ptr(); ln.ldy = W; ln.w = L.l1w.ptr(); ln.b = L.l1b.ptr();
     ln.eps = c.ln_eps; ln.rows = static_cast<int>(M); ln.D = W;
-    HB_LAUNCH(hb::layernorm_launch(ln, true, s));
+    HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, true, s));
     if ((r = run_gemm(m->h.tm, L.qkv, M, qkv, 3 * W, hb::EPI_BF16, s))) return r;
     hb::SmallAttnParams ap;
     ap.q = qkv; ap.k = qkv + W; ap.v = qkv + 2 * W; ap.out = m->h.ptr();
@@ -414,10 +461,10 @@ static int text_encode_chunk(HbText* m, const int64_t* ids, int Q, float* out, c
     ap.bsq = ap.bsk = ap.bsv = static_cast<long long>(C) * 3 * W; ap.bso = static_cast<long long>(C) * W;
     ap.scale = 0.125f;   // head_dim^-0.5, nn.MultiheadAttention
     ap.mask_mode = 1;    // causal, eva_model.py:224-230
-    HB_LAUNCH(hb::small_attn_launch(ap, s));
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::small_attn_launch(ap, s));
     if ((r = run_gemm(m->h.tm, L.out, M, x, W, hb::EPI_F32, s, x))) return r;
     ln.w = L.l2w.ptr(); ln.b = L.l2b.ptr();
-    HB_LAUNCH(hb::layernorm_launch(ln, true, s));
+    HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, true, s));
     if ((r = run_gemm(m->h.tm, L.fc, M, m->hid.ptr(), 4 * W, hb::EPI_GELU_BF16, s))) return r;
     if ((r = run_gemm(m->hid.tm, L.cproj, M, x, W, hb::EPI_F32, s, x))) return r;
   }
@@ -425,12 +472,13 @@ static int text_encode_chunk(HbText* m, const int64_t* ids, int Q, float* out, c
   hb::LayerNormParams ln;
   ln.x = x; ln.ldx = W; ln.row_idx = m->eot_row.as<int>(); ln.y = m->eot.ptr(); ln.ldy = W;
   ln.w = m->lfw.ptr(); ln.b = m->lfb.ptr(); ln.eps = c.ln_eps; ln.rows = Q; ln.D = W;
-  HB_LAUNCH(hb::layernorm_launch(ln, true, s));
+  HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, true, s));
   if ((r = run_gemm(m->eot.tm, m->proj, Q, out, E, hb::EPI_F32, s))) return r;
   return HB_OK;
 }
 
 int hb_text_encode(HbText* m, const int64_t* ids, int64_t Q, float* out, void* stream) {
+  if (Q == 0 && m) return HB_OK;
   if (!m || !ids || !out) return fail(HB_ERR_INVALID, "null argument");
   if (Q < 0) return fail(HB_ERR_INVALID, "negative batch");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -462,7 +510,7 @@ int hb_similarity(const float* text, int64_t Q, const float* video, int64_t V, i
   if (E % 8 != 0 || V % 16 != 0 || ld_scores % 4 != 0 || ld_scores < V)
     return fail(HB_ERR_INVALID, "hb_similarity needs E %% 8 == 0, V %% 16 == 0 (pad the gallery), ld_scores %% 4 == 0");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int Kx = exact ? 3 * E : E;
+  const int Kx = exact ? 6 * E : E;
   // scratch is allocated on the stream (cudaMallocAsync): no hidden sync, freed in stream order
   __nv_bfloat16 *tb = nullptr, *vb = nullptr;
   HB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&tb), static_cast<size_t>(Q) * Kx * 2, s));
@@ -478,14 +526,15 @@ int hb_similarity(const float* text, int64_t Q, const float* video, int64_t V, i
     }
     g_launches.fetch_add(2);
     CUtensorMap tmT, tmV;
+    const int cg = (V % 32 == 0) ? g_cg : 1;
     if (hb::make_tmap_bf16(&tmT, tb, Q, Kx, Kx, hb::gemm_a_box_rows()) ||
-        hb::make_tmap_bf16(&tmV, vb, V, Kx, Kx, hb::gemm_w_box_rows(g_cg))) {
+        hb::make_tmap_bf16(&tmV, vb, V, Kx, Kx, hb::gemm_w_box_rows(cg))) {
       rc = fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled failed for similarity operands");
       break;
     }
     hb::GemmParams p;
     p.M = static_cast<int>(Q); p.N = static_cast<int>(V); p.K = Kx; p.out = scores; p.ldo = static_cast<int>(ld_scores);
-    int r = hb::gemm_launch(tmT, tmV, p, hb::EPI_F32, g_cg, g_num_sms, s);
+    int r = hb::gemm_launch(tmT, tmV, p, hb::EPI_F32, cg, g_num_sms, s);
     if (r) { rc = fail(HB_ERR_CUDA, "similarity GEMM launch failed: %d", r); break; }
     g_launches.fetch_add(1);
   } while (0);
@@ -503,12 +552,13 @@ int hb_linear(const void* x, int64_t ldx, const void* w, int64_t ldw, const floa
   if (epilogue < 0 || epilogue > 2) return fail(HB_ERR_INVALID, "bad epilogue %d", epilogue);
   if (resid && epilogue != HB_EPI_F32) return fail(HB_ERR_INVALID, "residual needs HB_EPI_F32");
   CUtensorMap tmA, tmW;
-  if (hb::make_tmap_bf16(&tmA, x, M, K, ldx, hb::gemm_a_box_rows()) || hb::make_tmap_bf16(&tmW, w, N, K, ldw, hb::gemm_w_box_rows(g_cg)))
+  const int cg = (N % 32 == 0) ? g_cg : 1;
+  if (hb::make_tmap_bf16(&tmA, x, M, K, ldx, hb::gemm_a_box_rows()) || hb::make_tmap_bf16(&tmW, w, N, K, ldw, hb::gemm_w_box_rows(cg)))
     return fail(HB_ERR_INVALID, "cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)");
   hb::GemmParams p;
   p.M = static_cast<int>(M); p.N = static_cast<int>(N); p.K = static_cast<int>(K);
   p.bias = bias; p.out = out; p.ldo = static_cast<int>(ldo); p.resid = resid;
-  HB_LAUNCH(hb::gemm_launch(tmA, tmW, p, epilogue, g_cg, g_num_sms, static_cast<cudaStream_t>(stream)));
+  HB_LAUNCH(hb::gemm_launch(tmA, tmW, p, epilogue, cg, g_num_sms, static_cast<cudaStream_t>(stream)));
   return HB_OK;
 }
 

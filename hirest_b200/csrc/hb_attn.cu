@@ -9,10 +9,12 @@
 // (rank-1 update), and its query row is computed by one CUDA-core warp.  head_dim 88 is padded to 96
 // (zero chunk) for the K=16 UMMA steps.
 //
-//   warps 0-3 : loaders, then softmax + output for query tile 0 (one thread per row)
-//   warps 4-7 : loaders, then softmax + output for query tile 1
+//   warps 0-3 : loaders (cp.async), then softmax + output for query tile 0 (one thread per row)
+//   warps 4-7 : loaders (cp.async), then softmax + output for query tile 1
 //   warp  8   : TMEM allocation + single-thread MMA issue
-//   warp  9   : query row 256 on CUDA cores (reads K/V straight from L2)
+// Query row 256 is shared out over the same 256 threads: thread t scores key t from smem before P overwrites K,
+// a block reduction gives its softmax, and its P.V product is accumulated while the tensor core runs P.V of the
+// two big tiles.
 //
 // Shared memory (SWIZZLE_128B slabs, 128 B per row, 8-row groups 1024 B apart):
 //   Q region 64 KiB: tile g, slab s (d 0..63 | d 64..95)           -> later overwritten by P tile 1
@@ -29,9 +31,9 @@ constexpr int T_TOK = 257;
 constexpr int TQ = 256;       // tokens handled on tensor cores (queries and keys)
 constexpr int DH = 88;
 constexpr int NCHUNK = 11;    // 16-byte chunks per head row
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 288;
 constexpr uint32_t Q_OFF = 0, K_OFF = 65536, V_OFF = 131072, MISC_OFF = 196608;
-constexpr uint32_t ATT_SMEM = MISC_OFF + 2048 + 1024;
+constexpr uint32_t ATT_SMEM = MISC_OFF + 5632 + 128 + 1024;
 constexpr float LOG2E = 1.4426950408889634f;
 
 // MN-major SWIZZLE_128B descriptor (B operand = V[key][d], d contiguous): 64-element (128 B) rows along N,
@@ -61,21 +63,27 @@ __device__ __forceinline__ uint4 lds16(uint32_t addr) {
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
-// Copy 256 rows x 88 bf16 (row stride ld elements) into two SW128 slabs; chunk 11 (d 88..95) is zeroed.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Copy 256 rows x 88 bf16 (row stride ld elements) into two SW128 slabs with cp.async (no register staging, all
+// chunks of a thread in flight at once); chunk 11 (d 88..95) is zeroed.
 // rows_per_tile: 128 for Q (tile-major: [tile][slab]), 256 for K/V ([slab]).
 __device__ __forceinline__ void load_rows(uint32_t base, const __nv_bfloat16* __restrict__ src, int ld, int tid,
                                           int rows_per_tile) {
   const uint32_t slab_bytes = static_cast<uint32_t>(rows_per_tile) * 128u;
-#pragma unroll 4
-  for (int c = tid; c < TQ * 12; c += 256) {
+#pragma unroll
+  for (int it = 0; it < 12; ++it) {
+    const int c = tid + it * 256;
     const int row = c / 12, ch = c - row * 12;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (ch < NCHUNK) v = ldg16(src + static_cast<size_t>(row) * ld + ch * 8);
     const int tile = row / rows_per_tile, r = row - tile * rows_per_tile;
     const int slab = ch >> 3, cs = ch & 7;
     const uint32_t addr = base + static_cast<uint32_t>(tile * 2 + slab) * slab_bytes + static_cast<uint32_t>(r >> 3) * 1024u +
                           static_cast<uint32_t>(r & 7) * 128u + (static_cast<uint32_t>(cs ^ (r & 7)) << 4);
-    sts16(addr, v);
+    if (ch < NCHUNK) cp_async16(addr, src + static_cast<size_t>(row) * ld + ch * 8);
+    else sts16(addr, make_uint4(0u, 0u, 0u, 0u));
   }
 }
 
@@ -85,7 +93,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
   const uint32_t sbase = smem_u32(smem);
   float* kx = reinterpret_cast<float*>(smem + MISC_OFF);        // [96] key of token 256
   float* vx = kx + 96;                                          // [96] value of token 256
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MISC_OFF + 1024);
+  float* qx = vx + 96;                                          // [96] query of token 256 (pre-scaled)
+  float* red = qx + 96;                                         // [32] block-reduction scratch
+  float* px = red + 32;                                         // [256] softmax numerators of query 256
+  float* accx = px + 256;                                       // [8][96] per-warp partial outputs of query 256
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MISC_OFF + 5632);
   uint64_t* bar_load = bars;       // count 256
   uint64_t* bar_s = bars + 1;      // [2] count 1 (commit)
   uint64_t* bar_p = bars + 3;      // [2] count 128
@@ -127,10 +139,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
     load_rows(sbase + V_OFF, vg, ldq, tid, 256);
     if (tid < 96) {
       kx[tid] = (tid < DH) ? __bfloat162float(kg[static_cast<size_t>(TQ) * ldq + tid]) : 0.f;
+      qx[tid] = (tid < DH) ? __bfloat162float(qg[static_cast<size_t>(TQ) * ldq + tid]) : 0.f;
     } else if (tid >= 128 && tid < 224) {
       const int d = tid - 128;
       vx[d] = (d < DH) ? __bfloat162float(vg[static_cast<size_t>(TQ) * ldq + d]) : 0.f;
     }
+    cp_async_wait_all();
     fence_proxy_async_smem();
     mbar_arrive(bar_load);
     // all 256 threads must see kx/vx and the Q tile before the extra-key dot product
@@ -153,7 +167,42 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
                bf_lo(v.z) * kk[4] + bf_hi(v.z) * kk[5] + bf_lo(v.w) * kk[6] + bf_hi(v.w) * kk[7];
       }
     }
-    // Both S tiles must be complete (K and Q smem dead) and every thread done reading Q before P overwrites them.
+    // Query row 256, step A: thread tid scores key tid (K row tid from smem), block-wide softmax statistics.
+    float e_t = 0.f;
+    {
+      const uint32_t krow = sbase + K_OFF + static_cast<uint32_t>(tid >> 3) * 1024u + static_cast<uint32_t>(tid & 7) * 128u;
+#pragma unroll
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int slab = ch >> 3, cs = ch & 7;
+        const uint4 v = lds16(krow + static_cast<uint32_t>(slab) * 32768u + (static_cast<uint32_t>(cs ^ (tid & 7)) << 4));
+        const float* qq = qx + ch * 8;
+        e_t += bf_lo(v.x) * qq[0] + bf_hi(v.x) * qq[1] + bf_lo(v.y) * qq[2] + bf_hi(v.y) * qq[3] +
+               bf_lo(v.z) * qq[4] + bf_hi(v.z) * qq[5] + bf_lo(v.w) * qq[6] + bf_hi(v.w) * qq[7];
+      }
+    }
+    float e_self = 0.f;  // query 256 . key 256 (every thread, 88 broadcast FMAs)
+#pragma unroll 8
+    for (int d = 0; d < DH; ++d) e_self += qx[d] * kx[d];
+    {
+      float wm = e_t;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+      if (lane == 0) red[warp] = wm;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    float mx = e_self;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    const float px_t = exp2f((e_t - mx) * LOG2E);
+    const float px_self = exp2f((e_self - mx) * LOG2E);
+    px[tid] = px_t;
+    {
+      float ws = px_t;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
+      if (lane == 0) red[8 + warp] = ws;
+    }
+    // Both S tiles must be complete (K and Q smem dead) and every thread done reading Q/K before P overwrites them.
     mbar_wait(&bar_s[0], 0);
     mbar_wait(&bar_s[1], 0);
     tc_fence_after();
@@ -206,6 +255,40 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(&bar_p[g]);
+
+    // Query row 256, step B (overlaps the tensor-core P.V): warp w accumulates keys [32w, 32w+32), lanes over d.
+    {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      const bool has2 = lane < DH - 64;
+      const uint32_t voff0 = static_cast<uint32_t>(lane >> 3), vin = static_cast<uint32_t>(lane & 7) * 2u;
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const int key = warp * 32 + j;
+        const float pj = px[key];
+        const uint32_t vrow = sbase + V_OFF + static_cast<uint32_t>(key >> 3) * 1024u + static_cast<uint32_t>(key & 7) * 128u;
+        const uint32_t sw = static_cast<uint32_t>(key & 7);
+        uint16_t u0, u1, u2 = 0;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u0) : "r"(vrow + (((voff0) ^ sw) << 4) + vin));
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u1) : "r"(vrow + (((voff0 + 4u) ^ sw) << 4) + vin));
+        if (has2) asm volatile("ld.shared.u16 %0, [%1];" : "=h"(u2) : "r"(vrow + 32768u + (((voff0) ^ sw) << 4) + vin));
+        a0 += pj * __uint_as_float(static_cast<uint32_t>(u0) << 16);
+        a1 += pj * __uint_as_float(static_cast<uint32_t>(u1) << 16);
+        a2 += pj * __uint_as_float(static_cast<uint32_t>(u2) << 16);
+      }
+      accx[warp * 96 + lane] = a0;
+      accx[warp * 96 + 32 + lane] = a1;
+      accx[warp * 96 + 64 + lane] = a2;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (tid < DH) {
+      float tot = px_self;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) tot += red[8 + w];
+      float o = px_self * vx[tid];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) o += accx[w * 96 + tid];
+      og[static_cast<size_t>(TQ) * ldo + tid] = __float2bfloat16(o / tot);
+    }
 
     // ------------------------------------------------------------------ output
     mbar_wait(&bar_o[g], 0);
@@ -266,70 +349,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
       }
     }
     __syncwarp();
-  } else {
-    // ------------------------------------------------------------------ query row 256 on CUDA cores
-    // lanes over keys for q.k, then lanes over d for p.v; K/V are read from global (L2-resident).
-    float q[DH];
-    {
-      const __nv_bfloat16* qx = qg + static_cast<size_t>(TQ) * ldq;
-#pragma unroll
-      for (int ch = 0; ch < NCHUNK; ++ch) {
-        const uint4 v = ldg16(qx + ch * 8);
-        q[ch * 8 + 0] = bf_lo(v.x); q[ch * 8 + 1] = bf_hi(v.x);
-        q[ch * 8 + 2] = bf_lo(v.y); q[ch * 8 + 3] = bf_hi(v.y);
-        q[ch * 8 + 4] = bf_lo(v.z); q[ch * 8 + 5] = bf_hi(v.z);
-        q[ch * 8 + 6] = bf_lo(v.w); q[ch * 8 + 7] = bf_hi(v.w);
-      }
-    }
-    float s[9];
-    float m = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const int key = i * 32 + lane;
-      float acc = -INFINITY;
-      if (key < T_TOK) {
-        acc = 0.f;
-        const __nv_bfloat16* kr = kg + static_cast<size_t>(key) * ldq;
-#pragma unroll
-        for (int ch = 0; ch < NCHUNK; ++ch) {
-          const uint4 v = ldg16(kr + ch * 8);
-          acc += q[ch * 8 + 0] * bf_lo(v.x) + q[ch * 8 + 1] * bf_hi(v.x) + q[ch * 8 + 2] * bf_lo(v.y) +
-                 q[ch * 8 + 3] * bf_hi(v.y) + q[ch * 8 + 4] * bf_lo(v.z) + q[ch * 8 + 5] * bf_hi(v.z) +
-                 q[ch * 8 + 6] * bf_lo(v.w) + q[ch * 8 + 7] * bf_hi(v.w);
-        }
-      }
-      s[i] = acc;
-      m = fmaxf(m, acc);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      s[i] = exp2f((s[i] - m) * LOG2E);  // exp2f(-inf) = 0 for padded keys
-      sum += s[i];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.0f / sum;
-    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-    const bool has2 = (lane + 64) < DH;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const int nk = (i < 8) ? 32 : (T_TOK - 256);
-#pragma unroll 8
-      for (int j = 0; j < nk; ++j) {
-        const float pj = __shfl_sync(0xffffffffu, s[i], j);
-        const __nv_bfloat16* vr = vg + static_cast<size_t>(i * 32 + j) * ldq;
-        o0 += pj * __bfloat162float(vr[lane]);
-        o1 += pj * __bfloat162float(vr[lane + 32]);
-        if (has2) o2 += pj * __bfloat162float(vr[lane + 64]);
-      }
-    }
-    __nv_bfloat16* orow = og + static_cast<size_t>(TQ) * ldo;
-    orow[lane] = __float2bfloat16(o0 * inv);
-    orow[lane + 32] = __float2bfloat16(o1 * inv);
-    if (has2) orow[lane + 64] = __float2bfloat16(o2 * inv);
   }
 
   __syncthreads();

@@ -185,9 +185,13 @@ __global__ void __launch_bounds__(256) pool_normalize_kernel(const float* __rest
   }
 }
 
-// Split fp32 rows into bf16 hi / lo parts for the ~fp32-exact similarity GEMM:
-//   mode 0 (text side):  [hi | hi | lo]      mode 1 (video side): [hi | lo | hi]
-// so that  A'.B'^T = hi.hi + hi.lo + lo.hi  (the dropped lo.lo term is ~2^-16 relative).
+// Split fp32 rows into three bf16 parts (hi + mid + lo = the fp32 value exactly: 3 x 8 significant bits) and lay
+// them out so that ONE bf16 GEMM over K = 6E reproduces the fp32 dot product to ~2^-23 relative:
+//   mode 0 (text side):  [hi | lo | mid | mid | hi  | hi]
+//   mode 1 (video side): [lo | hi | mid | hi  | mid | hi]
+//   A'.B'^T = hi.lo + lo.hi + mid.mid + mid.hi + hi.mid + hi.hi      (dropped terms are <= 2^-24 relative)
+// Smallest terms first: the tensor core's fp32 accumulation truncates, so the error of each add scales with the
+// running sum; accumulating the 2^-16 / 2^-8 corrections before the dominant hi.hi segment keeps it ~1e-7.
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                          long long rows, int E, int mode) {
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -196,11 +200,15 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
   const int e = static_cast<int>(t - r * E);
   const float v = x[t];
   const __nv_bfloat16 hi = __float2bfloat16(v);
-  const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
-  __nv_bfloat16* o = out + r * 3 * E;
-  o[e] = hi;
-  o[E + e] = (mode == 0) ? hi : lo;
-  o[2 * E + e] = (mode == 0) ? lo : hi;
+  const float r1 = v - __bfloat162float(hi);
+  const __nv_bfloat16 mid = __float2bfloat16(r1);
+  const __nv_bfloat16 lo = __float2bfloat16(r1 - __bfloat162float(mid));
+  __nv_bfloat16* o = out + r * 6 * E;
+  if (mode == 0) {
+    o[e] = hi; o[E + e] = lo; o[2 * E + e] = mid; o[3 * E + e] = mid; o[4 * E + e] = hi; o[5 * E + e] = hi;
+  } else {
+    o[e] = lo; o[E + e] = hi; o[2 * E + e] = mid; o[3 * E + e] = hi; o[4 * E + e] = mid; o[5 * E + e] = hi;
+  }
 }
 
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,

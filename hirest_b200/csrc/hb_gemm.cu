@@ -37,17 +37,19 @@ struct Cfg {
   static constexpr int W_BYTES = W_ROWS * BK * 2;     // 32 / 16 KiB
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
   static constexpr int STAGES = (CG == 1) ? 4 : 6;    // 192 KiB either way
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per epilogue warp: one 32x32 fp32 transpose buffer
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + NUM_EPI_WARPS * EPI_STAGE_BYTES;
 };
 
 struct TileCoord {
   int m_blk, n_blk;
 };
 
+// bf16-output epilogues (thread-per-row): r = 32 consecutive fp32 accumulator columns [col0, col0+32) of one row.
 template <int EPI>
 __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const uint32_t (&r)[32], long long row_out,
                                                      int row_in, int col0, int n_valid) {
-  // r: 32 consecutive fp32 accumulator columns [col0, col0+32) of one row. n_valid = #columns < N in this chunk.
+  (void)row_in;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -64,59 +66,25 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const 
       }
     }
   }
-  if constexpr (EPI == EPI_BF16 || EPI == EPI_GELU_BF16) {
-    if constexpr (EPI == EPI_GELU_BF16) {
+  if constexpr (EPI == EPI_GELU_BF16) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-    } else {
-      if (col0 < p.qcols) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.qcols) ? v[j] * p.qscale : v[j];
-      }
-    }
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_out * p.ldo + col0;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (g * 8 < n_valid) {
-        uint4 q;
-        q.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
-        q.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-        q.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
-        q.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
-        *reinterpret_cast<uint4*>(o + 8 * g) = q;
-      }
-    }
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
   } else {
-    if (p.rowadd != nullptr) {
-      const float4* a4 = reinterpret_cast<const float4*>(p.rowadd + static_cast<long long>(row_in % p.remap_in) * p.N + col0);
+    if (col0 < p.qcols) {
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        if (g * 4 < n_valid) {
-          const float4 a = __ldg(a4 + g);
-          v[4 * g + 0] += a.x;
-          v[4 * g + 1] += a.y;
-          v[4 * g + 2] += a.z;
-          v[4 * g + 3] += a.w;
-        }
-      }
+      for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.qcols) ? v[j] * p.qscale : v[j];
     }
-    if (p.resid != nullptr) {
-      const float4* x4 = reinterpret_cast<const float4*>(p.resid + row_out * p.ldo + col0);
+  }
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_out * p.ldo + col0;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        if (g * 4 < n_valid) {
-          const float4 a = x4[g];
-          v[4 * g + 0] += a.x;
-          v[4 * g + 1] += a.y;
-          v[4 * g + 2] += a.z;
-          v[4 * g + 3] += a.w;
-        }
-      }
-    }
-    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row_out * p.ldo + col0);
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (g * 4 < n_valid) o4[g] = make_float4(v[4 * g + 0], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  for (int g = 0; g < 4; ++g) {
+    if (g * 8 < n_valid) {
+      uint4 q;
+      q.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
+      q.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+      q.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+      q.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+      *reinterpret_cast<uint4*>(o + 8 * g) = q;
     }
   }
 }
@@ -245,15 +213,122 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int row_in = m_blk * tile_m + static_cast<int>(cta_rank) * BM + q * 32 + lane;
       long long row_out = row_in;
       if (p.remap_in > 0) row_out = static_cast<long long>(row_in / p.remap_in) * p.remap_out + (row_in % p.remap_in) + p.remap_off;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
+      const int c_begin = half * (BN / 2);
       const int c_end = min(n_eff, (half + 1) * (BN / 2));
-      for (int c = half * (BN / 2); c < c_end; c += 32) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c);
-        tmem_ld_32x32(taddr, r);
-        tmem_ld_wait();
-        if (row_in < p.M) epilogue_store_chunk<EPI>(p, r, row_out, row_in, n0 + c, n_eff - c);
+      if constexpr (EPI == EPI_F32 || EPI == EPI_F32_ROWADD) {
+        // fp32 output (+ fp32 residual / row-add): the accumulator chunk is transposed through a per-warp swizzled smem
+        // buffer so that every global access is a full 128-byte row segment (thread-per-row access costs 32 L1
+        // wavefronts per instruction and made this epilogue the bottleneck of the K=1408 proj GEMM).  Residual values
+        // are prefetched one chunk ahead, in the coalesced mapping: instruction i covers rows 4i + lane/8, 16-byte
+        // column chunk lane%8.
+        const int rr_base = lane >> 3, cc = lane & 7;
+        const uint32_t stage = smem_u32(smem + C::STAGES * C::STAGE_BYTES + 256) + static_cast<uint32_t>(warp - 4) * C::EPI_STAGE_BYTES;
+        const int row_base = m_blk * tile_m + static_cast<int>(cta_rank) * BM + q * 32;
+        uint32_t okmask = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (row_base + 4 * i + rr_base < p.M) okmask |= (1u << i);
+        }
+        // element offset of output row i (and the row-add row), recomputed on use to keep registers for the prefetch
+        auto row_off = [&](int i, int& radd) -> long long {
+          const int ri = row_base + 4 * i + rr_base;
+          radd = 0;
+          if constexpr (EPI == EPI_F32_ROWADD) {  // row remapping exists only for the patch-embed kind
+            if (p.remap_in > 0) {
+              radd = ri % p.remap_in;
+              return (static_cast<long long>(ri / p.remap_in) * p.remap_out + radd + p.remap_off) * p.ldo;
+            }
+          }
+          return static_cast<long long>(ri) * p.ldo;
+        };
+        constexpr bool ROWADD = (EPI == EPI_F32_ROWADD);
+        const bool has_add = ROWADD ? (p.rowadd != nullptr) : (p.resid != nullptr);
+        // DRAM latency under load (~2-3k cycles) is far longer than one chunk of epilogue work, so the residual of the
+        // NEXT tile is pulled into L2 a whole tile ahead; the register prefetch below then only has to cover L2 latency.
+        if (!ROWADD && p.resid != nullptr) {
+          const int et = (warp - 4) * 32 + lane;  // 0..255: row et/2 of the tile, half et%2 of its column span
+          auto prefetch_tile = [&](int tt) {
+            const int pm = tt / n_tiles, pn = tt % n_tiles;
+            const int pri = pm * tile_m + static_cast<int>(cta_rank) * BM + (et >> 1);
+            const int pn0 = pn * BN, pne = min(BN, p.N - pn0);
+            if (pri < p.M) {
+              const float* base = p.resid + static_cast<long long>(pri) * p.ldo + pn0;
+              for (int cidx = (et & 1) * 128; cidx < min(pne, (et & 1) * 128 + 128); cidx += 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + cidx));
+            }
+          };
+          if (t == worker) prefetch_tile(t);
+          if (t + num_workers < total_tiles) prefetch_tile(t + num_workers);
+        }
+        auto load_add = [&](int col0, int n_valid, float4 (&res)[8]) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            res[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (((okmask >> i) & 1u) && cc * 4 < n_valid) {
+              // NOTE: one independent load per slot and nothing consuming it here — a dependent (even predicated-off)
+              // instruction would wait on the load's scoreboard and serialise the eight prefetches.
+              int radd;
+              const long long off = row_off(i, radd);
+              if constexpr (ROWADD) res[i] = __ldg(reinterpret_cast<const float4*>(p.rowadd + static_cast<long long>(radd) * p.N + col0 + cc * 4));
+              else res[i] = *reinterpret_cast<const float4*>(p.resid + off + col0 + cc * 4);
+            }
+          }
+        };
+        auto do_chunk = [&](int c, const float4 (&res)[8]) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c), r);
+          tmem_ld_wait();
+          const uint32_t my_row = stage + static_cast<uint32_t>(lane) * 128u;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + (static_cast<uint32_t>(g ^ (lane & 7)) << 4)),
+                         "r"(r[4 * g]), "r"(r[4 * g + 1]), "r"(r[4 * g + 2]), "r"(r[4 * g + 3]) : "memory");
+          }
+          __syncwarp();
+          const int col0 = n0 + c, n_valid = n_eff - c;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr && cc * 4 < n_valid) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cc * 4));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + rr_base;
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(stage + static_cast<uint32_t>(rr) * 128u + (static_cast<uint32_t>(cc ^ (rr & 7)) << 4)));
+            v.x += b4.x + res[i].x; v.y += b4.y + res[i].y; v.z += b4.z + res[i].z; v.w += b4.w + res[i].w;
+            if (((okmask >> i) & 1u) && cc * 4 < n_valid) {
+              int radd;
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row_off(i, radd) + col0 + cc * 4) = v;
+            }
+          }
+          __syncwarp();
+        };
+        float4 res_a[8], res_b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) res_a[i] = res_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_add && c_begin < c_end) load_add(n0 + c_begin, n_eff - c_begin, res_a);
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; c += 64) {
+          const bool second = (c + 32 < c_end);
+          if (has_add && second) load_add(n0 + c + 32, n_eff - c - 32, res_b);
+          do_chunk(c, res_a);
+          if (second) {
+            if (has_add && c + 64 < c_end) load_add(n0 + c + 64, n_eff - c - 64, res_a);
+            do_chunk(c + 32, res_b);
+          }
+        }
+      } else {
+        const bool row_ok = row_in < p.M;
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c), r);
+          tmem_ld_wait();
+          if (row_ok) epilogue_store_chunk<EPI>(p, r, row_out, row_in, n0 + c, n_eff - c);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -355,12 +430,14 @@ int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams
       case EPI_BF16: return launch_impl<1, EPI_BF16>(tmA, tmW, p, num_sms, stream);
       case EPI_GELU_BF16: return launch_impl<1, EPI_GELU_BF16>(tmA, tmW, p, num_sms, stream);
       case EPI_F32: return launch_impl<1, EPI_F32>(tmA, tmW, p, num_sms, stream);
+      case EPI_F32_ROWADD: return launch_impl<1, EPI_F32_ROWADD>(tmA, tmW, p, num_sms, stream);
     }
   } else if (cg == 2) {
     switch (epi) {
       case EPI_BF16: return launch_impl<2, EPI_BF16>(tmA, tmW, p, num_sms, stream);
       case EPI_GELU_BF16: return launch_impl<2, EPI_GELU_BF16>(tmA, tmW, p, num_sms, stream);
       case EPI_F32: return launch_impl<2, EPI_F32>(tmA, tmW, p, num_sms, stream);
+      case EPI_F32_ROWADD: return launch_impl<2, EPI_F32_ROWADD>(tmA, tmW, p, num_sms, stream);
     }
   }
   return -5;

@@ -15,7 +15,8 @@ namespace hb {
 enum GemmEpilogue : int {
   EPI_BF16 = 0,       // out bf16 = (acc + bias) * (col < qcols ? qscale : 1)
   EPI_GELU_BF16 = 1,  // out bf16 = gelu_erf(acc + bias)
-  EPI_F32 = 2,        // out f32  = acc + bias [+ resid[row_out, col]] [+ rowadd[row % remap_in, col]]
+  EPI_F32 = 2,        // out f32  = acc + bias [+ resid[row_out, col]]
+  EPI_F32_ROWADD = 3, // out f32  = acc + bias + rowadd[row % remap_in, col], rows remapped (patch embed + pos embed)
 };
 
 struct GemmParams {
@@ -24,7 +25,7 @@ struct GemmParams {
   void* out = nullptr;            // bf16 or f32, row-major, leading dim ldo (elements)
   int ldo = 0;
   const float* resid = nullptr;   // EPI_F32: fp32 residual, indexed like out (may alias out)
-  const float* rowadd = nullptr;  // EPI_F32: [remap_in, N] fp32 added by (row % remap_in)
+  const float* rowadd = nullptr;  // EPI_F32_ROWADD: [remap_in, N] fp32 added by (row % remap_in)
   int remap_in = 0;               // if > 0: out_row = (row / remap_in) * remap_out + row % remap_in + remap_off
   int remap_out = 0;
   int remap_off = 0;

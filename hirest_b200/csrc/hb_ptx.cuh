@@ -56,7 +56,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -254,6 +254,24 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-form (erf) GELU, x * Phi(x), with erf from Abramowitz & Stegun 7.1.26 (|error| < 1.5e-7 before fp32 rounding):
+//   erfc(z) = (a1 t + ... + a5 t^5) exp(-z^2),  t = 1 / (1 + p z),  z = |x| / sqrt(2)
+//   x >= 0: Phi = 1 - erfc/2      x < 0: Phi = erfc/2   (no cancellation in the negative tail)
+// ~15 instructions (2 MUFU) instead of ~30 for erff(): the fc1 epilogue is ALU-bound (profiles/r01_gemm_fc1_*.txt).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.3275911f * 0.70710678118654752440f, 1.0f)));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  poly *= t;
+  const float zz = ax * 0.84932180028801904272f;  // sqrt(log2(e) / 2): exp(-x^2/2) = exp2(-zz^2)
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-zz * zz));
+  const float half_erfc = poly * e;
+  return x * (x >= 0.f ? 1.0f - half_erfc : half_erfc);
+}
 
 }  // namespace hb

@@ -1,0 +1,156 @@
+"""Seeded synthetic weights / frames / token ids in the reference's state_dict layout.
+
+Used by bench.py, __graft_entry__.smoke(), the tests and (re-exported as oracle/weights.py) the CPU oracle.
+
+The reference ships no weights offline (README.md:272-346 are download links), so parity is defined on
+seeded random weights.  Key names / shapes follow the reference modules exactly:
+  EVA visual : EVA_clip/vit_model.py:256-300 (VisionTransformer.__init__), :66-119 (Attention), :46-55 (Mlp)
+  EVA text   : EVA_clip/eva_model.py:177-222 (TextTransformer), :110-141 (ResidualAttentionBlock)
+The distribution is OUR choice (documented here, not the reference's init): N(0, 0.02) linear weights with the
+reference's depth rescale of proj/fc2 (vit_model.py:302-308), non-trivial biases and LN affine terms so that
+every bias / affine code path is exercised.  Generation uses one CPU torch.Generator walked in a fixed key
+order, so the same (cfg, seed) gives bit-identical tensors on any box with this torch build.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import torch
+
+EVA_G14 = {
+    "embed_dim": 1024,
+    "vision_cfg": {"image_size": 224, "layers": 40, "width": 1408, "head_width": 88, "mlp_ratio": 4.3637,
+                   "patch_size": 14},
+    "text_cfg": {"context_length": 77, "vocab_size": 49408, "width": 768, "heads": 12, "layers": 12},
+}
+
+# Small config with the same awkward shapes (head_width 88, mlp_ratio 4.3637, 257 tokens, 77 ctx) that the CPU
+# oracle finishes in well under a second; used by the fast parity tests and the committed golden vectors.
+EVA_TINY = {
+    "embed_dim": 256,
+    "vision_cfg": {"image_size": 224, "layers": 3, "width": 352, "head_width": 88, "mlp_ratio": 4.3637,
+                   "patch_size": 14},
+    "text_cfg": {"context_length": 77, "vocab_size": 1024, "width": 128, "heads": 2, "layers": 2},
+}
+
+
+def _normal(gen, shape, std):
+    return torch.randn(shape, generator=gen, dtype=torch.float32, device=gen.device) * std
+
+
+def _generator(seed: int, device="cpu"):
+    """CPU generators give tensors that are bit-identical across boxes (used by the golden vectors); a cuda
+    generator is only for benchmarks, where the values need the right distribution but no oracle match."""
+    return torch.Generator(device=device).manual_seed(seed)
+
+
+def make_visual_state_dict(cfg: dict, seed: int = 0, device="cpu") -> "OrderedDict[str, torch.Tensor]":
+    v = cfg["vision_cfg"]
+    D, L, P = v["width"], v["layers"], v["patch_size"]
+    F = int(D * v["mlp_ratio"])
+    n_tok = (v["image_size"] // P) ** 2 + 1
+    E = cfg["embed_dim"]
+    g = _generator(seed, device)
+    sd = OrderedDict()
+    sd["cls_token"] = _normal(g, (1, 1, D), 0.02)
+    sd["pos_embed"] = _normal(g, (1, n_tok, D), 0.02)
+    sd["patch_embed.proj.weight"] = _normal(g, (D, 3, P, P), 0.02)
+    sd["patch_embed.proj.bias"] = _normal(g, (D,), 0.02)
+    for i in range(L):
+        p = f"blocks.{i}."
+        sd[p + "norm1.weight"] = 1.0 + _normal(g, (D,), 0.05)
+        sd[p + "norm1.bias"] = _normal(g, (D,), 0.02)
+        sd[p + "attn.q_bias"] = _normal(g, (D,), 0.02)
+        sd[p + "attn.v_bias"] = _normal(g, (D,), 0.02)
+        sd[p + "attn.qkv.weight"] = _normal(g, (3 * D, D), 0.02)
+        sd[p + "attn.proj.weight"] = _normal(g, (D, D), 0.02) / math.sqrt(2.0 * (i + 1))
+        sd[p + "attn.proj.bias"] = _normal(g, (D,), 0.02)
+        sd[p + "norm2.weight"] = 1.0 + _normal(g, (D,), 0.05)
+        sd[p + "norm2.bias"] = _normal(g, (D,), 0.02)
+        sd[p + "mlp.fc1.weight"] = _normal(g, (F, D), 0.02)
+        sd[p + "mlp.fc1.bias"] = _normal(g, (F,), 0.02)
+        sd[p + "mlp.fc2.weight"] = _normal(g, (D, F), 0.02) / math.sqrt(2.0 * (i + 1))
+        sd[p + "mlp.fc2.bias"] = _normal(g, (D,), 0.02)
+    sd["norm.weight"] = 1.0 + _normal(g, (D,), 0.05)
+    sd["norm.bias"] = _normal(g, (D,), 0.02)
+    sd["head.weight"] = _normal(g, (E, D), 0.02)
+    sd["head.bias"] = _normal(g, (E,), 0.02)
+    return sd
+
+
+def make_text_state_dict(cfg: dict, seed: int = 1, device="cpu") -> "OrderedDict[str, torch.Tensor]":
+    t = cfg["text_cfg"]
+    W, L, V, C = t["width"], t["layers"], t["vocab_size"], t["context_length"]
+    E = cfg["embed_dim"]
+    g = _generator(seed, device)
+    sd = OrderedDict()
+    sd["positional_embedding"] = _normal(g, (C, W), 0.01)
+    sd["text_projection"] = _normal(g, (W, E), W ** -0.5)
+    sd["logit_scale"] = torch.tensor(math.log(1 / 0.07), dtype=torch.float32, device=device)
+    sd["token_embedding.weight"] = _normal(g, (V, W), 0.02)
+    proj_std = (W ** -0.5) * ((2 * L) ** -0.5)
+    for i in range(L):
+        p = f"transformer.resblocks.{i}."
+        sd[p + "ln_1.weight"] = 1.0 + _normal(g, (W,), 0.05)
+        sd[p + "ln_1.bias"] = _normal(g, (W,), 0.02)
+        sd[p + "attn.in_proj_weight"] = _normal(g, (3 * W, W), W ** -0.5)
+        sd[p + "attn.in_proj_bias"] = _normal(g, (3 * W,), 0.02)
+        sd[p + "attn.out_proj.weight"] = _normal(g, (W, W), proj_std)
+        sd[p + "attn.out_proj.bias"] = _normal(g, (W,), 0.02)
+        sd[p + "ln_2.weight"] = 1.0 + _normal(g, (W,), 0.05)
+        sd[p + "ln_2.bias"] = _normal(g, (W,), 0.02)
+        sd[p + "mlp.c_fc.weight"] = _normal(g, (4 * W, W), (2 * W) ** -0.5)
+        sd[p + "mlp.c_fc.bias"] = _normal(g, (4 * W,), 0.02)
+        sd[p + "mlp.c_proj.weight"] = _normal(g, (W, 4 * W), proj_std)
+        sd[p + "mlp.c_proj.bias"] = _normal(g, (W,), 0.02)
+    sd["ln_final.weight"] = 1.0 + _normal(g, (W,), 0.05)
+    sd["ln_final.bias"] = _normal(g, (W,), 0.02)
+    return sd
+
+
+def make_eva_state_dict(cfg: dict, seed: int = 0, device="cpu") -> "OrderedDict[str, torch.Tensor]":
+    """Full EVA_CLIP state dict: 'visual.*' + 'text.*' (EVA_clip/eva_model.py:292-315)."""
+    sd = OrderedDict()
+    for k, v in make_visual_state_dict(cfg, seed, device).items():
+        sd["visual." + k] = v
+    for k, v in make_text_state_dict(cfg, seed + 1, device).items():
+        sd["text." + k] = v
+    return sd
+
+
+def make_frames(n: int, image_size: int = 224, seed: int = 1, device="cpu") -> torch.Tensor:
+    """Synthetic normalised frames [n, 3, S, S] fp32."""
+    g = _generator(seed, device)
+    return torch.randn((n, 3, image_size, image_size), generator=g, dtype=torch.float32, device=device)
+
+
+def make_tokens(n: int, cfg: dict, seed: int = 2) -> torch.Tensor:
+    """Synthetic CLIP token rows [n, ctx] int64: SOT, 3..20 word ids, EOT (= the row max,
+    EVA_clip/eva_model.py:243), zero padding.  SOT/EOT are the two highest ids of the vocabulary, as in
+    the real tokenizer (49406/49407 for vocab 49408, EVA_clip/clip.py:218-219)."""
+    t = cfg["text_cfg"]
+    V, C = t["vocab_size"], t["context_length"]
+    sot, eot = V - 2, V - 1
+    g = torch.Generator().manual_seed(seed)
+    out = torch.zeros((n, C), dtype=torch.int64)
+    for i in range(n):
+        L = int(torch.randint(3, 21, (1,), generator=g))
+        ids = torch.randint(1, V - 2, (L,), generator=g)
+        out[i, 0] = sot
+        out[i, 1:1 + L] = ids
+        out[i, 1 + L] = eot
+    return out
+
+
+def encode_image_flops(cfg) -> float:
+    """Algorithmic FLOPs per frame (2*M*N*K), SURVEY.md §8(d): 534.063 GFLOP for EVA-CLIP-g/14."""
+    v = cfg["vision_cfg"]
+    D, L, P = v["width"], v["layers"], v["patch_size"]
+    Fh = int(D * v["mlp_ratio"])
+    n = (v["image_size"] // P) ** 2
+    T = n + 1
+    patch = 2.0 * n * D * (3 * P * P)
+    per_layer = 2.0 * T * D * 3 * D + 2.0 * 2 * T * T * D + 2.0 * T * D * D + 2.0 * 2 * T * D * Fh
+    head = 2.0 * D * cfg["embed_dim"]
+    return patch + L * per_layer + head

@@ -47,6 +47,19 @@ HB_API int64_t hb_launch_count(void);
 /* cta_group used by the GEMMs: 2 (CTA pairs, default) or 1. */
 HB_API int hb_set_gemm_cta_group(int cg);
 
+/* Per-launch timing for bench.py's roofline: while enabled every kernel launch of this library is bracketed
+ * by CUDA events on its own stream.  hb_profile_stop synchronises the device and sums per category:
+ * 0 GEMM bf16-out (qkv), 1 GEMM GELU (fc1), 2 GEMM fp32-out (patch/proj/fc2/head/similarity), 3 ViT attention,
+ * 4 LayerNorm, 5 other.  flops = algorithmic 2*M*N*K (attention: 4*B*H*257*257*88). */
+#define HB_PROF_CATS 6
+typedef struct {
+  double ms[HB_PROF_CATS];
+  double flops[HB_PROF_CATS];
+  int64_t launches[HB_PROF_CATS];
+} HbProfileSummary;
+HB_API int hb_profile_start(void);
+HB_API int hb_profile_stop(HbProfileSummary* out);
+
 /* ---- EVA ViT frame encoder (EVA_clip/vit_model.py) -------------------------------------------- */
 typedef struct {
   int image_size;   /* 224 */
@@ -121,7 +134,8 @@ HB_API void hb_text_destroy(HbText* m);
 /* out[v,:] = l2norm(mean_f emb[v,f,:]); emb fp32 [V,F,E]; out fp32 [V,E].  F = 1 gives plain L2 normalise. */
 HB_API int hb_pool_normalize(const float* emb, int64_t V, int F, int E, float* out, void* stream);
 /* scores[q,v] = <text[q,:], video[v,:]>; text fp32 [Q,E], video fp32 [V,E], scores fp32 [Q, ld_scores].
- * exact != 0: split-bf16 (hi/lo) GEMM, ~fp32 accuracy (for bit-stable top-k); exact == 0: single bf16 GEMM. */
+ * exact != 0: one bf16 GEMM over 3-way split operands (hi+mid+lo = the fp32 value exactly), K = 6E: fp32-accurate
+ * scores, so top-k matches the reference's fp32 matmul up to fp32 rounding ties; exact == 0: single plain bf16 GEMM. */
 HB_API int hb_similarity(const float* text, int64_t Q, const float* video, int64_t V, int E, float* scores,
                   int64_t ld_scores, int exact, void* stream);
 

@@ -150,16 +150,3 @@ def recall_at_k(scores, video_names, gt_sets, ks=(1, 5, 10, 50)):
                 hits[k] += 1
     n = max(1, scores.shape[0])
     return {f"R@{k}": hits[k] / n * 100 for k in ks}
-
-
-def encode_image_flops(cfg) -> float:
-    """Algorithmic FLOPs per frame (2*M*N*K), SURVEY.md §8(d): 534.063 GFLOP for EVA-CLIP-g/14."""
-    v = cfg["vision_cfg"]
-    D, L, P = v["width"], v["layers"], v["patch_size"]
-    Fh = int(D * v["mlp_ratio"])
-    n = (v["image_size"] // P) ** 2
-    T = n + 1
-    patch = 2.0 * n * D * (3 * P * P)
-    per_layer = 2.0 * T * D * 3 * D + 2.0 * 2 * T * T * D + 2.0 * T * D * D + 2.0 * 2 * T * D * Fh
-    head = 2.0 * D * cfg["embed_dim"]
-    return patch + L * per_layer + head

@@ -1,0 +1,60 @@
+"""Host-side mirror of the reference interface: state_dict layout, error behaviour, ranking, sharding (no GPU)."""
+import numpy as np
+import pytest
+import torch
+
+from hirest_b200 import eva_clip, retrieval, synthetic
+from oracle import eva_oracle
+
+
+def test_state_dict_layout_matches_reference_keys():
+    cfg = synthetic.EVA_TINY
+    model = eva_clip.EVA_CLIP(**cfg)
+    sd = synthetic.make_eva_state_dict(cfg, seed=0)
+    assert sorted(model.state_dict().keys()) == sorted(sd.keys())
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    res = model.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert torch.equal(model.state_dict()["visual.blocks.1.attn.qkv.weight"], sd["visual.blocks.1.attn.qkv.weight"])
+
+
+def test_g14_parameter_counts_match_survey():
+    cfg = eva_clip.get_model_config("EVA_CLIP_g_14")
+    vis = sum(int(np.prod(s)) for s in eva_clip._visual_shapes(cfg["embed_dim"], cfg["vision_cfg"]).values())
+    txt = sum(int(np.prod(s)) for s in eva_clip._text_shapes(cfg["embed_dim"], cfg["text_cfg"]).values())
+    assert round(vis / 1e6, 2) == 1012.59 and round(txt / 1e6, 2) == 123.85
+
+
+def test_no_cpu_fallback_and_shape_asserts():
+    cfg = synthetic.EVA_TINY
+    model = eva_clip.EVA_CLIP(**cfg).eval()
+    with pytest.raises(AssertionError, match="doesn't match model"):  # vit_model.py:203-204
+        model.encode_image(torch.zeros(1, 3, 200, 224))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.encode_image(torch.zeros(1, 3, 224, 224))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.encode_text(torch.zeros(1, 77, dtype=torch.int64))
+    with pytest.raises(RuntimeError, match="not found"):
+        eva_clip.create_model("no_such_model", "x.pt")
+
+
+def test_rank_videos_equals_reference_rule_with_ties():
+    rng = np.random.default_rng(0)
+    names = [f"v{int(i):03d}" for i in rng.permutation(50)]
+    scores = np.round(rng.normal(size=50), 1)  # many exact ties
+    assert retrieval.rank_videos(scores, names) == eva_oracle.rank_videos(scores.tolist(), names)
+
+
+def test_shard_range_covers_everything_in_order():
+    for n, w in ((4096, 8), (10, 4), (3, 8), (0, 2)):
+        spans = [retrieval.shard_range(n, r, w) for r in range(w)]
+        flat = [i for lo, hi in spans for i in range(lo, hi)]
+        assert flat == list(range(n))
+
+
+def test_synthetic_tokens_have_eot_as_row_max():
+    cfg = synthetic.EVA_G14
+    t = synthetic.make_tokens(16, cfg, seed=3)
+    assert t.shape == (16, 77) and (t[:, 0] == 49406).all()
+    am = t.argmax(-1)
+    assert (t[torch.arange(16), am] == 49407).all() and (am >= 4).all()

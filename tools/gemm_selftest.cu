@@ -139,6 +139,7 @@ static int run_case(const Case& c, int num_sms, bool verify, int iters) {
 int main(int argc, char** argv) {
   const bool quick = argc > 1 && std::string(argv[1]) == "quick";
   const int only_cg = argc > 2 ? atoi(argv[2]) : 0;  // 0 = both
+  const std::string only_case = argc > 3 ? argv[3] : "";  // run just this big case (for ncu)
   int dev = 0;
   CK(cudaSetDevice(dev));
   cudaDeviceProp prop;
@@ -162,6 +163,7 @@ int main(int argc, char** argv) {
   };
   for (const Case& c : small) {
     if (only_cg && c.cg != only_cg) continue;
+    if (!only_case.empty()) continue;
     int r = run_case(c, sms, true, 0);
     if (r == 2) { printf("sticky CUDA error, aborting remaining cases\n"); return 2; }
     fails += (r != 0);
@@ -180,6 +182,7 @@ int main(int argc, char** argv) {
     };
     for (const Case& c : big) {
       if (only_cg && c.cg != only_cg) continue;
+      if (!only_case.empty() && only_case != c.name) continue;
       int r = run_case(c, sms, false, 5);
       if (r == 2) { printf("sticky CUDA error, aborting\n"); return 2; }
     }
