@@ -22,6 +22,7 @@
 //   V region 64 KiB: slab s, 256 key rows (MN-major B operand of P·V)
 // q arrives pre-scaled by head_dim^-0.5 (QKV GEMM epilogue).
 #include "hb_attn.cuh"
+#include "hb_gemm.cuh"
 #include "hb_ptx.cuh"
 
 namespace hb {
@@ -48,9 +49,6 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint3
   return d;
 }
 
-__device__ __forceinline__ uint4 ldg16(const void* p) {
-  return __ldg(reinterpret_cast<const uint4*>(p));
-}
 __device__ __forceinline__ void sts16(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
                : "memory");
@@ -63,31 +61,13 @@ __device__ __forceinline__ uint4 lds16(uint32_t addr) {
 __device__ __forceinline__ float bf_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#ifdef HB_ATTN_TIMING
+#define TSTAMP(i) do { if (threadIdx.x == 0 && p.timing) p.timing[blockIdx.x * 16 + (i)] = clock64(); } while (0)
+#else
+#define TSTAMP(i) do { } while (0)
+#endif
 
-// Copy 256 rows x 88 bf16 (row stride ld elements) into two SW128 slabs with cp.async (no register staging, all
-// chunks of a thread in flight at once); chunk 11 (d 88..95) is zeroed.
-// rows_per_tile: 128 for Q (tile-major: [tile][slab]), 256 for K/V ([slab]).
-__device__ __forceinline__ void load_rows(uint32_t base, const __nv_bfloat16* __restrict__ src, int ld, int tid,
-                                          int rows_per_tile) {
-  const uint32_t slab_bytes = static_cast<uint32_t>(rows_per_tile) * 128u;
-#pragma unroll
-  for (int it = 0; it < 12; ++it) {
-    const int c = tid + it * 256;
-    const int row = c / 12, ch = c - row * 12;
-    const int tile = row / rows_per_tile, r = row - tile * rows_per_tile;
-    const int slab = ch >> 3, cs = ch & 7;
-    const uint32_t addr = base + static_cast<uint32_t>(tile * 2 + slab) * slab_bytes + static_cast<uint32_t>(r >> 3) * 1024u +
-                          static_cast<uint32_t>(r & 7) * 128u + (static_cast<uint32_t>(cs ^ (r & 7)) << 4);
-    if (ch < NCHUNK) cp_async16(addr, src + static_cast<size_t>(row) * ld + ch * 8);
-    else sts16(addr, make_uint4(0u, 0u, 0u, 0u));
-  }
-}
-
-__global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t sbase = smem_u32(smem);
@@ -98,12 +78,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
   float* px = red + 32;                                         // [256] softmax numerators of query 256
   float* accx = px + 256;                                       // [8][96] per-warp partial outputs of query 256
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MISC_OFF + 5632);
-  uint64_t* bar_load = bars;       // count 256
+  uint64_t* bar_load = bars;       // count 1 + 12 TMA boxes of 16 KiB (complete_tx)
   uint64_t* bar_s = bars + 1;      // [2] count 1 (commit)
   uint64_t* bar_p = bars + 3;      // [2] count 128
   uint64_t* bar_o = bars + 5;      // [2] count 1 (commit)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
+  TSTAMP(0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
   const int ldq = 3 * p.H * DH;
@@ -115,7 +96,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
 
   if (warp == 8) {
     if (lane == 0) {
-      mbar_init(bar_load, 256);
+      mbar_init(bar_load, 1);
+      tma_prefetch_desc(&tmQKV);
       for (int i = 0; i < 2; ++i) {
         mbar_init(&bar_s[i], 1);
         mbar_init(&bar_p[i], 128);
@@ -130,59 +112,70 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  TSTAMP(1);
 
   if (warp < 8) {
     // ------------------------------------------------------------------ load phase
     const int tid = threadIdx.x;
-    load_rows(sbase + Q_OFF, qg, ldq, tid, 128);
-    load_rows(sbase + K_OFF, kg, ldq, tid, 256);
-    load_rows(sbase + V_OFF, vg, ldq, tid, 256);
+    // Q/K/V tiles arrive by TMA (issued by warp 8); meanwhile fetch token 256's q/k/v rows (extra key / extra query).
+    float xa = 0.f, xb = 0.f;
     if (tid < 96) {
-      kx[tid] = (tid < DH) ? __bfloat162float(kg[static_cast<size_t>(TQ) * ldq + tid]) : 0.f;
-      qx[tid] = (tid < DH) ? __bfloat162float(qg[static_cast<size_t>(TQ) * ldq + tid]) : 0.f;
+      if (tid < DH) {
+        xa = __bfloat162float(kg[static_cast<size_t>(TQ) * ldq + tid]);
+        xb = __bfloat162float(qg[static_cast<size_t>(TQ) * ldq + tid]);
+      }
     } else if (tid >= 128 && tid < 224) {
-      const int d = tid - 128;
-      vx[d] = (d < DH) ? __bfloat162float(vg[static_cast<size_t>(TQ) * ldq + d]) : 0.f;
+      if (tid - 128 < DH) xa = __bfloat162float(vg[static_cast<size_t>(TQ) * ldq + (tid - 128)]);
     }
-    cp_async_wait_all();
-    fence_proxy_async_smem();
-    mbar_arrive(bar_load);
-    // all 256 threads must see kx/vx and the Q tile before the extra-key dot product
+    if (tid < 96) { kx[tid] = xa; qx[tid] = xb; }
+    else if (tid >= 128 && tid < 224) vx[tid - 128] = xa;
+    TSTAMP(2);
+    mbar_wait(bar_load, 0);
+    // all 256 threads must see kx/qx/vx before the extra-key / extra-query dot products
     asm volatile("bar.sync 1, 256;" ::: "memory");
 
+    TSTAMP(3);
     const int g = warp >> 2;           // query tile
     const int wq = warp & 3;           // TMEM lane quarter
     const int r = wq * 32 + lane;      // row within the tile
     // score against the extra key (token 256): s_x = q_row . k_x  (q is pre-scaled)
-    float s_x = 0.f;
+    float s_x;
     {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       const uint32_t qrow = sbase + Q_OFF + static_cast<uint32_t>(g * 2) * 16384u + static_cast<uint32_t>(r >> 3) * 1024u +
                             static_cast<uint32_t>(r & 7) * 128u;
 #pragma unroll
       for (int ch = 0; ch < NCHUNK; ++ch) {
         const int slab = ch >> 3, cs = ch & 7;
         const uint4 v = lds16(qrow + static_cast<uint32_t>(slab) * 16384u + (static_cast<uint32_t>(cs ^ (r & 7)) << 4));
-        const float* kk = kx + ch * 8;
-        s_x += bf_lo(v.x) * kk[0] + bf_hi(v.x) * kk[1] + bf_lo(v.y) * kk[2] + bf_hi(v.y) * kk[3] +
-               bf_lo(v.z) * kk[4] + bf_hi(v.z) * kk[5] + bf_lo(v.w) * kk[6] + bf_hi(v.w) * kk[7];
+        const float4 k0 = *reinterpret_cast<const float4*>(kx + ch * 8), k1 = *reinterpret_cast<const float4*>(kx + ch * 8 + 4);
+        a0 = fmaf(bf_lo(v.x), k0.x, a0); a1 = fmaf(bf_hi(v.x), k0.y, a1); a2 = fmaf(bf_lo(v.y), k0.z, a2); a3 = fmaf(bf_hi(v.y), k0.w, a3);
+        a0 = fmaf(bf_lo(v.z), k1.x, a0); a1 = fmaf(bf_hi(v.z), k1.y, a1); a2 = fmaf(bf_lo(v.w), k1.z, a2); a3 = fmaf(bf_hi(v.w), k1.w, a3);
       }
+      s_x = (a0 + a1) + (a2 + a3);
     }
     // Query row 256, step A: thread tid scores key tid (K row tid from smem), block-wide softmax statistics.
-    float e_t = 0.f;
+    float e_t;
     {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       const uint32_t krow = sbase + K_OFF + static_cast<uint32_t>(tid >> 3) * 1024u + static_cast<uint32_t>(tid & 7) * 128u;
 #pragma unroll
       for (int ch = 0; ch < NCHUNK; ++ch) {
         const int slab = ch >> 3, cs = ch & 7;
         const uint4 v = lds16(krow + static_cast<uint32_t>(slab) * 32768u + (static_cast<uint32_t>(cs ^ (tid & 7)) << 4));
-        const float* qq = qx + ch * 8;
-        e_t += bf_lo(v.x) * qq[0] + bf_hi(v.x) * qq[1] + bf_lo(v.y) * qq[2] + bf_hi(v.y) * qq[3] +
-               bf_lo(v.z) * qq[4] + bf_hi(v.z) * qq[5] + bf_lo(v.w) * qq[6] + bf_hi(v.w) * qq[7];
+        const float4 q0 = *reinterpret_cast<const float4*>(qx + ch * 8), q1 = *reinterpret_cast<const float4*>(qx + ch * 8 + 4);
+        a0 = fmaf(bf_lo(v.x), q0.x, a0); a1 = fmaf(bf_hi(v.x), q0.y, a1); a2 = fmaf(bf_lo(v.y), q0.z, a2); a3 = fmaf(bf_hi(v.y), q0.w, a3);
+        a0 = fmaf(bf_lo(v.z), q1.x, a0); a1 = fmaf(bf_hi(v.z), q1.y, a1); a2 = fmaf(bf_lo(v.w), q1.z, a2); a3 = fmaf(bf_hi(v.w), q1.w, a3);
       }
+      e_t = (a0 + a1) + (a2 + a3);
     }
-    float e_self = 0.f;  // query 256 . key 256 (every thread, 88 broadcast FMAs)
-#pragma unroll 8
-    for (int d = 0; d < DH; ++d) e_self += qx[d] * kx[d];
+    float e_self;  // query 256 . key 256: lanes over d, warp reduction (every warp computes it redundantly)
+    {
+      float a = qx[lane] * kx[lane] + qx[lane + 32] * kx[lane + 32] + qx[lane + 64] * kx[lane + 64];  // d >= 88 are zeros
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      e_self = a;
+    }
     {
       float wm = e_t;
 #pragma unroll
@@ -202,12 +195,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
       for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(0xffffffffu, ws, o);
       if (lane == 0) red[8 + warp] = ws;
     }
+    TSTAMP(4);
     // Both S tiles must be complete (K and Q smem dead) and every thread done reading Q/K before P overwrites them.
     mbar_wait(&bar_s[0], 0);
     mbar_wait(&bar_s[1], 0);
     tc_fence_after();
     asm volatile("bar.sync 1, 256;" ::: "memory");
 
+    TSTAMP(5);
     const uint32_t t_s = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(g * 256);
     float m = s_x;
     {
@@ -220,8 +215,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
         for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
       }
     }
+    TSTAMP(6);
     const float m2 = m * LOG2E;
-    float sum = 0.f;
+    float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
     const uint32_t prow = sbase + (g == 0 ? K_OFF : Q_OFF) + static_cast<uint32_t>(r >> 3) * 1024u +
                           static_cast<uint32_t>(r & 7) * 128u;
     {
@@ -233,9 +229,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
         float e[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          e[j] = exp2f(__uint_as_float(v[j]) * LOG2E - m2);
-          sum += e[j];
+          float ex;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(fmaf(__uint_as_float(v[j]), LOG2E, -m2)));
+          e[j] = ex;
         }
+        // (a polynomial exp2 on the FMA pipe for every other element was tried and was slower: this pass is
+        //  issue/latency-bound with two warps per scheduler, not MUFU-bound)
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) { sum0 += e[j]; sum1 += e[j + 1]; sum2 += e[j + 2]; sum3 += e[j + 3]; }
         const uint32_t slab_addr = prow + static_cast<uint32_t>(c >> 1) * 16384u;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
@@ -250,11 +251,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
       }
     }
     const float p_x = exp2f(s_x * LOG2E - m2);
-    sum += p_x;
+    const float sum = (sum0 + sum1) + (sum2 + sum3) + p_x;
     const float inv = 1.0f / sum;
     fence_proxy_async_smem();
     tc_fence_before();
     mbar_arrive(&bar_p[g]);
+    TSTAMP(7);
 
     // Query row 256, step B (overlaps the tensor-core P.V): warp w accumulates keys [32w, 32w+32), lanes over d.
     {
@@ -290,10 +292,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
       og[static_cast<size_t>(TQ) * ldo + tid] = __float2bfloat16(o / tot);
     }
 
+    TSTAMP(8);
     // ------------------------------------------------------------------ output
     mbar_wait(&bar_o[g], 0);
+    TSTAMP(9);
     tc_fence_after();
-    __nv_bfloat16* orow = og + static_cast<size_t>(g * 128 + r) * ldo;
+    // O rows (88 bf16 = 176 B) are staged in this tile's dead P region and written out as contiguous 16-byte chunks
+    // (thread-per-row global stores cost 32 L1 wavefronts per instruction).
+    const uint32_t ostage = sbase + (g == 0 ? K_OFF : Q_OFF);
     {
       uint32_t v[32];
 #pragma unroll 1
@@ -312,15 +318,46 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
             q.y = pack_bf16x2(o[2], o[3]);
             q.z = pack_bf16x2(o[4], o[5]);
             q.w = pack_bf16x2(o[6], o[7]);
-            *reinterpret_cast<uint4*>(orow + d0) = q;
+            sts16(ostage + static_cast<uint32_t>(r) * 176u + static_cast<uint32_t>(d0) * 2u, q);
           }
         }
+      }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync %0, 128;" ::"r"(2 + g) : "memory");
+    {
+      const int tl = tid & 127;
+      __nv_bfloat16* otile = og + static_cast<size_t>(g * 128) * ldo;
+#pragma unroll
+      for (int i = 0; i < NCHUNK; ++i) {
+        const int c = tl + 128 * i;           // chunk index within the tile: row = c / 11, 16-byte chunk = c % 11
+        const int row = c / NCHUNK, ch = c - row * NCHUNK;
+        const uint4 q = lds16(ostage + static_cast<uint32_t>(c) * 16u);
+        *reinterpret_cast<uint4*>(otile + static_cast<size_t>(row) * ldo + ch * 8) = q;
       }
     }
     tc_fence_before();
   } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issue
     if (lane == 0) {
+      // TMA: 12 boxes of [128 rows x 64 d] (d >= 88 zero-filled by the tensor map's bounds) straight into the
+      // SWIZZLE_128B slabs.  Tensor map dims: (d = 88, which*H + head, row).
+      mbar_arrive_expect_tx(bar_load, 12u * 16384u);
+      const int row0 = b * T_TOK;
+#pragma unroll
+      for (int w = 0; w < 3; ++w) {      // 0 = Q, 1 = K, 2 = V (same [tile/half][slab] order for all three)
+        uint8_t* region = smem + (w == 0 ? Q_OFF : (w == 1 ? K_OFF : V_OFF));
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int slab = 0; slab < 2; ++slab) {
+            // Q: tile-major [tile][slab] x 16 KiB; K/V: [slab] x 32 KiB with the two 128-row halves back to back
+            const uint32_t off = (w == 0) ? static_cast<uint32_t>(half * 2 + slab) * 16384u
+                                          : static_cast<uint32_t>(slab) * 32768u + static_cast<uint32_t>(half) * 16384u;
+            tma_load_3d(region + off, &tmQKV, bar_load, slab * 64, w * p.H + h, row0 + half * 128);
+          }
+        }
+      }
       mbar_wait(bar_load, 0);
       tc_fence_after();
       const uint32_t idesc_s = umma_idesc_bf16(128, 256);
@@ -351,9 +388,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) vit_attn_kernel(const AttnPara
     __syncwarp();
   }
 
+  TSTAMP(10);
   __syncthreads();
   tc_fence_after();
   if (warp == 8) tmem_dealloc<1>(tmem_base, 512);
+  TSTAMP(11);
 }
 
 }  // namespace
@@ -366,7 +405,12 @@ int vit_attn_launch(const AttnParams& p, cudaStream_t stream) {
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  vit_attn_kernel<<<p.B * p.H, ATT_THREADS, ATT_SMEM, stream>>>(p);
+  CUtensorMap tm;
+  const uint64_t dims[3] = {static_cast<uint64_t>(DH), static_cast<uint64_t>(3 * p.H), static_cast<uint64_t>(p.B) * T_TOK};
+  const uint64_t strides[2] = {static_cast<uint64_t>(DH) * 2, static_cast<uint64_t>(3 * p.H * DH) * 2};
+  const uint32_t box[3] = {64, 1, 128};
+  if (int r = make_tmap_bf16_3d(&tm, p.qkv, dims, strides, box)) return r;
+  vit_attn_kernel<<<p.B * p.H, ATT_THREADS, ATT_SMEM, stream>>>(tm, p);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -14,6 +14,7 @@ struct AttnParams {
   __nv_bfloat16* out = nullptr;
   int B = 0;
   int H = 0;
+  long long* timing = nullptr;  // debug (HB_ATTN_TIMING builds): 16 clock64 stamps per CTA
 };
 int vit_attn_launch(const AttnParams& p, cudaStream_t stream);
 
