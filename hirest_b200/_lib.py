@@ -45,6 +45,21 @@ class HbTextWeights(C.Structure):
                 ("ln_final_b", C.c_void_p), ("text_projection", C.c_void_p)]
 
 
+class HbMomentConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("embed_dim", "hidden", "heads", "ffn", "layers", "asr_dim", "clip_dim", "max_pos")]
+
+
+MOMENT_WEIGHT_FIELDS = ("asr_ln_w", "asr_ln_b", "asr_w", "asr_b", "temp_w1", "temp_b1", "temp_w2", "temp_b2", "mask_embed",
+                        "boundary_embed", "head_w", "head_b", "vis_norm_w", "vis_norm_b", "clip_g_map_w", "clip_g_map_b",
+                        "clip_g_map_text_w", "clip_g_map_text_b", "emb_w", "emb_b", "pos_emb", "emb_ln_w", "emb_ln_b",
+                        "q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "ao_w", "ao_b", "ao_ln_w", "ao_ln_b", "i_w", "i_b", "o_w", "o_b",
+                        "o_ln_w", "o_ln_b")
+
+
+class HbMomentWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in MOMENT_WEIGHT_FIELDS]
+
+
 class HbProfileSummary(C.Structure):
     _fields_ = [("ms", C.c_double * 6), ("flops", C.c_double * 6), ("launches", C.c_int64 * 6)]
 
@@ -69,6 +84,15 @@ SIGNATURES = {
                                  C.POINTER(C.c_void_p)]),
     "hb_text_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "hb_text_destroy": (None, [C.c_void_p]),
+    "hb_moment_create": (C.c_int, [C.POINTER(HbMomentConfig), C.POINTER(HbMomentWeights), C.c_int64, C.c_int, C.c_void_p,
+                                   C.POINTER(C.c_void_p)]),
+    "hb_moment_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_moment_destroy": (None, [C.c_void_p]),
+    "hb_moment_mr_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "hb_moment_ms_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                    C.c_double, C.c_void_p, C.c_void_p]),
+    "hb_trim_feats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hb_pool_normalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hb_similarity": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int,
                                 C.c_void_p]),

@@ -18,6 +18,7 @@
 #include "hb_attn.cuh"
 #include "hb_elem.cuh"
 #include "hb_gemm.cuh"
+#include "hb_moment.cuh"
 
 namespace {
 
@@ -592,6 +593,226 @@ int hb_small_attention(const void* q, const void* k, const void* v, void* out, i
   ap.bsq = bsq; ap.bsk = bsk; ap.bsv = bsv; ap.bso = bso; ap.scale = scale; ap.mask_mode = mask_mode;
   ap.mask_const = mask_const; ap.causal_soft = causal_soft;
   HB_LAUNCH(hb::small_attn_launch(ap, static_cast<cudaStream_t>(stream)));
+  return HB_OK;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// MomentModel shared encoder + heads
+// =================================================================================================
+namespace {
+
+// nn.Linear as a 3-term split-bf16 GEMM: weight [N, 3K] = [hi | lo | hi], activations [R, 3K] = [lo | hi | hi].
+struct SplitLinear {
+  DevBuf w, b;
+  CUtensorMap tm;
+  int N = 0, K = 0, cg = 2;
+  bool has_bias = false;
+  int init_from(const float* w_f32 /*device [N,K]*/, const float* bias, int N_, int K_, cudaStream_t s) {
+    N = N_; K = K_; cg = (N_ % 32 == 0) ? g_cg : 1;
+    if (int r = w.alloc(static_cast<size_t>(N) * 3 * K * 2)) return r;
+    if (int r = hb::split3_weight_launch(w_f32, w.as<__nv_bfloat16>(), N, K, s)) return fail(HB_ERR_CUDA, "split3_weight launch failed: %d", r);
+    if (bias) {
+      has_bias = true;
+      if (int r = b.alloc(static_cast<size_t>(N) * 4)) return r;
+      HB_CUDA(cudaMemcpyAsync(b.p, bias, static_cast<size_t>(N) * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    if (hb::make_tmap_bf16(&tm, w.p, N, 3 * K, 3 * K, hb::gemm_w_box_rows(cg))) return fail(HB_ERR_CUDA, "tensor map (split weight) failed");
+    return 0;
+  }
+};
+
+}  // namespace
+
+struct HbMoment {
+  HbMomentConfig cfg;
+  long long max_rows = 0;
+  int max_batch = 0;
+  F32Vec asr_ln_w, asr_ln_b, temp_w1, temp_b1, memb, bemb, head_w, head_b, vn_w, vn_b, pos, emb_ln_w, emb_ln_b;
+  SplitLinear asr, temp2, gmap, gmap_text, emb;
+  struct Layer {
+    SplitLinear qkv, ao, inter, out;
+    F32Vec ao_ln_w, ao_ln_b, o_ln_w, o_ln_b;
+  };
+  std::vector<std::unique_ptr<Layer>> layers;
+  DevBuf op, opT;                 // bf16 split operands [max_rows, 3*ffn], [max_batch, 3*clip_dim]
+  DevBuf vlin, asr_ln, asr_lin, tanh_in, temporal, base, f, tlin, that, e_lin, x, qkv, att, t1, h, mid;
+  // A-operand maps over `op` for each K in use
+  CUtensorMap tm_clip, tm_asr, tm_e, tm_hd, tm_ffn, tm_text;
+};
+
+namespace {
+
+int split_gemm(HbMoment* m, const float* act, long long rows, int K, int gelu, const CUtensorMap& tmA, const SplitLinear& L,
+               float* out, int epi, cudaStream_t s, const float* resid = nullptr, const float* rowadd = nullptr, int remap = 0,
+               __nv_bfloat16* opbuf = nullptr) {
+  __nv_bfloat16* dst = opbuf ? opbuf : m->op.as<__nv_bfloat16>();
+  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(act, dst, rows, K, gelu, s));
+  hb::GemmParams p;
+  p.M = static_cast<int>(rows); p.N = L.N; p.K = 3 * K;
+  p.bias = L.has_bias ? L.b.as<float>() : nullptr; p.out = out; p.ldo = L.N; p.resid = resid;
+  p.rowadd = rowadd; p.remap_in = remap; p.remap_out = remap; p.remap_off = 0;
+  HB_LAUNCH_P(CAT_GEMM_F32, 2.0 * rows * L.N * 3.0 * K, s, hb::gemm_launch(tmA, L.tm, p, epi, L.cg, g_num_sms, s));
+  return 0;
+}
+
+int ln_f32(const float* x, float* y, const F32Vec& w, const F32Vec& b, float eps, long long rows, int D, cudaStream_t s) {
+  hb::LayerNormParams ln;
+  ln.x = x; ln.ldx = D; ln.y = y; ln.ldy = D; ln.w = w.ptr(); ln.b = b.ptr(); ln.eps = eps; ln.rows = static_cast<int>(rows); ln.D = D;
+  HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, false, s));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb_moment_create(const HbMomentConfig* cfg, const HbMomentWeights* w, int64_t max_rows, int max_batch, void* stream,
+                     HbMoment** out) {
+  if (!g_inited) return fail(HB_ERR_INVALID, "hb_init() not called");
+  if (!cfg || !w || !out || max_rows <= 0 || max_batch <= 0) return fail(HB_ERR_INVALID, "null argument");
+  const int E = cfg->embed_dim, Hd = cfg->hidden, Ff = cfg->ffn, A = cfg->asr_dim, Cd = cfg->clip_dim;
+  if (Hd != cfg->heads * 64) return fail(HB_ERR_INVALID, "head_dim must be 64");
+  if (E % 32 || Hd % 32 || Ff % 32 || A % 8 || Cd % 8 || E > 1024) return fail(HB_ERR_INVALID, "unsupported MomentModel dims");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::unique_ptr<HbMoment> m(new (std::nothrow) HbMoment);
+  if (!m) return fail(HB_ERR_NOMEM, "host allocation failed");
+  m->cfg = *cfg; m->max_rows = max_rows; m->max_batch = max_batch;
+  int r;
+#define INITV(dst, src, n) if ((r = m->dst.init(w->src, static_cast<size_t>(n), s))) return r
+  INITV(asr_ln_w, asr_ln_w, A); INITV(asr_ln_b, asr_ln_b, A); INITV(temp_w1, temp_w1, E); INITV(temp_b1, temp_b1, E);
+  INITV(memb, mask_embed, 2 * E); INITV(bemb, boundary_embed, 2 * E); INITV(head_w, head_w, 3 * Hd); INITV(head_b, head_b, 3);
+  INITV(vn_w, vis_norm_w, E); INITV(vn_b, vis_norm_b, E); INITV(pos, pos_emb, static_cast<size_t>(cfg->max_pos) * Hd);
+  INITV(emb_ln_w, emb_ln_w, Hd); INITV(emb_ln_b, emb_ln_b, Hd);
+#undef INITV
+  if ((r = m->asr.init_from(w->asr_w, w->asr_b, E, A, s))) return r;
+  if ((r = m->temp2.init_from(w->temp_w2, w->temp_b2, E, E, s))) return r;
+  if ((r = m->gmap.init_from(w->clip_g_map_w, w->clip_g_map_b, E, Cd, s))) return r;
+  if ((r = m->gmap_text.init_from(w->clip_g_map_text_w, w->clip_g_map_text_b, E, Cd, s))) return r;
+  if ((r = m->emb.init_from(w->emb_w, w->emb_b, Hd, E, s))) return r;
+  DevBuf tmpw, tmpb;
+  if ((r = tmpw.alloc(static_cast<size_t>(3) * Hd * Hd * 4))) return r;
+  if ((r = tmpb.alloc(static_cast<size_t>(3) * Hd * 4))) return r;
+  for (int i = 0; i < cfg->layers; ++i) {
+    std::unique_ptr<HbMoment::Layer> L(new HbMoment::Layer);
+    const float* ws[3] = {w->q_w[i], w->k_w[i], w->v_w[i]};
+    const float* bs[3] = {w->q_b[i], w->k_b[i], w->v_b[i]};
+    for (int j = 0; j < 3; ++j) {  // separate query / key / value Linears fused into one [3*Hd, Hd] GEMM
+      HB_CUDA(cudaMemcpyAsync(tmpw.as<float>() + static_cast<size_t>(j) * Hd * Hd, ws[j], static_cast<size_t>(Hd) * Hd * 4, cudaMemcpyDeviceToDevice, s));
+      HB_CUDA(cudaMemcpyAsync(tmpb.as<float>() + static_cast<size_t>(j) * Hd, bs[j], static_cast<size_t>(Hd) * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    if ((r = L->qkv.init_from(tmpw.as<float>(), tmpb.as<float>(), 3 * Hd, Hd, s))) return r;
+    if ((r = L->ao.init_from(w->ao_w[i], w->ao_b[i], Hd, Hd, s))) return r;
+    if ((r = L->inter.init_from(w->i_w[i], w->i_b[i], Ff, Hd, s))) return r;
+    if ((r = L->out.init_from(w->o_w[i], w->o_b[i], Hd, Ff, s))) return r;
+    if ((r = L->ao_ln_w.init(w->ao_ln_w[i], Hd, s))) return r;
+    if ((r = L->ao_ln_b.init(w->ao_ln_b[i], Hd, s))) return r;
+    if ((r = L->o_ln_w.init(w->o_ln_w[i], Hd, s))) return r;
+    if ((r = L->o_ln_b.init(w->o_ln_b[i], Hd, s))) return r;
+    m->layers.push_back(std::move(L));
+  }
+  const size_t R = static_cast<size_t>(max_rows);
+  const int Kmax = std::max(std::max(Ff, Cd), std::max(Hd, E));
+  if ((r = m->op.alloc(R * 3 * Kmax * 2))) return r;
+  if ((r = m->opT.alloc(static_cast<size_t>(max_batch) * 3 * Cd * 2))) return r;
+#define ALLOCF(buf, cols) if ((r = m->buf.alloc(R * static_cast<size_t>(cols) * 4))) return r
+  ALLOCF(vlin, E); ALLOCF(asr_ln, A); ALLOCF(asr_lin, E); ALLOCF(tanh_in, E); ALLOCF(temporal, E); ALLOCF(base, E); ALLOCF(f, E);
+  ALLOCF(e_lin, Hd); ALLOCF(x, Hd); ALLOCF(qkv, 3 * Hd); ALLOCF(att, Hd); ALLOCF(t1, Hd); ALLOCF(h, Hd); ALLOCF(mid, Ff);
+#undef ALLOCF
+  if ((r = m->tlin.alloc(static_cast<size_t>(max_batch) * E * 4))) return r;
+  if ((r = m->that.alloc(static_cast<size_t>(max_batch) * E * 4))) return r;
+  auto amap = [&](CUtensorMap* tm, void* ptr, long long rows, int K) {
+    return hb::make_tmap_bf16(tm, ptr, rows, 3 * K, 3 * K, hb::gemm_a_box_rows());
+  };
+  if (amap(&m->tm_clip, m->op.p, max_rows, Cd) || amap(&m->tm_asr, m->op.p, max_rows, A) || amap(&m->tm_e, m->op.p, max_rows, E) ||
+      amap(&m->tm_hd, m->op.p, max_rows, Hd) || amap(&m->tm_ffn, m->op.p, max_rows, Ff) || amap(&m->tm_text, m->opT.p, max_batch, Cd))
+    return fail(HB_ERR_CUDA, "tensor map (moment operands) failed");
+  HB_CUDA(cudaStreamSynchronize(s));  // tmpw/tmpb are released on return
+  *out = m.release();
+  return HB_OK;
+}
+
+void hb_moment_destroy(HbMoment* m) { delete m; }
+
+int hb_moment_forward(HbMoment* m, const float* video, const float* text_feat, const float* asr, const int64_t* video_mask,
+                      const int64_t* moment_mask, const int64_t* boundary_mask, int B, int T, int flags, float* out_feats,
+                      float* out_logits, void* stream) {
+  if (!m || !moment_mask || !out_logits) return fail(HB_ERR_INVALID, "null argument");
+  if (B <= 0 || T <= 0) return fail(HB_ERR_INVALID, "empty batch");
+  const long long R = static_cast<long long>(B) * T;
+  const HbMomentConfig& c = m->cfg;
+  if (R > m->max_rows || B > m->max_batch) return fail(HB_ERR_INVALID, "batch of %d x %d frames exceeds the handle's capacity", B, T);
+  if (T > c.max_pos) return fail(HB_ERR_INVALID, "T = %d exceeds max_position_embeddings %d", T, c.max_pos);
+  if (T > 400) return fail(HB_ERR_INVALID, "T = %d > 400 frames is not supported yet (fp32 attention keeps K/V of one head in smem)", T);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int E = c.embed_dim, Hd = c.hidden, Ff = c.ffn, A = c.asr_dim, Cd = c.clip_dim;
+  int r;
+  if (!(flags & HB_MOMENT_REUSE_BASE)) {
+    if (!video || !text_feat || !asr || !video_mask) return fail(HB_ERR_INVALID, "null argument");
+    // clip_g_map (modeling.py:158), clip_g_map_text + L2 norm (:159,163)
+    if ((r = split_gemm(m, video, R, Cd, 0, m->tm_clip, m->gmap, m->vlin.as<float>(), hb::EPI_F32, s))) return r;
+    if ((r = split_gemm(m, text_feat, B, Cd, 0, m->tm_text, m->gmap_text, m->tlin.as<float>(), hb::EPI_F32, s, nullptr, nullptr, 0,
+                        m->opT.as<__nv_bfloat16>())))
+      return r;
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::pool_normalize_launch(m->tlin.as<float>(), m->that.p, B, 1, E, true, false, s));
+    // asr_enc_layer = LayerNorm(1e-5) -> Linear (:167-169)
+    if ((r = ln_f32(asr, m->asr_ln.as<float>(), m->asr_ln_w, m->asr_ln_b, 1e-5f, R, A, s))) return r;
+    if ((r = split_gemm(m, m->asr_ln.as<float>(), R, A, 0, m->tm_asr, m->asr, m->asr_lin.as<float>(), hb::EPI_F32, s))) return r;
+    // temporal_embed = Linear(1,E) -> tanh -> Linear(E,E) on the per-sample time grid (:178-196)
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::time_tanh_launch(reinterpret_cast<const long long*>(video_mask), m->temp_w1.ptr(),
+                                                        m->temp_b1.ptr(), m->tanh_in.as<float>(), B, T, E, s));
+    if ((r = split_gemm(m, m->tanh_in.as<float>(), R, E, 0, m->tm_e, m->temp2, m->temporal.as<float>(), hb::EPI_F32, s))) return r;
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::moment_base_launch(m->vlin.as<float>(), m->vn_w.ptr(), m->vn_b.ptr(), m->that.as<float>(),
+                                                          m->asr_lin.as<float>(), m->temporal.as<float>(), m->base.as<float>(), B, T, E, s));
+  }
+  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::moment_embed_launch(m->base.as<float>(), m->bemb.ptr(), m->memb.ptr(),
+                                                         reinterpret_cast<const long long*>(boundary_mask),
+                                                         reinterpret_cast<const long long*>(moment_mask), m->f.as<float>(), R, E, s));
+  // VisualEmbeddings: Linear(E,Hd) + position embedding + LN (module_visual.py:118-130)
+  if ((r = split_gemm(m, m->f.as<float>(), R, E, 0, m->tm_e, m->emb, m->e_lin.as<float>(), hb::EPI_F32_ROWADD, s, nullptr, m->pos.ptr(), T)))
+    return r;
+  float* x = m->x.as<float>();
+  if ((r = ln_f32(m->e_lin.as<float>(), x, m->emb_ln_w, m->emb_ln_b, 1e-12f, R, Hd, s))) return r;
+  for (auto& Lp : m->layers) {
+    HbMoment::Layer& L = *Lp;
+    if ((r = split_gemm(m, x, R, Hd, 0, m->tm_hd, L.qkv, m->qkv.as<float>(), hb::EPI_F32, s))) return r;
+    hb::SmallAttnF32Params ap;
+    ap.q = m->qkv.as<float>(); ap.k = ap.q + Hd; ap.v = ap.q + 2 * Hd; ap.out = m->att.as<float>();
+    ap.B = B; ap.H = c.heads; ap.Tq = T; ap.Tk = T;
+    ap.ldq = ap.ldk = ap.ldv = 3 * Hd; ap.ldo = Hd;
+    ap.bsq = ap.bsk = ap.bsv = static_cast<long long>(T) * 3 * Hd; ap.bso = static_cast<long long>(T) * Hd;
+    ap.scale = 0.125f; ap.mask_mode = 2; ap.mask_const = -10000.0f;  // all-zeros mask quirk, modeling.py:208
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::small_attn_f32_launch(ap, s));
+    if ((r = split_gemm(m, m->att.as<float>(), R, Hd, 0, m->tm_hd, L.ao, m->t1.as<float>(), hb::EPI_F32, s, x))) return r;
+    if ((r = ln_f32(m->t1.as<float>(), m->h.as<float>(), L.ao_ln_w, L.ao_ln_b, 1e-12f, R, Hd, s))) return r;
+    if ((r = split_gemm(m, m->h.as<float>(), R, Hd, 0, m->tm_hd, L.inter, m->mid.as<float>(), hb::EPI_F32, s))) return r;
+    if ((r = split_gemm(m, m->mid.as<float>(), R, Ff, /*gelu=*/1, m->tm_ffn, L.out, m->t1.as<float>(), hb::EPI_F32, s, m->h.as<float>()))) return r;
+    if ((r = ln_f32(m->t1.as<float>(), x, L.o_ln_w, L.o_ln_b, 1e-12f, R, Hd, s))) return r;
+  }
+  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::moment_heads_launch(x, m->head_w.ptr(), m->head_b.ptr(), out_logits, R, Hd, s));
+  if (out_feats) HB_CUDA(cudaMemcpyAsync(out_feats, x, static_cast<size_t>(R) * Hd * 4, cudaMemcpyDeviceToDevice, s));
+  return HB_OK;
+}
+
+int hb_moment_mr_decode(const float* logits, const int64_t* video_mask, int64_t* pred, int B, int T, void* stream) {
+  if (!logits || !video_mask || !pred) return fail(HB_ERR_INVALID, "null argument");
+  HB_LAUNCH(hb::mr_argmax_launch(logits, reinterpret_cast<const long long*>(video_mask), reinterpret_cast<long long*>(pred), B, T,
+                                 static_cast<cudaStream_t>(stream)));
+  return HB_OK;
+}
+
+int hb_moment_ms_step(const float* logits, int64_t* moment_mask, int64_t* boundary_mask, int32_t* steps, int32_t* nsteps, int max_steps,
+                      int B, int T, double threshold, float* probs_out, void* stream) {
+  if (!logits || !moment_mask || !boundary_mask || !steps || !nsteps) return fail(HB_ERR_INVALID, "null argument");
+  HB_LAUNCH(hb::ms_step_launch(logits, reinterpret_cast<long long*>(moment_mask), reinterpret_cast<long long*>(boundary_mask), steps,
+                               nsteps, max_steps, B, T, threshold, probs_out, static_cast<cudaStream_t>(stream)));
+  return HB_OK;
+}
+
+int hb_trim_feats(const float* x, const int64_t* mask, float* out, int B, int T, int C, int F, void* stream) {
+  if (!x || !mask || !out) return fail(HB_ERR_INVALID, "null argument");
+  HB_LAUNCH(hb::trim_feats_launch(x, reinterpret_cast<const long long*>(mask), out, B, T, C, F, static_cast<cudaStream_t>(stream)));
   return HB_OK;
 }
 

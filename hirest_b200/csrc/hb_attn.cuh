@@ -38,4 +38,20 @@ struct SmallAttnParams {
 };
 int small_attn_launch(const SmallAttnParams& p, cudaStream_t stream);
 
+// fp32 in / fp32 out variant (Tk <= 400), same semantics; used by the MomentModel's fp32-accurate path.
+struct SmallAttnF32Params {
+  const float* q = nullptr;
+  const float* k = nullptr;
+  const float* v = nullptr;
+  float* out = nullptr;
+  int B = 0, H = 0, Tq = 0, Tk = 0;
+  int ldq = 0, ldk = 0, ldv = 0, ldo = 0;
+  long long bsq = 0, bsk = 0, bsv = 0, bso = 0;
+  float scale = 1.f;
+  int mask_mode = 0;
+  float mask_const = 0.f;
+  int causal_soft = 0;
+};
+int small_attn_f32_launch(const SmallAttnF32Params& p, cudaStream_t stream);
+
 }  // namespace hb

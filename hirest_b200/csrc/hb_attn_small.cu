@@ -115,7 +115,105 @@ __global__ void __launch_bounds__(SA_THREADS) small_attn_kernel(const SmallAttnP
   }
 }
 
+// ---- fp32 variant (MomentModel "precise" path): q/k/v/out fp32, K/V of one head in smem (Tk <= 400) -------------------
+constexpr int KF_STRIDE = 272;  // 256 + 16 pad
+constexpr int VF_STRIDE = 256;
+constexpr int MAX_TK_F32 = 400;
+constexpr int MAXJ_F32 = (MAX_TK_F32 + 31) / 32;
+
+__global__ void __launch_bounds__(SA_THREADS) small_attn_f32_kernel(const SmallAttnF32Params p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  uint8_t* sk = smem;
+  uint8_t* sv = smem + static_cast<size_t>(p.Tk) * KF_STRIDE;
+  const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* qg = p.q + b * p.bsq + h * DH;
+  const float* kg = p.k + b * p.bsk + h * DH;
+  const float* vg = p.v + b * p.bsv + h * DH;
+  float* og = p.out + b * p.bso + h * DH;
+  for (int c = threadIdx.x; c < p.Tk * 16; c += SA_THREADS) {
+    const int row = c >> 4, ch = c & 15;
+    *reinterpret_cast<float4*>(sk + row * KF_STRIDE + ch * 16) = __ldg(reinterpret_cast<const float4*>(kg + static_cast<size_t>(row) * p.ldk + ch * 4));
+    *reinterpret_cast<float4*>(sv + row * VF_STRIDE + ch * 16) = __ldg(reinterpret_cast<const float4*>(vg + static_cast<size_t>(row) * p.ldv + ch * 4));
+  }
+  __syncthreads();
+  for (int i = warp; i < p.Tq; i += SA_THREADS / 32) {
+    float q[DH];
+#pragma unroll
+    for (int ch = 0; ch < 16; ++ch) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(qg + static_cast<size_t>(i) * p.ldq) + ch);
+      q[ch * 4] = v.x; q[ch * 4 + 1] = v.y; q[ch * 4 + 2] = v.z; q[ch * 4 + 3] = v.w;
+    }
+    const int tk_eff = (p.mask_mode == 1) ? min(p.Tk, i + 1) : p.Tk;
+    float s[MAXJ_F32];
+    float m = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < MAXJ_F32; ++jj) {
+      s[jj] = -INFINITY;
+      if (jj * 32 < tk_eff) {
+        const int key = jj * 32 + lane;
+        if (key < tk_eff) {
+          const uint8_t* kr = sk + key * KF_STRIDE;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < 16; ++ch) {
+            const float4 v = *reinterpret_cast<const float4*>(kr + ch * 16);
+            a0 = fmaf(q[ch * 4], v.x, a0); a1 = fmaf(q[ch * 4 + 1], v.y, a1);
+            a2 = fmaf(q[ch * 4 + 2], v.z, a2); a3 = fmaf(q[ch * 4 + 3], v.w, a3);
+          }
+          float acc = ((a0 + a1) + (a2 + a3)) * p.scale;
+          if (p.mask_mode == 2) {
+            acc = acc + p.mask_const;   // fp32 add: quantises the logit exactly as the reference's mask add does
+            if (p.causal_soft && key > i) acc = acc + (-10000.0f);
+          }
+          s[jj] = acc;
+          m = fmaxf(m, acc);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < MAXJ_F32; ++jj) {
+      if (jj * 32 < tk_eff) { s[jj] = expf(s[jj] - m); sum += s[jj]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < MAXJ_F32; ++jj) {
+      if (jj * 32 < tk_eff) {
+        const int nk = min(32, tk_eff - jj * 32);
+        for (int j = 0; j < nk; ++j) {
+          const float pj = __shfl_sync(0xffffffffu, s[jj], j);
+          const float2 vv = *reinterpret_cast<const float2*>(sv + (jj * 32 + j) * VF_STRIDE + lane * 8);
+          o0 = fmaf(pj, vv.x, o0);
+          o1 = fmaf(pj, vv.y, o1);
+        }
+      }
+    }
+    *reinterpret_cast<float2*>(og + static_cast<size_t>(i) * p.ldo + lane * 2) = make_float2(o0 * inv, o1 * inv);
+  }
+}
+
 }  // namespace
+
+int small_attn_f32_launch(const SmallAttnF32Params& p, cudaStream_t stream) {
+  if (p.B <= 0 || p.H <= 0 || p.Tq <= 0 || p.Tk <= 0) return -3;
+  if (p.Tk > MAX_TK_F32) return -6;
+  const size_t smem = static_cast<size_t>(p.Tk) * (KF_STRIDE + VF_STRIDE);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(small_attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         MAX_TK_F32 * (KF_STRIDE + VF_STRIDE));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  small_attn_f32_kernel<<<p.B * p.H, SA_THREADS, smem, stream>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
 
 int small_attn_launch(const SmallAttnParams& p, cudaStream_t stream) {
   if (p.B <= 0 || p.H <= 0 || p.Tq <= 0 || p.Tk <= 0) return -3;

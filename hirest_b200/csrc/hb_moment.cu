@@ -1,0 +1,343 @@
+// hb_moment.cu — row kernels of the MomentModel path (see hb_moment.cuh for the reference lines each one restates).
+// These kernels are launch/latency-bound at the reference's sizes (B*T ~ 19k rows): one warp per row, 128-bit accesses.
+#include "hb_moment.cuh"
+
+#include <cfloat>
+
+namespace hb {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float gelu_exact(float x) { return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(256) split3_act_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                         long long rows, int K, int gelu) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= rows * K) return;
+  const long long r = t / K;
+  const int k = static_cast<int>(t - r * K);
+  float v = x[t];
+  if (gelu) v = gelu_exact(v);
+  const __nv_bfloat16 hi = __float2bfloat16(v);
+  const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+  __nv_bfloat16* o = out + r * 3 * K;
+  o[k] = lo;
+  o[K + k] = hi;
+  o[2 * K + k] = hi;
+}
+
+__global__ void __launch_bounds__(256) split3_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int N,
+                                                            int K) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(N) * K) return;
+  const long long n = t / K;
+  const int k = static_cast<int>(t - n * K);
+  const float v = w[t];
+  const __nv_bfloat16 hi = __float2bfloat16(v);
+  const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+  __nv_bfloat16* o = out + n * 3 * K;
+  o[k] = hi;
+  o[K + k] = lo;
+  o[2 * K + k] = hi;
+}
+
+__global__ void __launch_bounds__(256) time_tanh_kernel(const long long* __restrict__ vmask, const float* __restrict__ w1,
+                                                        const float* __restrict__ b1, float* __restrict__ out, int B, int T, int E) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * T) return;
+  const int b = warp / T, t = warp - b * T;
+  int n = 0;
+  for (int i = lane; i < T; i += 32) n += (vmask[static_cast<long long>(b) * T + i] != 0);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  float g = 0.f;
+  if (t < n) {
+    float lin = 0.f;
+    if (n > 1) {  // torch.linspace(0, 1, n) in fp32: two-sided formula around the midpoint
+      const float step = __fdiv_rn(1.0f, static_cast<float>(n - 1));
+      lin = (t < n / 2) ? __fmul_rn(step, static_cast<float>(t)) : __fsub_rn(1.0f, __fmul_rn(step, static_cast<float>(n - t - 1)));
+    }
+    g = __fmul_rn(__fsub_rn(lin, 0.5f), 2.0f);
+  }
+  float* o = out + static_cast<long long>(warp) * E;
+  for (int e = lane; e < E; e += 32) o[e] = tanhf(fmaf(w1[e], g, b1[e]));
+}
+
+// E = 512 fixed by the reference (modeling.py:26); generic in E % 128 == 0, E <= 1024 (<= 8 float4 per lane).
+__global__ void __launch_bounds__(256) moment_base_kernel(const float* __restrict__ vlin, const float* __restrict__ lnw,
+                                                          const float* __restrict__ lnb, const float* __restrict__ that,
+                                                          const float* __restrict__ asr_lin, const float* __restrict__ temporal,
+                                                          float* __restrict__ base, int B, int T, int E) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * T) return;
+  const int b = warp / T;
+  const int nv = E >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(vlin + static_cast<long long>(warp) * E);
+  float4 v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) { v[i] = x4[idx]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(E);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+      ss += a * a + c * c + d * d + e * e;
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(ss) / static_cast<float>(E) + 1e-12f);
+  const float4* w4 = reinterpret_cast<const float4*>(lnw);
+  const float4* b4 = reinterpret_cast<const float4*>(lnb);
+  const float4* t4 = reinterpret_cast<const float4*>(that + static_cast<long long>(b) * E);
+  const float4* a4 = reinterpret_cast<const float4*>(asr_lin + static_cast<long long>(warp) * E);
+  const float4* p4 = reinterpret_cast<const float4*>(temporal + static_cast<long long>(warp) * E);
+  float4* o4 = reinterpret_cast<float4*>(base + static_cast<long long>(warp) * E);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float4 w = w4[idx], bb = b4[idx], th = t4[idx], a = a4[idx], p = p4[idx];
+      float4 o;
+      o.x = (w.x * ((v[i].x - mean) * rstd) + bb.x) * th.x + a.x + p.x;
+      o.y = (w.y * ((v[i].y - mean) * rstd) + bb.y) * th.y + a.y + p.y;
+      o.z = (w.z * ((v[i].z - mean) * rstd) + bb.z) * th.z + a.z + p.z;
+      o.w = (w.w * ((v[i].w - mean) * rstd) + bb.w) * th.w + a.w + p.w;
+      o4[idx] = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) moment_embed_kernel(const float* __restrict__ base, const float* __restrict__ bemb,
+                                                           const float* __restrict__ memb, const long long* __restrict__ bm,
+                                                           const long long* __restrict__ mm, float* __restrict__ f, long long rows,
+                                                           int E) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int nv = E >> 2;
+  if (t >= rows * nv) return;
+  const long long r = t / nv;
+  const int i = static_cast<int>(t - r * nv);
+  float4 v = reinterpret_cast<const float4*>(base)[t];
+  if (bm != nullptr) {
+    const float4 e = reinterpret_cast<const float4*>(bemb + (bm[r] != 0 ? E : 0))[i];
+    v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+  }
+  const float4 e = reinterpret_cast<const float4*>(memb + (mm[r] != 0 ? E : 0))[i];
+  v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w;
+  reinterpret_cast<float4*>(f)[t] = v;
+}
+
+__global__ void __launch_bounds__(256) moment_heads_kernel(const float* __restrict__ feats, const float* __restrict__ w3,
+                                                           const float* __restrict__ b3, float* __restrict__ logits, long long rows,
+                                                           int Hd) {
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* x = feats + warp * Hd;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int k = lane; k < Hd; k += 32) {
+    const float v = x[k];
+    a0 = fmaf(v, w3[k], a0);
+    a1 = fmaf(v, w3[Hd + k], a1);
+    a2 = fmaf(v, w3[2 * Hd + k], a2);
+  }
+  a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2);
+  if (lane == 0) {
+    logits[warp * 3 + 0] = a0 + b3[0];
+    logits[warp * 3 + 1] = a1 + b3[1];
+    logits[warp * 3 + 2] = a2 + b3[2];
+  }
+}
+
+// one warp per (sample, head): first-max argmax over T with the -1e10 fill on padded frames
+__global__ void __launch_bounds__(64) mr_argmax_kernel(const float* __restrict__ logits, const long long* __restrict__ vmask,
+                                                       long long* __restrict__ pred, int B, int T) {
+  const int b = blockIdx.x, which = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int t = lane; t < T; t += 32) {
+    float v = logits[(static_cast<long long>(b) * T + t) * 3 + which];
+    if (vmask[static_cast<long long>(b) * T + t] == 0) v = -1e10f;
+    if (v > best) { best = v; arg = t; }  // ascending t per lane: keeps the first maximum
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  if (lane == 0) pred[b * 2 + which] = arg;
+}
+
+__global__ void __launch_bounds__(256) ms_step_kernel(const float* __restrict__ logits, long long* __restrict__ moment_mask,
+                                                      long long* __restrict__ boundary_mask, int* __restrict__ steps,
+                                                      int* __restrict__ nsteps, int max_steps, int T, double threshold,
+                                                      float* __restrict__ probs_out) {
+  extern __shared__ float sp[];  // [T] probabilities
+  __shared__ float red[8];
+  __shared__ int redi[8];
+  __shared__ int bounds[2];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  long long* mm = moment_mask + static_cast<long long>(b) * T;
+  long long* bm = boundary_mask + static_cast<long long>(b) * T;
+  // masked logits and their maximum
+  float best = -INFINITY;
+  for (int t = tid; t < T; t += 256) {
+    float v = logits[(static_cast<long long>(b) * T + t) * 3 + 2];
+    if (mm[t] == 0) v = -FLT_MAX;
+    sp[t] = v;
+    best = fmaxf(best, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if (lane == 0) red[warp] = best;
+  __syncthreads();
+  best = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) best = fmaxf(best, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int t = tid; t < T; t += 256) {
+    const float e = expf(sp[t] - best);
+    sp[t] = e;
+    s += e;
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  __syncthreads();
+  // probabilities and their FIRST maximum (torch.argmax on the softmax output, modeling.py:397)
+  float pbest = -1.f;
+  int arg = 0x7fffffff;
+  for (int t = tid; t < T; t += 256) {
+    const float pr = sp[t] / tot;
+    sp[t] = pr;
+    if (probs_out != nullptr) probs_out[static_cast<long long>(b) * T + t] = pr;
+    if (pr > pbest) { pbest = pr; arg = t; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, pbest, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob > pbest || (ob == pbest && oa < arg)) { pbest = ob; arg = oa; }
+  }
+  if (lane == 0) { red[warp] = pbest; redi[warp] = arg; }
+  __syncthreads();
+  pbest = red[0]; arg = redi[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) {
+    if (red[w] > pbest || (red[w] == pbest && redi[w] < arg)) { pbest = red[w]; arg = redi[w]; }
+  }
+  if (tid == 0) {
+    const double mx = static_cast<double>(sp[arg]);
+    int l = arg, r = arg;
+    bool accept = !(mx < 0.00001);
+    if (accept) {
+      while (static_cast<double>(sp[l]) / mx > threshold) { if (l == 0) break; --l; }
+      while (static_cast<double>(sp[r]) / mx > threshold) { if (r == T - 1) break; ++r; }
+      if (l == 0 || r == 0) accept = false;
+    }
+    bounds[0] = accept ? l : -1;
+    bounds[1] = r;
+    if (accept) {
+      const int k = nsteps[b];
+      if (k < max_steps) { steps[(b * max_steps + k) * 2] = l; steps[(b * max_steps + k) * 2 + 1] = r; nsteps[b] = k + 1; }
+    }
+  }
+  __syncthreads();
+  const int l = bounds[0], r = bounds[1];
+  if (l >= 0) {
+    for (int t = l + tid; t <= r; t += 256) mm[t] = 0;
+    if (tid == 0) { bm[l] = 1; bm[r] = 1; }
+  }
+}
+
+__global__ void __launch_bounds__(256) trim_feats_kernel(const float* __restrict__ x, const long long* __restrict__ mask,
+                                                         float* __restrict__ out, int T, int C, int F) {
+  __shared__ int src[64];  // source frame of each output slot (F <= 64)
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int t = 0; t < T; ++t) n += (mask[static_cast<long long>(b) * T + t] == 1);
+    // k-th selected frame -> slots [(k*F)/n, ((k+1)*F)/n) when n <= F, else the first F selected frames
+    int k = 0;
+    for (int j = 0; j < F; ++j) src[j] = -1;
+    for (int t = 0; t < T; ++t) {
+      if (mask[static_cast<long long>(b) * T + t] != 1) continue;
+      if (n > F) { if (k < F) src[k] = t; }
+      else { for (int j = (k * F) / n; j < ((k + 1) * F) / n; ++j) src[j] = t; }
+      ++k;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < F * C; i += 256) {
+    const int j = i / C, c = i - j * C;
+    const int t = src[j];
+    out[(static_cast<long long>(b) * F + j) * C + c] = (t >= 0) ? x[(static_cast<long long>(b) * T + t) * C + c] : 0.f;
+  }
+}
+
+inline unsigned nblocks(long long n, int per) { return static_cast<unsigned>((n + per - 1) / per); }
+
+}  // namespace
+
+int split3_act_launch(const float* x, __nv_bfloat16* out, long long rows, int K, int gelu, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  split3_act_kernel<<<nblocks(rows * K, 256), 256, 0, s>>>(x, out, rows, K, gelu);
+  return static_cast<int>(cudaGetLastError());
+}
+int split3_weight_launch(const float* w, __nv_bfloat16* out, int N, int K, cudaStream_t s) {
+  split3_weight_kernel<<<nblocks(static_cast<long long>(N) * K, 256), 256, 0, s>>>(w, out, N, K);
+  return static_cast<int>(cudaGetLastError());
+}
+int time_tanh_launch(const long long* video_mask, const float* w1, const float* b1, float* out, int B, int T, int E,
+                     cudaStream_t s) {
+  time_tanh_kernel<<<nblocks(static_cast<long long>(B) * T, 8), 256, 0, s>>>(video_mask, w1, b1, out, B, T, E);
+  return static_cast<int>(cudaGetLastError());
+}
+int moment_base_launch(const float* vlin, const float* lnw, const float* lnb, const float* that, const float* asr_lin,
+                       const float* temporal, float* base, int B, int T, int E, cudaStream_t s) {
+  if (E % 4 != 0 || E > 1024) return -7;
+  moment_base_kernel<<<nblocks(static_cast<long long>(B) * T, 8), 256, 0, s>>>(vlin, lnw, lnb, that, asr_lin, temporal, base, B, T, E);
+  return static_cast<int>(cudaGetLastError());
+}
+int moment_embed_launch(const float* base, const float* bemb, const float* memb, const long long* bm, const long long* mm,
+                        float* f, long long rows, int E, cudaStream_t s) {
+  if (E % 4 != 0) return -7;
+  moment_embed_kernel<<<nblocks(rows * (E / 4), 256), 256, 0, s>>>(base, bemb, memb, bm, mm, f, rows, E);
+  return static_cast<int>(cudaGetLastError());
+}
+int moment_heads_launch(const float* feats, const float* w3, const float* b3, float* logits, long long rows, int Hd,
+                        cudaStream_t s) {
+  moment_heads_kernel<<<nblocks(rows, 8), 256, 0, s>>>(feats, w3, b3, logits, rows, Hd);
+  return static_cast<int>(cudaGetLastError());
+}
+int mr_argmax_launch(const float* logits, const long long* vmask, long long* pred, int B, int T, cudaStream_t s) {
+  mr_argmax_kernel<<<B, 64, 0, s>>>(logits, vmask, pred, B, T);
+  return static_cast<int>(cudaGetLastError());
+}
+int ms_step_launch(const float* logits, long long* moment_mask, long long* boundary_mask, int* steps, int* nsteps, int max_steps,
+                   int B, int T, double threshold, float* probs_out, cudaStream_t s) {
+  if (T > 8192) return -7;
+  ms_step_kernel<<<B, 256, static_cast<size_t>(T) * 4, s>>>(logits, moment_mask, boundary_mask, steps, nsteps, max_steps, T,
+                                                             threshold, probs_out);
+  return static_cast<int>(cudaGetLastError());
+}
+int trim_feats_launch(const float* x, const long long* mask, float* out, int B, int T, int C, int F, cudaStream_t s) {
+  if (F > 64) return -7;
+  trim_feats_kernel<<<B, 256, 0, s>>>(x, mask, out, T, C, F);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace hb

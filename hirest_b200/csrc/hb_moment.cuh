@@ -1,0 +1,40 @@
+// hb_moment.cuh — row kernels of the MomentModel path (implementation in hb_moment.cu).
+// Reference: modeling.py:155-224 (shared encoder + heads), :272-310 (MR decode), :353-474 (MS decode), :529-554 (trim).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace hb {
+
+// fp32 rows [R, K] -> bf16 [R, 3K] = [lo | hi | hi] (activation side of the ~fp32-accurate split GEMM; the weight side is
+// [hi | lo | hi], so A'.W'^T = lo.hi + hi.lo + hi.hi, smallest terms first).  gelu != 0 applies erf-GELU first.
+int split3_act_launch(const float* x, __nv_bfloat16* out, long long rows, int K, int gelu, cudaStream_t s);
+// weight repack for the split GEMM: fp32 [N, K] -> bf16 [N, 3K] = [hi | lo | hi]
+int split3_weight_launch(const float* w, __nv_bfloat16* out, int N, int K, cudaStream_t s);
+
+// h1[b,t,:] = tanh(w1 * g(b,t) + b1), g = the reference's time grid (modeling.py:178-193): (linspace(0,1,n_b)[t]-0.5)*2 for
+// t < n_b (torch.linspace's fp32 two-sided formula), 0 for padding.  Output fp32 [B*T, E].
+int time_tanh_launch(const long long* video_mask, const float* w1, const float* b1, float* out, int B, int T, int E,
+                     cudaStream_t s);
+
+// base[b,t,:] = TF_LN(vlin[b,t,:]; lnw, lnb, 1e-12) * that[b,:] + asr_lin[b,t,:] + temporal[b,t,:]   (modeling.py:161-196)
+int moment_base_launch(const float* vlin, const float* lnw, const float* lnb, const float* that, const float* asr_lin,
+                       const float* temporal, float* base, int B, int T, int E, cudaStream_t s);
+// f[b,t,:] = base + boundary_embed[bm[b,t]] (if bm) + mask_embed[mm[b,t]]                              (modeling.py:171-199)
+int moment_embed_launch(const float* base, const float* bemb, const float* memb, const long long* bm, const long long* mm,
+                        float* f, long long rows, int E, cudaStream_t s);
+// logits[r, j] = feats[r,:] . w[j,:] + b[j], j < 3 (start, end, segment), fp32 (modeling.py:218-219,319)
+int moment_heads_launch(const float* feats, const float* w3, const float* b3, float* logits, long long rows, int Hd,
+                        cudaStream_t s);
+// MR decode (modeling.py:294-298): logits[vmask==0] = -1e10; argmax over T for start / end -> pred int64 [B,2]
+int mr_argmax_launch(const float* logits, const long long* vmask, long long* pred, int B, int T, cudaStream_t s);
+// One MS iteration (modeling.py:394-433) per sample on the device: mask to -FLT_MAX outside the moment, softmax over T,
+// argmax, region growing at `threshold` (ratios in double, like the reference's Python floats), then
+// moment_mask[l..r] = 0, boundary_mask[l] = boundary_mask[r] = 1, steps[b, nsteps[b]++] = (l, r).
+int ms_step_launch(const float* logits, long long* moment_mask, long long* boundary_mask, int* steps, int* nsteps,
+                   int max_steps, int B, int T, double threshold, float* probs_out, cudaStream_t s);
+// trim_feats (modeling.py:529-554): frames with mask==1, truncated to F or repeat-padded -> out fp32 [B, F, C]
+int trim_feats_launch(const float* x, const long long* mask, float* out, int B, int T, int C, int F, cudaStream_t s);
+
+}  // namespace hb

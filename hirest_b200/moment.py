@@ -1,0 +1,326 @@
+"""Host-side mirror of the reference's joint model for the inference path (modeling.py:18-632), backed by libhirest_b200.so.
+
+Same surface as the reference for this path: ``MomentModel(n_frames, asr_dim, args)``, ``.test_step(batch, **kwargs)``
+returning ``{'prediction': list}``, ``.freeze_clip()``, ``state_dict()`` with the reference's key layout (``clip_model.*`` plus
+the non-CLIP keys of SURVEY.md Appendix B, so ``HiREST_BEST.pth`` loads with ``strict=False`` exactly as trainer_base.py:128-147
+does).  Batches are the collate dicts of hirest_dataset.py:409-531 (CPU tensors; moved to the model's device here, as
+modeling.py:275-286 does).
+
+Round 1 covers moment retrieval and moment segmentation (shared encoder, heads, both decoders, trim_feats); step captioning
+(beam decoder) and training are not implemented and raise.  No CPU / eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from copy import deepcopy
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from . import _lib
+from .eva_clip import _Engine, _ParamTree
+
+_DEFAULTS = dict(embed_dim=512, hidden=768, heads=12, ffn=3072, max_pos_visual=2048, max_pos_decoder=512, vocab=30522, clip_dim=1024)
+
+
+def _moment_shapes(asr_dim: int, visual_layers: int, decoder_layers: int, d=_DEFAULTS) -> dict:
+    E, Hd, Ff, V, Cd = d["embed_dim"], d["hidden"], d["ffn"], d["vocab"], d["clip_dim"]
+    s = {}
+
+    def lin(n, o, i):
+        s[n + ".weight"] = (o, i)
+        s[n + ".bias"] = (o,)
+
+    def ln(n, k):
+        s[n + ".weight"] = (k,)
+        s[n + ".bias"] = (k,)
+
+    if asr_dim > 0:
+        ln("asr_enc_layer.0", asr_dim)
+        lin("asr_enc_layer.1", E, asr_dim)
+    lin("temporal_embed.0", E, 1)
+    lin("temporal_embed.2", E, E)
+    s["mask_embed.weight"] = (2, E)
+    s["boundary_embed.weight"] = (2, E)
+    for c in ("0", "2"):
+        s[f"moment_conv.{c}.weight"] = (E, E, 3)
+        s[f"moment_conv.{c}.bias"] = (E,)
+    for h in ("start_predictor.0", "end_predictor.0", "segment_predictor.0"):
+        lin(h, 1, Hd)
+    v = "clip4cap_model.visual."
+    lin(v + "embeddings.word_embeddings", Hd, E)
+    s[v + "embeddings.position_embeddings.weight"] = (d["max_pos_visual"], Hd)
+    ln(v + "embeddings.LayerNorm", Hd)
+    for i in range(visual_layers):
+        p = f"{v}encoder.layer.{i}."
+        for n in ("query", "key", "value"):
+            lin(p + "attention.self." + n, Hd, Hd)
+        lin(p + "attention.output.dense", Hd, Hd)
+        ln(p + "attention.output.LayerNorm", Hd)
+        lin(p + "intermediate.dense", Ff, Hd)
+        lin(p + "output.dense", Hd, Ff)
+        ln(p + "output.LayerNorm", Hd)
+    lin(v + "pooler.dense", Hd, Hd)
+    dd = "clip4cap_model.decoder."
+    s[dd + "embeddings.word_embeddings.weight"] = (V, Hd)
+    s[dd + "embeddings.position_embeddings.weight"] = (d["max_pos_decoder"], Hd)
+    ln(dd + "embeddings.LayerNorm", Hd)
+    for i in range(decoder_layers):
+        p = f"{dd}decoder.layer.{i}."
+        for att in ("slf_attn", "enc_attn"):
+            for n in ("query", "key", "value"):
+                lin(f"{p}{att}.att.{n}", Hd, Hd)
+            lin(f"{p}{att}.output.dense", Hd, Hd)
+            ln(f"{p}{att}.output.LayerNorm", Hd)
+        lin(p + "intermediate.dense", Ff, Hd)
+        lin(p + "output.dense", Hd, Ff)
+        ln(p + "output.LayerNorm", Hd)
+    s[dd + "classifier.cls.predictions.bias"] = (V,)
+    lin(dd + "classifier.cls.predictions.transform.dense", Hd, Hd)
+    ln(dd + "classifier.cls.predictions.transform.LayerNorm", Hd)
+    s[dd + "classifier.cls.predictions.decoder.weight"] = (V, Hd)
+    ln("clip4cap_model.normalize_video.visual_norm2d", E)
+    lin("clip_g_map", E, Cd)
+    lin("clip_g_map_text", E, Cd)
+    return s
+
+
+def default_args(**over):
+    """The reference's argparse defaults that this path reads (args.py:51-61)."""
+    a = dict(max_frames_step_captioning=20, max_words=48, visual_num_hidden_layers=2, decoder_num_hidden_layers=2,
+             moment_segmentation_difference_threshold=0.50, moment_segmentation_max_iterations=20, num_beams=5,
+             eva_clip_path="./pretrained_weights/eva_clip_psz14.pt")
+    a.update(over)
+    return SimpleNamespace(**a)
+
+
+class MomentModel(nn.Module):
+    def __init__(self, n_frames=-1, asr_dim=-1, args=None, clip_model=None, max_rows: int = 64 * 300, max_batch: int = 64):
+        super().__init__()
+        self.args = args if args is not None else default_args()
+        self.n_frames = n_frames
+        self.asr_dim = asr_dim
+        self.use_asr = asr_dim > 0
+        if not self.use_asr:
+            raise NotImplementedError("hirest_b200.MomentModel: the ASR-free variant (asr_dim <= 0) is not implemented")
+        vl = getattr(self.args, "visual_num_hidden_layers", 2)
+        dl = getattr(self.args, "decoder_num_hidden_layers", 2)
+        self.visual_layers = vl
+        for head, sub in _split_top(_moment_shapes(asr_dim, vl, dl)).items():
+            self.add_module(head, _ParamTree(sub))
+        # mutate args like the reference does (modeling.py:103-105)
+        self.args.d_model = 512
+        self.args.video_dim = 512
+        self.args.max_frames = getattr(self.args, "max_frames_step_captioning", 20)
+        if clip_model is None:
+            from .eva_clip import build_eva_model_and_transforms
+
+            clip_model, self.clip_preprocess = build_eva_model_and_transforms(
+                "EVA_CLIP_g_14", pretrained=getattr(self.args, "eva_clip_path", "./pretrained_weights/eva_clip_psz14.pt"))
+        self.clip_model = clip_model
+        self.max_rows, self.max_batch = max_rows, max_batch
+        self._engine = None
+        self._engine_key = None
+        self.freeze_clip()
+        self.eval()
+
+    # ------------------------------------------------------------------ reference surface
+    def freeze_clip(self):
+        if isinstance(self.clip_model, nn.Module):
+            for p in self.clip_model.parameters():
+                p.requires_grad = False
+            self.clip_model.eval()
+
+    def train_step(self, batch):
+        raise NotImplementedError("hirest_b200 implements the inference path only (training is out of scope, SURVEY.md §2)")
+
+    def test_step(self, batch, **kwargs):
+        task = batch["tasks"][0]
+        if task == "moment_retrieval":
+            return self.test_moment_retrieval(batch, **kwargs)
+        elif task == "moment_segmentation":
+            return self.test_moment_segmentation(batch, **kwargs)
+        elif task == "step_captioning":
+            raise NotImplementedError("step captioning (beam decoder) is not implemented yet in hirest_b200")
+        else:
+            raise NotImplementedError
+
+    # ------------------------------------------------------------------ engine
+    def _own_params(self):
+        return [p for n, p in self.named_parameters() if not n.startswith("clip_model.")]
+
+    def _device(self):
+        return self.clip_g_map.weight.device
+
+    def _get_engine(self, rows: int, batch: int):
+        ps = self._own_params()
+        key = (self._device(), ps[0].data_ptr(), tuple(q._version for q in ps), self.max_rows, self.max_batch)
+        if self._engine is not None and key == self._engine_key and rows <= self.max_rows and batch <= self.max_batch:
+            return self._engine
+        self.max_rows, self.max_batch = max(self.max_rows, rows), max(self.max_batch, batch)
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("hirest_b200: MomentModel runs on a B200 only; move it to a cuda device (no CPU fallback)")
+        lib = _lib.init(dev.index or 0)
+        sd = {k: v.detach().float().contiguous() for k, v in self.state_dict().items() if not k.startswith("clip_model.")}
+        L = self.visual_layers
+        keep = []
+        head_w = torch.cat([sd["start_predictor.0.weight"], sd["end_predictor.0.weight"], sd["segment_predictor.0.weight"]], 0).contiguous()
+        head_b = torch.cat([sd["start_predictor.0.bias"], sd["end_predictor.0.bias"], sd["segment_predictor.0.bias"]], 0).contiguous()
+        keep += [head_w, head_b]
+
+        def per_layer(fmt):
+            arr = _lib.ptr_array([sd[fmt.format(i)] for i in range(L)])
+            keep.append(arr)
+            return C.cast(arr, C.c_void_p)
+
+        v = "clip4cap_model.visual."
+        e = v + "encoder.layer.{}."
+        w = _lib.HbMomentWeights(
+            sd["asr_enc_layer.0.weight"].data_ptr(), sd["asr_enc_layer.0.bias"].data_ptr(), sd["asr_enc_layer.1.weight"].data_ptr(),
+            sd["asr_enc_layer.1.bias"].data_ptr(), sd["temporal_embed.0.weight"].data_ptr(), sd["temporal_embed.0.bias"].data_ptr(),
+            sd["temporal_embed.2.weight"].data_ptr(), sd["temporal_embed.2.bias"].data_ptr(), sd["mask_embed.weight"].data_ptr(),
+            sd["boundary_embed.weight"].data_ptr(), head_w.data_ptr(), head_b.data_ptr(),
+            sd["clip4cap_model.normalize_video.visual_norm2d.weight"].data_ptr(),
+            sd["clip4cap_model.normalize_video.visual_norm2d.bias"].data_ptr(), sd["clip_g_map.weight"].data_ptr(),
+            sd["clip_g_map.bias"].data_ptr(), sd["clip_g_map_text.weight"].data_ptr(), sd["clip_g_map_text.bias"].data_ptr(),
+            sd[v + "embeddings.word_embeddings.weight"].data_ptr(), sd[v + "embeddings.word_embeddings.bias"].data_ptr(),
+            sd[v + "embeddings.position_embeddings.weight"].data_ptr(), sd[v + "embeddings.LayerNorm.weight"].data_ptr(),
+            sd[v + "embeddings.LayerNorm.bias"].data_ptr(),
+            per_layer(e + "attention.self.query.weight"), per_layer(e + "attention.self.query.bias"),
+            per_layer(e + "attention.self.key.weight"), per_layer(e + "attention.self.key.bias"),
+            per_layer(e + "attention.self.value.weight"), per_layer(e + "attention.self.value.bias"),
+            per_layer(e + "attention.output.dense.weight"), per_layer(e + "attention.output.dense.bias"),
+            per_layer(e + "attention.output.LayerNorm.weight"), per_layer(e + "attention.output.LayerNorm.bias"),
+            per_layer(e + "intermediate.dense.weight"), per_layer(e + "intermediate.dense.bias"),
+            per_layer(e + "output.dense.weight"), per_layer(e + "output.dense.bias"),
+            per_layer(e + "output.LayerNorm.weight"), per_layer(e + "output.LayerNorm.bias"))
+        d = _DEFAULTS
+        cfg = _lib.HbMomentConfig(d["embed_dim"], d["hidden"], d["heads"], d["ffn"], L, self.asr_dim, d["clip_dim"], d["max_pos_visual"])
+        handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(lib.hb_moment_create(C.byref(cfg), C.byref(w), int(self.max_rows), int(self.max_batch), _lib.stream_ptr(dev),
+                                            C.byref(handle)), "hb_moment_create")
+        self._engine = _Engine(handle, lib.hb_moment_destroy)
+        self._engine_key = (self._device(), ps[0].data_ptr(), tuple(q._version for q in ps), self.max_rows, self.max_batch)
+        return self._engine
+
+    @torch.no_grad()
+    def _forward(self, video, text_feat, asr, vmask, mmask, bmask=None, reuse_base=False, want_feats=False):
+        """foward_moment_shared (modeling.py:155-210) + heads -> (logits [B,T,3] = start/end/segment, feats [B,T,768] or None)."""
+        B, T, _ = video.shape
+        eng = self._get_engine(B * T, B)
+        dev = self._device()
+        logits = torch.empty((B, T, 3), dtype=torch.float32, device=dev)
+        feats = torch.empty((B, T, _DEFAULTS["hidden"]), dtype=torch.float32, device=dev) if want_feats else None
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            _lib.check(lib.hb_moment_forward(eng.handle, video.data_ptr(), text_feat.data_ptr(), asr.data_ptr(), vmask.data_ptr(),
+                                             mmask.data_ptr(), bmask.data_ptr() if bmask is not None else None, B, T,
+                                             1 if reuse_base else 0, feats.data_ptr() if want_feats else None, logits.data_ptr(),
+                                             _lib.stream_ptr(dev)), "hb_moment_forward")
+        return logits, feats
+
+    def _inputs(self, batch):
+        dev = self._device()
+        video = batch["vis_feats"].to(dev).float().contiguous()
+        vmask = batch["vis_mask"].to(dev).long().contiguous()
+        asr = batch["asr_feats"].to(dev).float().contiguous()
+        text_feat = self.clip_model.encode_text(batch["clip_text_ids"].to(dev)).float().contiguous()
+        return video, vmask, asr, text_feat
+
+    def foward_moment_shared(self, video_feats, text_feat, video_mask=None, moment_mask=None, asr_feats=None, boundary_mask=None):
+        """Same (misspelt) name and argument order as modeling.py:155."""
+        dev = self._device()
+        B, T, _ = video_feats.shape
+        if video_mask is None:
+            video_mask = torch.ones((B, T), dtype=torch.long, device=dev)
+        _, feats = self._forward(video_feats.to(dev).float().contiguous(), text_feat.to(dev).float().contiguous(),
+                                 asr_feats.to(dev).float().contiguous(), video_mask.to(dev).long().contiguous(),
+                                 moment_mask.to(dev).long().contiguous(),
+                                 boundary_mask.to(dev).long().contiguous() if boundary_mask is not None else None, want_feats=True)
+        return feats
+
+    @torch.no_grad()
+    def test_moment_retrieval(self, batch, **kwargs):
+        """modeling.py:272-310."""
+        dev = self._device()
+        video, vmask, asr, text_feat = self._inputs(batch)
+        mmask = batch["moment_mask"].to(dev).long().contiguous()
+        logits, _ = self._forward(video, text_feat, asr, vmask, mmask)
+        B, T = vmask.shape
+        pred = torch.empty((B, 2), dtype=torch.int64, device=dev)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            _lib.check(lib.hb_moment_mr_decode(logits.data_ptr(), vmask.data_ptr(), pred.data_ptr(), B, T, _lib.stream_ptr(dev)),
+                       "hb_moment_mr_decode")
+        return {"prediction": pred.tolist()}
+
+    @torch.no_grad()
+    def test_moment_segmentation(self, batch, threshold=0.15, **kwargs):
+        """modeling.py:353-474: <= 20 shared forwards, each followed by the on-device region-growing step; one D2H at the end."""
+        dev = self._device()
+        video, vmask, asr, text_feat = self._inputs(batch)
+        B, T = vmask.shape
+        starts = batch["moment_bound_frames"][:, 0].tolist()
+        lasts = batch["moment_bound_frames"][:, 1].tolist()
+        idx = torch.arange(T)[None, :]
+        b0 = batch["moment_bound_frames"][:, :1].cpu()
+        b1 = batch["moment_bound_frames"][:, 1:2].cpu()
+        mmask = ((idx >= b0) & (idx <= b1)).long().to(dev).contiguous()       # :376-378
+        bmask = (idx == b0).long().to(dev).contiguous()                       # :380-382
+        n_iter = self.args.moment_segmentation_max_iterations
+        thr = float(self.args.moment_segmentation_difference_threshold)
+        steps = torch.zeros((B, n_iter, 2), dtype=torch.int32, device=dev)
+        nsteps = torch.zeros((B,), dtype=torch.int32, device=dev)
+        lib = _lib.load()
+        for it in range(n_iter):
+            logits, _ = self._forward(video, text_feat, asr, vmask, mmask, bmask, reuse_base=(it > 0))
+            with torch.cuda.device(dev):
+                _lib.check(lib.hb_moment_ms_step(logits.data_ptr(), mmask.data_ptr(), bmask.data_ptr(), steps.data_ptr(),
+                                                 nsteps.data_ptr(), n_iter, B, T, thr, None, _lib.stream_ptr(dev)), "hb_moment_ms_step")
+        steps_h, n_h = steps.cpu().tolist(), nsteps.cpu().tolist()
+        preds = []
+        for b in range(B):
+            sp = [[starts[b], starts[b]]] + [list(x) for x in steps_h[b][:n_h[b]]]
+            preds.append(_postprocess_steps(sp, lasts[b]))
+        return {"raw_predictions": deepcopy(preds), "prediction": preds}
+
+    @torch.no_grad()
+    def trim_feats(self, visual_output, moment_mask, B=None, device=None):
+        """modeling.py:529-554 on the device."""
+        dev = self._device()
+        x = visual_output.to(dev).float().contiguous()
+        mk = moment_mask.to(dev).long().contiguous()
+        Bx, T, Cc = x.shape
+        F = self.args.max_frames
+        out = torch.empty((Bx, F, Cc), dtype=torch.float32, device=dev)
+        lib = _lib.init(dev.index or 0)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hb_trim_feats(x.data_ptr(), mk.data_ptr(), out.data_ptr(), Bx, T, Cc, F, _lib.stream_ptr(dev)), "hb_trim_feats")
+        return out
+
+
+def _split_top(shapes: dict) -> dict:
+    out = {}
+    for name, shape in shapes.items():
+        head, _, rest = name.partition(".")
+        out.setdefault(head, {})[rest] = shape
+    return out
+
+
+def _postprocess_steps(steps, last_bound):
+    """Host post-processing of modeling.py:435-463 (sort, flatten, drop values past the moment end, unique, min gap of 5)."""
+    steps = sorted(steps + [[last_bound, last_bound]], key=lambda x: x[0])
+    flat = [v for pair in steps for v in pair]
+    while flat[-1] > last_bound:
+        flat.pop(-1)
+    flat = sorted(set(flat))
+    out = [flat[0]]
+    cur = flat[0]
+    for i in range(1, len(flat) - 1):
+        if flat[i] - cur >= 5:
+            out.append(flat[i])
+            cur = flat[i]
+    return out

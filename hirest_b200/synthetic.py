@@ -154,3 +154,98 @@ def encode_image_flops(cfg) -> float:
     per_layer = 2.0 * T * D * 3 * D + 2.0 * 2 * T * T * D + 2.0 * T * D * D + 2.0 * 2 * T * D * Fh
     head = 2.0 * D * cfg["embed_dim"]
     return patch + L * per_layer + head
+
+
+# ---------------------------------------------------------------------------------------------------
+# MomentModel (modeling.py:18-123) non-CLIP parameters, reference state_dict layout
+# ---------------------------------------------------------------------------------------------------
+MOMENT_CFG = {"embed_dim": 512, "hidden": 768, "heads": 12, "ffn": 3072, "visual_layers": 2, "decoder_layers": 2,
+              "max_pos_visual": 2048, "max_pos_decoder": 512, "vocab": 30522, "asr_dim": 384, "clip_dim": 1024,
+              "max_frames_caption": 20, "max_words": 48}
+
+
+def make_moment_state_dict(seed: int = 3, device="cpu", cfg: dict = MOMENT_CFG) -> "OrderedDict[str, torch.Tensor]":
+    """Seeded weights for every non-CLIP parameter of the reference MomentModel (same keys / shapes; the tied decoder
+    classifier weight is the word-embedding tensor itself, clip4caption/modules/modeling.py:121-123,137)."""
+    g = _generator(seed, device)
+    E, Hd, Ff, A, Cd, V = cfg["embed_dim"], cfg["hidden"], cfg["ffn"], cfg["asr_dim"], cfg["clip_dim"], cfg["vocab"]
+    sd = OrderedDict()
+
+    def lin(name, out_f, in_f, std=0.03, bias=True):
+        sd[name + ".weight"] = _normal(g, (out_f, in_f), std)
+        if bias:
+            sd[name + ".bias"] = _normal(g, (out_f,), 0.02)
+
+    def ln(name, dim):
+        sd[name + ".weight"] = 1.0 + _normal(g, (dim,), 0.05)
+        sd[name + ".bias"] = _normal(g, (dim,), 0.02)
+
+    ln("asr_enc_layer.0", A)
+    lin("asr_enc_layer.1", E, A)
+    lin("temporal_embed.0", E, 1, std=1.0)
+    lin("temporal_embed.2", E, E)
+    sd["mask_embed.weight"] = _normal(g, (2, E), 0.5)
+    sd["boundary_embed.weight"] = _normal(g, (2, E), 0.5)
+    sd["moment_conv.0.weight"] = _normal(g, (E, E, 3), 0.02)   # dead parameters (modeling.py:60-74), kept for layout
+    sd["moment_conv.0.bias"] = _normal(g, (E,), 0.02)
+    sd["moment_conv.2.weight"] = _normal(g, (E, E, 3), 0.02)
+    sd["moment_conv.2.bias"] = _normal(g, (E,), 0.02)
+    for h in ("start_predictor.0", "end_predictor.0", "segment_predictor.0"):
+        lin(h, 1, Hd, std=0.08)
+    v = "clip4cap_model.visual."
+    lin(v + "embeddings.word_embeddings", Hd, E)
+    sd[v + "embeddings.position_embeddings.weight"] = _normal(g, (cfg["max_pos_visual"], Hd), 0.02)
+    ln(v + "embeddings.LayerNorm", Hd)
+    for i in range(cfg["visual_layers"]):
+        p = f"{v}encoder.layer.{i}."
+        for n in ("query", "key", "value"):
+            lin(p + "attention.self." + n, Hd, Hd)
+        lin(p + "attention.output.dense", Hd, Hd)
+        ln(p + "attention.output.LayerNorm", Hd)
+        lin(p + "intermediate.dense", Ff, Hd)
+        lin(p + "output.dense", Hd, Ff)
+        ln(p + "output.LayerNorm", Hd)
+    lin(v + "pooler.dense", Hd, Hd)   # dead (module_visual.py:421), kept for layout
+    d = "clip4cap_model.decoder."
+    sd[d + "embeddings.word_embeddings.weight"] = _normal(g, (V, Hd), 0.03)
+    sd[d + "embeddings.position_embeddings.weight"] = _normal(g, (cfg["max_pos_decoder"], Hd), 0.02)
+    ln(d + "embeddings.LayerNorm", Hd)
+    for i in range(cfg["decoder_layers"]):
+        p = f"{d}decoder.layer.{i}."
+        for att in ("slf_attn", "enc_attn"):
+            for n in ("query", "key", "value"):
+                lin(f"{p}{att}.att.{n}", Hd, Hd)
+            lin(f"{p}{att}.output.dense", Hd, Hd)
+            ln(f"{p}{att}.output.LayerNorm", Hd)
+        lin(p + "intermediate.dense", Ff, Hd)
+        lin(p + "output.dense", Hd, Ff)
+        ln(p + "output.LayerNorm", Hd)
+    sd[d + "classifier.cls.predictions.bias"] = _normal(g, (V,), 0.02)
+    lin(d + "classifier.cls.predictions.transform.dense", Hd, Hd)
+    ln(d + "classifier.cls.predictions.transform.LayerNorm", Hd)
+    sd[d + "classifier.cls.predictions.decoder.weight"] = sd[d + "embeddings.word_embeddings.weight"]
+    ln("clip4cap_model.normalize_video.visual_norm2d", E)
+    lin("clip_g_map", E, Cd)
+    lin("clip_g_map_text", E, Cd)
+    return sd
+
+
+def make_moment_batch(B: int, T: int, seed: int = 5, ragged: bool = True, cfg: dict = MOMENT_CFG):
+    """Synthetic collate output (hirest_dataset.py:409-531): unit-norm frame features (extract_features.py:64), ASR
+    features, masks, moment bounds; plus fixed stand-in text features [B, 1024] (what encode_text would return)."""
+    g = torch.Generator().manual_seed(seed)
+    vis = torch.randn((B, T, cfg["clip_dim"]), generator=g)
+    vis = vis / vis.norm(dim=-1, keepdim=True)
+    asr = torch.randn((B, T, cfg["asr_dim"]), generator=g)
+    n = torch.full((B,), T, dtype=torch.int64)
+    if ragged and B > 1:
+        n[1:] = torch.randint(max(8, T // 2), T + 1, (B - 1,), generator=g)
+    vis_mask = (torch.arange(T)[None, :] < n[:, None]).long()
+    vis = vis * vis_mask[..., None]
+    asr = asr * vis_mask[..., None]
+    bounds = torch.stack([torch.div(n, 8, rounding_mode="floor") + 1, n - torch.div(n, 8, rounding_mode="floor") - 2], dim=1)
+    moment_mask = ((torch.arange(T)[None, :] >= bounds[:, :1]) & (torch.arange(T)[None, :] <= bounds[:, 1:])).long()
+    text_feat = torch.randn((B, cfg["clip_dim"]), generator=g)
+    return {"vis_feats": vis, "vis_mask": vis_mask, "asr_feats": asr, "moment_mask": moment_mask,
+            "moment_bound_frames": bounds, "text_feat": text_feat, "n_frames": n,
+            "clip_text_ids": torch.zeros((B, 77), dtype=torch.int64)}

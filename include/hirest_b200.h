@@ -130,6 +130,56 @@ HB_API int hb_text_create(const HbTextConfig* cfg, const HbTextWeights* w, int m
 HB_API int hb_text_encode(HbText* m, const int64_t* ids, int64_t Q, float* out, void* stream);
 HB_API void hb_text_destroy(HbText* m);
 
+/* ---- MomentModel shared encoder + heads (modeling.py:155-224, 272-474, 529-554) ----------------------- */
+typedef struct {
+  int embed_dim;  /* 512  (modeling.py:26) */
+  int hidden;     /* 768  (visual_config.json) */
+  int heads;      /* 12, head_dim must be 64 */
+  int ffn;        /* 3072 */
+  int layers;     /* 2    (args.py:53) */
+  int asr_dim;    /* 384 */
+  int clip_dim;   /* 1024 */
+  int max_pos;    /* rows of visual.embeddings.position_embeddings (2048) */
+} HbMomentConfig;
+
+/* fp32 device pointers, reference state_dict tensors. head_w/head_b are the start / end / segment
+ * predictors stacked to [3, hidden] / [3]. Per-layer members: host arrays of `layers` device pointers. */
+typedef struct {
+  const float* asr_ln_w; const float* asr_ln_b; const float* asr_w; const float* asr_b;
+  const float* temp_w1; const float* temp_b1; const float* temp_w2; const float* temp_b2;
+  const float* mask_embed; const float* boundary_embed;
+  const float* head_w; const float* head_b;
+  const float* vis_norm_w; const float* vis_norm_b;
+  const float* clip_g_map_w; const float* clip_g_map_b; const float* clip_g_map_text_w; const float* clip_g_map_text_b;
+  const float* emb_w; const float* emb_b; const float* pos_emb; const float* emb_ln_w; const float* emb_ln_b;
+  const float* const* q_w; const float* const* q_b; const float* const* k_w; const float* const* k_b;
+  const float* const* v_w; const float* const* v_b; const float* const* ao_w; const float* const* ao_b;
+  const float* const* ao_ln_w; const float* const* ao_ln_b; const float* const* i_w; const float* const* i_b;
+  const float* const* o_w; const float* const* o_b; const float* const* o_ln_w; const float* const* o_ln_b;
+} HbMomentWeights;
+
+typedef struct HbMoment HbMoment;
+HB_API int hb_moment_create(const HbMomentConfig* cfg, const HbMomentWeights* w, int64_t max_rows, int max_batch, void* stream,
+                            HbMoment** out);
+#define HB_MOMENT_REUSE_BASE 1 /* video/text/asr/time terms unchanged since the previous call (segmentation iterations) */
+/* foward_moment_shared + the three 768->1 heads.  video fp32 [B,T,clip_dim]; text_feat fp32 [B,clip_dim] (encode_text
+ * output); asr fp32 [B,T,asr_dim]; masks int64 [B,T] (boundary_mask may be NULL, as in moment retrieval).
+ * out_feats fp32 [B,T,hidden] (may be NULL); out_logits fp32 [B,T,3] = (start, end, segment).  All GEMMs run as 3-term
+ * split-bf16 tcgen05 GEMMs (fp32-accurate) and attention in fp32, so that the integer outputs of the MR / MS decoders
+ * match the fp32 reference.  T <= 400 and T <= max_pos. */
+HB_API int hb_moment_forward(HbMoment* m, const float* video, const float* text_feat, const float* asr,
+                             const int64_t* video_mask, const int64_t* moment_mask, const int64_t* boundary_mask, int B, int T,
+                             int flags, float* out_feats, float* out_logits, void* stream);
+HB_API void hb_moment_destroy(HbMoment* m);
+/* MR decode (modeling.py:294-298): pred int64 [B,2] = argmax of start / end logits with -1e10 on padded frames. */
+HB_API int hb_moment_mr_decode(const float* logits, const int64_t* video_mask, int64_t* pred, int B, int T, void* stream);
+/* One MS iteration (modeling.py:394-433) on the device; masks updated in place; steps int32 [B,max_steps,2],
+ * nsteps int32 [B]; probs_out fp32 [B,T] optional. */
+HB_API int hb_moment_ms_step(const float* logits, int64_t* moment_mask, int64_t* boundary_mask, int32_t* steps, int32_t* nsteps,
+                             int max_steps, int B, int T, double threshold, float* probs_out, void* stream);
+/* trim_feats (modeling.py:529-554): x fp32 [B,T,C], mask int64 [B,T] -> out fp32 [B,F,C]. */
+HB_API int hb_trim_feats(const float* x, const int64_t* mask, float* out, int B, int T, int C, int F, void* stream);
+
 /* ---- retrieval scoring ------------------------------------------------------------------------ */
 /* out[v,:] = l2norm(mean_f emb[v,f,:]); emb fp32 [V,F,E]; out fp32 [V,E].  F = 1 gives plain L2 normalise. */
 HB_API int hb_pool_normalize(const float* emb, int64_t V, int F, int E, float* out, void* stream);

@@ -1,0 +1,152 @@
+"""MomentModel (shared encoder + MR / MS decoders + trim_feats) on the GPU vs the reference-generated golden and the CPU oracle.
+
+The GEMMs run as 3-term split-bf16 tcgen05 GEMMs and attention in fp32, so the bar is: features / logits within 2e-4 relative
+of the fp32 reference, and the INTEGER outputs (MR [start, end], MS boundary lists, trimmed frame selection) identical."""
+import os
+
+import pytest
+import torch
+
+from hirest_b200 import _lib, moment, synthetic
+from oracle import moment_oracle as mo
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+CASES = {"small": (3, 40, 5), "t300": (2, 300, 6)}
+
+
+class FixedText:
+    """Stands in for clip_model: encode_text returns the batch's fixed text features (as oracle/make_golden_moment.py does)."""
+
+    def __init__(self):
+        self.feat = None
+
+    def encode_text(self, ids):
+        return self.feat.to(ids.device)
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.fixture(scope="module")
+def model(hb):
+    clip = FixedText()
+    m = moment.MomentModel(-1, 384, moment.default_args(), clip_model=clip, max_rows=1024, max_batch=8)
+    m.load_state_dict(synthetic.make_moment_state_dict(seed=3), strict=True)
+    return m.to(DEV), clip
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return torch.load(os.path.join(golden_dir, "moment.pt"))
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_shared_encoder_and_logits(model, golden, case):
+    m, clip = model
+    B, T, seed = CASES[case]
+    b = synthetic.make_moment_batch(B, T, seed=seed)
+    g = golden[case]
+    feats = m.foward_moment_shared(b["vis_feats"], b["text_feat"], b["vis_mask"], moment_mask=b["moment_mask"], asr_feats=b["asr_feats"])
+    ref = g["shared"]
+    got = feats.cpu() if case == "small" else feats.cpu()[:, :8]
+    assert rel(got, ref) < 2e-4
+    logits, _ = m._forward(b["vis_feats"].to(DEV), b["text_feat"].to(DEV), b["asr_feats"].to(DEV), b["vis_mask"].to(DEV),
+                           b["moment_mask"].to(DEV))
+    assert float((logits[..., 0].cpu() - g["start_logits"]).abs().max()) < 2e-3
+    assert float((logits[..., 1].cpu() - g["end_logits"]).abs().max()) < 2e-3
+    bm = torch.zeros_like(b["moment_mask"])
+    bm[:, 3] = 1
+    logits, _ = m._forward(b["vis_feats"].to(DEV), b["text_feat"].to(DEV), b["asr_feats"].to(DEV), b["vis_mask"].to(DEV),
+                           b["moment_mask"].to(DEV), bm.to(DEV))
+    assert float((logits[..., 2].cpu() - g["ms_logits"]).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_moment_retrieval_and_segmentation_predictions_match_reference(model, golden, case):
+    m, clip = model
+    B, T, seed = CASES[case]
+    b = synthetic.make_moment_batch(B, T, seed=seed)
+    clip.feat = b["text_feat"]
+    b["tasks"] = ["moment_retrieval"] * B
+    assert m.test_step(b)["prediction"] == golden[case]["mr_pred"]
+    b["tasks"] = ["moment_segmentation"] * B
+    out = m.test_step(b)
+    assert out["prediction"] == golden[case]["ms_pred"]
+    assert out["raw_predictions"] == out["prediction"]
+
+
+def test_ms_step_kernel_matches_reference_control_flow(hb):
+    """The on-device region growing (modeling.py:399-433) against the verbatim Python restatement, incl. edge cases."""
+    g = torch.Generator().manual_seed(0)
+    B, T = 6, 57
+    logits = torch.randn(B, T, 3, generator=g) * 2
+    mm = torch.ones(B, T, dtype=torch.long)
+    mm[0, :10] = 0
+    mm[1, 20:] = 0
+    mm[2] = 0                      # empty moment: uniform softmax over -FLT_MAX -> max prob 1/T, accepted unless l == 0
+    logits[3, 0, 2] = 50.0         # peak at frame 0 -> left bound 0 -> rejected (modeling.py:425-426)
+    logits[4, :, 2] = 0.0          # flat -> grows to both ends
+    bm = torch.zeros(B, T, dtype=torch.long)
+    mm_d, bm_d = mm.to(DEV), bm.to(DEV)
+    steps = torch.zeros(B, 4, 2, dtype=torch.int32, device=DEV)
+    ns = torch.zeros(B, dtype=torch.int32, device=DEV)
+    probs = torch.empty(B, T, device=DEV)
+    _lib.check(hb.hb_moment_ms_step(logits.to(DEV).data_ptr(), mm_d.data_ptr(), bm_d.data_ptr(), steps.data_ptr(), ns.data_ptr(), 4,
+                                    B, T, 0.5, probs.data_ptr(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    lg = logits[..., 2].clone()
+    lg[mm == 0] = -torch.finfo(torch.float32).max
+    ref_p = lg.softmax(dim=1)
+    assert float((probs.cpu() - ref_p).abs().max()) < 1e-6
+    for b in range(B):
+        sc = ref_p[b].tolist()
+        mi = int(ref_p[b].argmax())
+        exp_mm, exp_bm, exp_steps = mm[b].clone(), bm[b].clone(), []
+        if not sc[mi] < 0.00001:
+            l, r = mo.grow_region(sc, mi, 0.5)
+            if not (l == 0 or r == 0):
+                exp_mm[l:r + 1] = 0
+                exp_bm[l] = 1
+                exp_bm[r] = 1
+                exp_steps = [[l, r]]
+        assert torch.equal(mm_d[b].cpu(), exp_mm) and torch.equal(bm_d[b].cpu(), exp_bm), b
+        assert steps[b, :int(ns[b])].cpu().tolist() == exp_steps, b
+
+
+def test_mr_decode_masks_padded_frames(hb):
+    B, T = 3, 33
+    logits = torch.zeros(B, T, 3)
+    logits[0, 30, 0] = 9.0   # padded frame wins unless masked
+    logits[0, 5, 0] = 1.0
+    logits[1, 7, 1] = 2.0
+    logits[1, 9, 1] = 2.0    # tie -> first index
+    vm = torch.ones(B, T, dtype=torch.long)
+    vm[0, 20:] = 0
+    pred = torch.empty(B, 2, dtype=torch.int64, device=DEV)
+    _lib.check(hb.hb_moment_mr_decode(logits.to(DEV).data_ptr(), vm.to(DEV).data_ptr(), pred.data_ptr(), B, T, _lib.stream_ptr()))
+    lg = logits.clone()
+    lg[vm == 0] = -1e10
+    assert pred.cpu().tolist() == torch.stack([lg[..., 0].argmax(1), lg[..., 1].argmax(1)], -1).tolist()
+
+
+def test_trim_feats(model):
+    m, _ = model
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(4, 50, 768, generator=g)
+    mask = torch.zeros(4, 50, dtype=torch.long)
+    mask[0, 3:10] = 1      # 7 frames  -> repeat-padded to 20
+    mask[1, 0:45] = 1      # 45 frames -> first 20
+    mask[2, 10:30] = 1     # exactly 20
+    mask[3, 7] = 1         # a single frame
+    got = m.trim_feats(x, mask).cpu()
+    assert torch.equal(got, mo.trim_feats(x, mask, 20))
+
+
+def test_rejects_long_clips(model):
+    m, _ = model
+    b = synthetic.make_moment_batch(1, 401, seed=1, ragged=False)
+    with pytest.raises(RuntimeError, match="> 400 frames"):
+        m.foward_moment_shared(b["vis_feats"], b["text_feat"], b["vis_mask"], moment_mask=b["moment_mask"], asr_feats=b["asr_feats"])

@@ -58,3 +58,26 @@ def test_synthetic_tokens_have_eot_as_row_max():
     assert t.shape == (16, 77) and (t[:, 0] == 49406).all()
     am = t.argmax(-1)
     assert (t[torch.arange(16), am] == 49407).all() and (am >= 4).all()
+
+
+def test_moment_model_state_dict_layout_and_errors():
+    from hirest_b200 import moment
+
+    class Stub:
+        def encode_text(self, ids):
+            return None
+
+    m = moment.MomentModel(-1, 384, moment.default_args(), clip_model=Stub())
+    sd = synthetic.make_moment_state_dict(seed=3)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    assert sum(v.numel() for v in sd.values()) == 86_627_901  # 86.63 M state-dict elements
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert m.args.max_frames == 20 and m.args.d_model == 512  # args mutated like modeling.py:103-105
+    with pytest.raises(NotImplementedError):
+        m.train_step({"tasks": ["moment_retrieval"]})
+    with pytest.raises(NotImplementedError):
+        m.test_step({"tasks": ["step_captioning"]})
+    b = synthetic.make_moment_batch(1, 16, seed=1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.foward_moment_shared(b["vis_feats"], b["text_feat"], b["vis_mask"], moment_mask=b["moment_mask"], asr_feats=b["asr_feats"])
