@@ -60,6 +60,19 @@ class HbMomentWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in MOMENT_WEIGHT_FIELDS]
 
 
+class HbDecoderConfig(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("hidden", "heads", "ffn", "layers", "vocab", "max_pos", "max_words", "bos", "eos")]
+
+
+DECODER_WEIGHT_FIELDS = ("word_emb", "pos_emb", "emb_ln_w", "emb_ln_b", "sq_w", "sq_b", "sk_w", "sk_b", "sv_w", "sv_b", "so_w", "so_b",
+                         "so_ln_w", "so_ln_b", "eq_w", "eq_b", "ek_w", "ek_b", "ev_w", "ev_b", "eo_w", "eo_b", "eo_ln_w", "eo_ln_b",
+                         "i_w", "i_b", "o_w", "o_b", "o_ln_w", "o_ln_b", "cls_dense_w", "cls_dense_b", "cls_ln_w", "cls_ln_b", "cls_bias")
+
+
+class HbDecoderWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in DECODER_WEIGHT_FIELDS]
+
+
 class HbProfileSummary(C.Structure):
     _fields_ = [("ms", C.c_double * 6), ("flops", C.c_double * 6), ("launches", C.c_int64 * 6)]
 
@@ -93,6 +106,12 @@ SIGNATURES = {
     "hb_moment_ms_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                     C.c_double, C.c_void_p, C.c_void_p]),
     "hb_trim_feats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hb_decoder_create": (C.c_int, [C.POINTER(HbDecoderConfig), C.POINTER(HbDecoderWeights), C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.POINTER(C.c_void_p)]),
+    "hb_decoder_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "hb_decoder_step": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hb_decoder_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hb_decoder_destroy": (None, [C.c_void_p]),
     "hb_pool_normalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hb_similarity": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int,
                                 C.c_void_p]),

@@ -817,3 +817,233 @@ int hb_trim_feats(const float* x, const int64_t* mask, float* out, int B, int T,
 }
 
 }  // extern "C"
+
+// =================================================================================================
+// Caption decoder + beam search
+// =================================================================================================
+struct HbDecoder {
+  HbDecoderConfig cfg;
+  int max_inst = 0, max_beam = 0, max_enc = 0, Vpad = 0;
+  int n_inst = 0, beam = 0, enc_len = 0, step = 0;
+  F32Vec word_emb, pos_emb, emb_ln_w, emb_ln_b, cls_ln_w, cls_ln_b;
+  SplitLinear cls_dense, cls_vocab;
+  struct Layer {
+    SplitLinear sqkv, so, eq, ekv, eo, inter, out;
+    F32Vec so_ln_w, so_ln_b, eo_ln_w, eo_ln_b, o_ln_w, o_ln_b;
+    DevBuf kc[2], vc[2];   // self-attention caches [R, max_words, Hd], ping-pong for the beam re-order
+    DevBuf ekv_buf;        // cross keys | values [n_inst * enc_len, 2 * Hd]
+  };
+  std::vector<std::unique_ptr<Layer>> layers;
+  int cur = 0;             // which ping-pong cache holds the live data
+  DevBuf op, x, qkv, att, t1, s1, qc, c1, mid, th, logits;
+  DevBuf tok, scores, done, nsteps, prev_k, ys;
+  CUtensorMap tm_hd, tm_ffn, tm_enc;
+};
+
+extern "C" {
+
+int hb_decoder_create(const HbDecoderConfig* cfg, const HbDecoderWeights* w, int max_inst, int max_beam, int max_enc_len, void* stream,
+                      HbDecoder** out) {
+  if (!g_inited) return fail(HB_ERR_INVALID, "hb_init() not called");
+  if (!cfg || !w || !out || max_inst <= 0 || max_beam <= 0 || max_beam > 8 || max_enc_len <= 0) return fail(HB_ERR_INVALID, "bad argument");
+  const int Hd = cfg->hidden, Ff = cfg->ffn, V = cfg->vocab;
+  if (Hd != cfg->heads * 64 || Hd % 32 || Ff % 32 || cfg->max_words > cfg->max_pos || cfg->max_words > 400)
+    return fail(HB_ERR_INVALID, "unsupported decoder dims");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std::unique_ptr<HbDecoder> d(new (std::nothrow) HbDecoder);
+  if (!d) return fail(HB_ERR_NOMEM, "host allocation failed");
+  d->cfg = *cfg; d->max_inst = max_inst; d->max_beam = max_beam; d->max_enc = max_enc_len;
+  d->Vpad = (V + 31) / 32 * 32;
+  const size_t R = static_cast<size_t>(max_inst) * max_beam;
+  int r;
+  if ((r = d->word_emb.init(w->word_emb, static_cast<size_t>(V) * Hd, s))) return r;
+  if ((r = d->pos_emb.init(w->pos_emb, static_cast<size_t>(cfg->max_pos) * Hd, s))) return r;
+  if ((r = d->emb_ln_w.init(w->emb_ln_w, Hd, s))) return r;
+  if ((r = d->emb_ln_b.init(w->emb_ln_b, Hd, s))) return r;
+  if ((r = d->cls_ln_w.init(w->cls_ln_w, Hd, s))) return r;
+  if ((r = d->cls_ln_b.init(w->cls_ln_b, Hd, s))) return r;
+  if ((r = d->cls_dense.init_from(w->cls_dense_w, w->cls_dense_b, Hd, Hd, s))) return r;
+  {  // tied classifier: word embedding [V, Hd] padded with zero rows to Vpad; bias padded likewise
+    DevBuf tw, tb;
+    if ((r = tw.alloc(static_cast<size_t>(d->Vpad) * Hd * 4))) return r;
+    if ((r = tb.alloc(static_cast<size_t>(d->Vpad) * 4))) return r;
+    HB_CUDA(cudaMemsetAsync(tw.p, 0, tw.bytes, s));
+    HB_CUDA(cudaMemsetAsync(tb.p, 0, tb.bytes, s));
+    HB_CUDA(cudaMemcpyAsync(tw.p, w->word_emb, static_cast<size_t>(V) * Hd * 4, cudaMemcpyDeviceToDevice, s));
+    HB_CUDA(cudaMemcpyAsync(tb.p, w->cls_bias, static_cast<size_t>(V) * 4, cudaMemcpyDeviceToDevice, s));
+    if ((r = d->cls_vocab.init_from(tw.as<float>(), tb.as<float>(), d->Vpad, Hd, s))) return r;
+    HB_CUDA(cudaStreamSynchronize(s));
+  }
+  DevBuf tmpw, tmpb;
+  if ((r = tmpw.alloc(static_cast<size_t>(3) * Hd * Hd * 4))) return r;
+  if ((r = tmpb.alloc(static_cast<size_t>(3) * Hd * 4))) return r;
+  auto fuse = [&](const float* const* ws, const float* const* bs, int n) -> int {
+    for (int j = 0; j < n; ++j) {
+      HB_CUDA(cudaMemcpyAsync(tmpw.as<float>() + static_cast<size_t>(j) * Hd * Hd, ws[j], static_cast<size_t>(Hd) * Hd * 4, cudaMemcpyDeviceToDevice, s));
+      HB_CUDA(cudaMemcpyAsync(tmpb.as<float>() + static_cast<size_t>(j) * Hd, bs[j], static_cast<size_t>(Hd) * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+  };
+  for (int i = 0; i < cfg->layers; ++i) {
+    std::unique_ptr<HbDecoder::Layer> L(new HbDecoder::Layer);
+    const float* w3[3] = {w->sq_w[i], w->sk_w[i], w->sv_w[i]};
+    const float* b3[3] = {w->sq_b[i], w->sk_b[i], w->sv_b[i]};
+    if ((r = fuse(w3, b3, 3))) return r;
+    if ((r = L->sqkv.init_from(tmpw.as<float>(), tmpb.as<float>(), 3 * Hd, Hd, s))) return r;
+    const float* w2[2] = {w->ek_w[i], w->ev_w[i]};
+    const float* b2[2] = {w->ek_b[i], w->ev_b[i]};
+    if ((r = fuse(w2, b2, 2))) return r;
+    if ((r = L->ekv.init_from(tmpw.as<float>(), tmpb.as<float>(), 2 * Hd, Hd, s))) return r;
+    if ((r = L->so.init_from(w->so_w[i], w->so_b[i], Hd, Hd, s))) return r;
+    if ((r = L->eq.init_from(w->eq_w[i], w->eq_b[i], Hd, Hd, s))) return r;
+    if ((r = L->eo.init_from(w->eo_w[i], w->eo_b[i], Hd, Hd, s))) return r;
+    if ((r = L->inter.init_from(w->i_w[i], w->i_b[i], Ff, Hd, s))) return r;
+    if ((r = L->out.init_from(w->o_w[i], w->o_b[i], Hd, Ff, s))) return r;
+    if ((r = L->so_ln_w.init(w->so_ln_w[i], Hd, s))) return r;
+    if ((r = L->so_ln_b.init(w->so_ln_b[i], Hd, s))) return r;
+    if ((r = L->eo_ln_w.init(w->eo_ln_w[i], Hd, s))) return r;
+    if ((r = L->eo_ln_b.init(w->eo_ln_b[i], Hd, s))) return r;
+    if ((r = L->o_ln_w.init(w->o_ln_w[i], Hd, s))) return r;
+    if ((r = L->o_ln_b.init(w->o_ln_b[i], Hd, s))) return r;
+    for (int j = 0; j < 2; ++j) {
+      if ((r = L->kc[j].alloc(R * cfg->max_words * Hd * 4))) return r;
+      if ((r = L->vc[j].alloc(R * cfg->max_words * Hd * 4))) return r;
+    }
+    if ((r = L->ekv_buf.alloc(static_cast<size_t>(max_inst) * max_enc_len * 2 * Hd * 4))) return r;
+    d->layers.push_back(std::move(L));
+  }
+  const size_t Rop = std::max(R, static_cast<size_t>(max_inst) * max_enc_len);
+  if ((r = d->op.alloc(Rop * 3 * Ff * 2))) return r;
+#define ALLOCD(buf, cols) if ((r = d->buf.alloc(R * static_cast<size_t>(cols) * 4))) return r
+  ALLOCD(x, Hd); ALLOCD(qkv, 3 * Hd); ALLOCD(att, Hd); ALLOCD(t1, Hd); ALLOCD(s1, Hd); ALLOCD(qc, Hd); ALLOCD(c1, Hd); ALLOCD(mid, Ff);
+  ALLOCD(th, Hd); ALLOCD(logits, d->Vpad);
+#undef ALLOCD
+  if ((r = d->tok.alloc(R * 8))) return r;
+  if ((r = d->scores.alloc(R * 4))) return r;
+  if ((r = d->done.alloc(static_cast<size_t>(max_inst) * 4))) return r;
+  if ((r = d->nsteps.alloc(static_cast<size_t>(max_inst) * 4))) return r;
+  if ((r = d->prev_k.alloc(static_cast<size_t>(cfg->max_words) * R * 4))) return r;
+  if ((r = d->ys.alloc(static_cast<size_t>(cfg->max_words) * R * 4))) return r;
+  if (hb::make_tmap_bf16(&d->tm_hd, d->op.p, R, 3 * Hd, 3 * Hd, hb::gemm_a_box_rows()) ||
+      hb::make_tmap_bf16(&d->tm_ffn, d->op.p, R, 3 * Ff, 3 * Ff, hb::gemm_a_box_rows()) ||
+      hb::make_tmap_bf16(&d->tm_enc, d->op.p, static_cast<uint64_t>(max_inst) * max_enc_len, 3 * Hd, 3 * Hd, hb::gemm_a_box_rows()))
+    return fail(HB_ERR_CUDA, "tensor map (decoder operands) failed");
+  HB_CUDA(cudaStreamSynchronize(s));
+  *out = d.release();
+  return HB_OK;
+}
+
+void hb_decoder_destroy(HbDecoder* d) { delete d; }
+
+}  // extern "C"
+
+namespace {
+
+// act [rows, K] fp32 -> split operand -> GEMM with SplitLinear -> out fp32 [rows, N] (+ fp32 residual)
+int dec_gemm(HbDecoder* d, const float* act, long long rows, int K, int gelu, const CUtensorMap& tmA, const SplitLinear& L, float* out,
+             cudaStream_t s, const float* resid = nullptr) {
+  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(act, d->op.as<__nv_bfloat16>(), rows, K, gelu, s));
+  hb::GemmParams p;
+  p.M = static_cast<int>(rows); p.N = L.N; p.K = 3 * K;
+  p.bias = L.has_bias ? L.b.as<float>() : nullptr; p.out = out; p.ldo = L.N; p.resid = resid;
+  HB_LAUNCH_P(CAT_GEMM_F32, 2.0 * rows * L.N * 3.0 * K, s, hb::gemm_launch(tmA, L.tm, p, hb::EPI_F32, L.cg, g_num_sms, s));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hb_decoder_begin(HbDecoder* d, const float* enc, int n_inst, int enc_len, int beam, void* stream) {
+  if (!d || !enc) return fail(HB_ERR_INVALID, "null argument");
+  if (n_inst <= 0 || n_inst > d->max_inst || beam <= 0 || beam > d->max_beam || enc_len <= 0 || enc_len > d->max_enc)
+    return fail(HB_ERR_INVALID, "decoder batch (%d instances, beam %d, %d frames) exceeds the handle's capacity", n_inst, beam, enc_len);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  d->n_inst = n_inst; d->beam = beam; d->enc_len = enc_len; d->step = 0; d->cur = 0;
+  const int R = n_inst * beam, Hd = d->cfg.hidden;
+  int r;
+  for (auto& L : d->layers)  // cross-attention keys / values: once per search instead of once per step
+    if ((r = dec_gemm(d, enc, static_cast<long long>(n_inst) * enc_len, Hd, 0, d->tm_enc, L->ekv, L->ekv_buf.as<float>(), s))) return r;
+  std::vector<long long> tok(R, d->cfg.bos);
+  HB_CUDA(cudaMemcpyAsync(d->tok.p, tok.data(), tok.size() * 8, cudaMemcpyHostToDevice, s));
+  HB_CUDA(cudaMemsetAsync(d->scores.p, 0, static_cast<size_t>(R) * 4, s));
+  HB_CUDA(cudaMemsetAsync(d->done.p, 0, static_cast<size_t>(n_inst) * 4, s));
+  HB_CUDA(cudaMemsetAsync(d->nsteps.p, 0, static_cast<size_t>(n_inst) * 4, s));
+  HB_CUDA(cudaMemsetAsync(d->prev_k.p, 0, d->prev_k.bytes, s));
+  HB_CUDA(cudaMemsetAsync(d->ys.p, 0, d->ys.bytes, s));
+  HB_CUDA(cudaStreamSynchronize(s));  // `tok` is a host temporary
+  return HB_OK;
+}
+
+int hb_decoder_step(HbDecoder* d, void* stream) {
+  if (!d || d->n_inst <= 0) return fail(HB_ERR_INVALID, "hb_decoder_begin() not called");
+  if (d->step >= d->cfg.max_words) return fail(HB_ERR_INVALID, "max_words steps already taken");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const HbDecoderConfig& c = d->cfg;
+  const int R = d->n_inst * d->beam, Hd = c.hidden, Ff = c.ffn, pos = d->step, Tmax = c.max_words;
+  float* x = d->x.as<float>();
+  int r;
+  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::dec_embed_launch(d->tok.as<long long>(), d->word_emb.ptr(), d->pos_emb.ptr(), d->emb_ln_w.ptr(),
+                                                      d->emb_ln_b.ptr(), pos, x, R, Hd, s));
+  for (auto& Lp : d->layers) {
+    HbDecoder::Layer& L = *Lp;
+    float* kc = L.kc[d->cur].as<float>();
+    float* vc = L.vc[d->cur].as<float>();
+    if ((r = dec_gemm(d, x, R, Hd, 0, d->tm_hd, L.sqkv, d->qkv.as<float>(), s))) return r;
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::dec_cache_append_launch(d->qkv.as<float>(), kc, vc, pos, R, Tmax, Hd, s));
+    hb::SmallAttnF32Params ap;  // one query (the new token) over the cached prefix: every cached key is <= the query position
+    ap.q = d->qkv.as<float>(); ap.k = kc; ap.v = vc; ap.out = d->att.as<float>();
+    ap.B = R; ap.H = c.heads; ap.Tq = 1; ap.Tk = pos + 1;
+    ap.ldq = 3 * Hd; ap.ldk = Hd; ap.ldv = Hd; ap.ldo = Hd;
+    ap.bsq = 3 * Hd; ap.bsk = ap.bsv = static_cast<long long>(Tmax) * Hd; ap.bso = Hd;
+    ap.scale = 0.125f; ap.mask_mode = 0;
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::small_attn_f32_launch(ap, s));
+    if ((r = dec_gemm(d, d->att.as<float>(), R, Hd, 0, d->tm_hd, L.so, d->t1.as<float>(), s, x))) return r;
+    if ((r = ln_f32(d->t1.as<float>(), d->s1.as<float>(), L.so_ln_w, L.so_ln_b, 1e-12f, R, Hd, s))) return r;
+    if ((r = dec_gemm(d, d->s1.as<float>(), R, Hd, 0, d->tm_hd, L.eq, d->qc.as<float>(), s))) return r;
+    hb::SmallAttnF32Params cp;  // cross attention; the all-zeros video mask puts -10000 on every key (modeling.py:591)
+    cp.q = d->qc.as<float>(); cp.k = L.ekv_buf.as<float>(); cp.v = L.ekv_buf.as<float>() + Hd; cp.out = d->att.as<float>();
+    cp.B = R; cp.H = c.heads; cp.Tq = 1; cp.Tk = d->enc_len;
+    cp.ldq = Hd; cp.ldk = cp.ldv = 2 * Hd; cp.ldo = Hd;
+    cp.bsq = Hd; cp.bsk = cp.bsv = static_cast<long long>(d->enc_len) * 2 * Hd; cp.bso = Hd;
+    cp.scale = 0.125f; cp.mask_mode = 2; cp.mask_const = -10000.0f; cp.kv_div = d->beam;
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::small_attn_f32_launch(cp, s));
+    if ((r = dec_gemm(d, d->att.as<float>(), R, Hd, 0, d->tm_hd, L.eo, d->t1.as<float>(), s, d->s1.as<float>()))) return r;
+    if ((r = ln_f32(d->t1.as<float>(), d->c1.as<float>(), L.eo_ln_w, L.eo_ln_b, 1e-12f, R, Hd, s))) return r;
+    if ((r = dec_gemm(d, d->c1.as<float>(), R, Hd, 0, d->tm_hd, L.inter, d->mid.as<float>(), s))) return r;
+    if ((r = dec_gemm(d, d->mid.as<float>(), R, Ff, 1, d->tm_ffn, L.out, d->t1.as<float>(), s, d->c1.as<float>()))) return r;
+    if ((r = ln_f32(d->t1.as<float>(), x, L.o_ln_w, L.o_ln_b, 1e-12f, R, Hd, s))) return r;
+  }
+  // classifier on the last position only: transform (dense -> GELU -> LN) then the tied vocabulary projection
+  if ((r = dec_gemm(d, x, R, Hd, 0, d->tm_hd, d->cls_dense, d->th.as<float>(), s))) return r;
+  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::gelu_f32_launch(d->th.as<float>(), static_cast<long long>(R) * Hd, s));
+  if ((r = ln_f32(d->th.as<float>(), d->t1.as<float>(), d->cls_ln_w, d->cls_ln_b, 1e-12f, R, Hd, s))) return r;
+  if ((r = dec_gemm(d, d->t1.as<float>(), R, Hd, 0, d->tm_hd, d->cls_vocab, d->logits.as<float>(), s))) return r;
+  int* pk = d->prev_k.as<int>() + static_cast<size_t>(pos) * R;
+  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::beam_advance_launch(d->logits.as<float>(), d->Vpad, c.vocab, d->scores.as<float>(), d->done.as<int>(),
+                                                         d->nsteps.as<int>(), d->prev_k.as<int>(), d->ys.as<int>(), d->tok.as<long long>(),
+                                                         pos, d->n_inst, d->beam, c.eos, s));
+  // beams re-order: new beam j continues old beam prev_k[j]
+  for (auto& Lp : d->layers) {
+    HbDecoder::Layer& L = *Lp;
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::dec_cache_reorder_launch(L.kc[d->cur].as<float>(), L.vc[d->cur].as<float>(), L.kc[d->cur ^ 1].as<float>(),
+                                                                L.vc[d->cur ^ 1].as<float>(), pk, pos + 1, R, d->beam, Tmax, Hd, s));
+  }
+  d->cur ^= 1;
+  d->step += 1;
+  return HB_OK;
+}
+
+int hb_decoder_read(HbDecoder* d, int32_t* prev_k, int32_t* ys, int32_t* nsteps, int32_t* done, float* scores, void* stream) {
+  if (!d || d->n_inst <= 0) return fail(HB_ERR_INVALID, "hb_decoder_begin() not called");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t R = static_cast<size_t>(d->n_inst) * d->beam;
+  if (prev_k) HB_CUDA(cudaMemcpyAsync(prev_k, d->prev_k.p, static_cast<size_t>(d->cfg.max_words) * R * 4, cudaMemcpyDefault, s));
+  if (ys) HB_CUDA(cudaMemcpyAsync(ys, d->ys.p, static_cast<size_t>(d->cfg.max_words) * R * 4, cudaMemcpyDefault, s));
+  if (nsteps) HB_CUDA(cudaMemcpyAsync(nsteps, d->nsteps.p, static_cast<size_t>(d->n_inst) * 4, cudaMemcpyDefault, s));
+  if (done) HB_CUDA(cudaMemcpyAsync(done, d->done.p, static_cast<size_t>(d->n_inst) * 4, cudaMemcpyDefault, s));
+  if (scores) HB_CUDA(cudaMemcpyAsync(scores, d->scores.p, R * 4, cudaMemcpyDefault, s));
+  return HB_OK;
+}
+
+}  // extern "C"

@@ -51,6 +51,7 @@ struct SmallAttnF32Params {
   int mask_mode = 0;
   float mask_const = 0.f;
   int causal_soft = 0;
+  int kv_div = 1;  // K/V batch index = b / kv_div (beams of one instance share the encoder keys / values)
 };
 int small_attn_f32_launch(const SmallAttnF32Params& p, cudaStream_t stream);
 

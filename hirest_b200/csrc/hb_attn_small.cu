@@ -128,8 +128,8 @@ __global__ void __launch_bounds__(SA_THREADS) small_attn_f32_kernel(const SmallA
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* qg = p.q + b * p.bsq + h * DH;
-  const float* kg = p.k + b * p.bsk + h * DH;
-  const float* vg = p.v + b * p.bsv + h * DH;
+  const float* kg = p.k + (b / p.kv_div) * p.bsk + h * DH;
+  const float* vg = p.v + (b / p.kv_div) * p.bsv + h * DH;
   float* og = p.out + b * p.bso + h * DH;
   for (int c = threadIdx.x; c < p.Tk * 16; c += SA_THREADS) {
     const int row = c >> 4, ch = c & 15;

@@ -288,6 +288,156 @@ __global__ void __launch_bounds__(256) trim_feats_kernel(const float* __restrict
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// caption decoder
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dec_embed_kernel(const long long* __restrict__ tok, const float* __restrict__ word_emb,
+                                                        const float* __restrict__ pos_emb, const float* __restrict__ lnw,
+                                                        const float* __restrict__ lnb, int pos, float* __restrict__ x, int R, int Hd) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  const float* e = word_emb + tok[warp] * Hd;
+  const float* pe = pos_emb + static_cast<long long>(pos) * Hd;
+  float v[32];  // Hd <= 1024
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int k = lane + i * 32;
+    v[i] = (k < Hd) ? e[k] + pe[k] : 0.f;
+    s += v[i];
+  }
+  const float mean = warp_sum(s) / static_cast<float>(Hd);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int k = lane + i * 32;
+    if (k < Hd) { const float d = v[i] - mean; ss += d * d; }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(ss) / static_cast<float>(Hd) + 1e-12f);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int k = lane + i * 32;
+    if (k < Hd) x[static_cast<long long>(warp) * Hd + k] = lnw[k] * ((v[i] - mean) * rstd) + lnb[k];
+  }
+}
+
+__global__ void __launch_bounds__(256) dec_cache_append_kernel(const float* __restrict__ qkv, float* __restrict__ kc,
+                                                               float* __restrict__ vc, int pos, int R, int Tmax, int Hd) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(R) * Hd) return;
+  const long long r = t / Hd;
+  const int k = static_cast<int>(t - r * Hd);
+  kc[(r * Tmax + pos) * Hd + k] = qkv[r * 3 * Hd + Hd + k];
+  vc[(r * Tmax + pos) * Hd + k] = qkv[r * 3 * Hd + 2 * Hd + k];
+}
+
+__global__ void __launch_bounds__(256) dec_cache_reorder_kernel(const float* __restrict__ ksrc, const float* __restrict__ vsrc,
+                                                                float* __restrict__ kdst, float* __restrict__ vdst,
+                                                                const int* __restrict__ prev_k, int len, int R, int beam, int Tmax,
+                                                                int Hd) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long per_row = static_cast<long long>(len) * (Hd / 4);
+  if (t >= static_cast<long long>(R) * per_row) return;
+  const long long r = t / per_row;
+  const long long off = t - r * per_row;
+  const long long src_r = (r / beam) * beam + prev_k[r];
+  reinterpret_cast<float4*>(kdst + r * Tmax * Hd)[off] = reinterpret_cast<const float4*>(ksrc + src_r * Tmax * Hd)[off];
+  reinterpret_cast<float4*>(vdst + r * Tmax * Hd)[off] = reinterpret_cast<const float4*>(vsrc + src_r * Tmax * Hd)[off];
+}
+
+__global__ void __launch_bounds__(256) gelu_f32_kernel(float* __restrict__ x, long long n) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t < n) x[t] = gelu_exact(x[t]);
+}
+
+constexpr int BEAM_MAX = 8;
+
+__global__ void __launch_bounds__(256) beam_advance_kernel(const float* __restrict__ logits, int ldl, int V, float* __restrict__ scores,
+                                                           int* __restrict__ done, int* __restrict__ nsteps, int* __restrict__ prev_k_rec,
+                                                           int* __restrict__ ys_rec, long long* __restrict__ tok, int step, int n_inst,
+                                                           int beam, int eos) {
+  __shared__ float red[8];
+  __shared__ float lse[BEAM_MAX];
+  __shared__ float cand_v[256 * BEAM_MAX];
+  __shared__ int cand_i[256 * BEAM_MAX];
+  const int inst = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int* pk_out = prev_k_rec + (static_cast<long long>(step) * n_inst + inst) * beam;
+  int* ys_out = ys_rec + (static_cast<long long>(step) * n_inst + inst) * beam;
+  if (done[inst]) {  // finished: frozen; identity back-pointers keep the cache re-order a no-op
+    if (tid < beam) { pk_out[tid] = tid; ys_out[tid] = 0; }
+    return;
+  }
+  const int rows = (step == 0) ? 1 : beam;  // Beam.advance uses word_prob[0] only before any back-pointer exists
+  for (int k = 0; k < rows; ++k) {
+    const float* row = logits + static_cast<long long>(inst * beam + k) * ldl;
+    float m = -INFINITY;
+    for (int j = tid; j < V; j += 256) m = fmaxf(m, row[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float s = 0.f;
+    for (int j = tid; j < V; j += 256) s += expf(row[j] - m);
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < 8; ++w) tot += red[w];
+      lse[k] = m + logf(tot);
+    }
+    __syncthreads();
+  }
+  // thread-local top-`beam` over the flat [rows * V] candidates (value descending, lower flat index first on ties)
+  float bv[BEAM_MAX];
+  int bi[BEAM_MAX];
+#pragma unroll
+  for (int i = 0; i < BEAM_MAX; ++i) { bv[i] = -INFINITY; bi[i] = 0x7fffffff; }
+  for (int k = 0; k < rows; ++k) {
+    const float* row = logits + static_cast<long long>(inst * beam + k) * ldl;
+    const float add = (step == 0) ? 0.f : scores[inst * beam + k];
+    const float l = lse[k];
+    for (int j = tid; j < V; j += 256) {
+      const float val = (row[j] - l) + add;     // log_softmax, then + beam score (beam.py:76)
+      if (val > bv[beam - 1]) {
+        int pos = beam - 1;
+        bv[pos] = val; bi[pos] = k * V + j;
+        while (pos > 0 && bv[pos] > bv[pos - 1]) {
+          const float tv = bv[pos]; bv[pos] = bv[pos - 1]; bv[pos - 1] = tv;
+          const int ti = bi[pos]; bi[pos] = bi[pos - 1]; bi[pos - 1] = ti;
+          --pos;
+        }
+      }
+    }
+  }
+  for (int i = 0; i < beam; ++i) { cand_v[tid * beam + i] = bv[i]; cand_i[tid * beam + i] = bi[i]; }
+  __syncthreads();
+  if (tid == 0) {
+    const int n = 256 * beam;
+    for (int sel = 0; sel < beam; ++sel) {
+      int best = -1;
+      for (int c = 0; c < n; ++c) {
+        if (cand_i[c] == 0x7fffffff) continue;
+        if (best < 0 || cand_v[c] > cand_v[best] || (cand_v[c] == cand_v[best] && cand_i[c] < cand_i[best])) best = c;
+      }
+      const int id = cand_i[best];
+      const int pk = id / V, y = id - pk * V;
+      scores[inst * beam + sel] = cand_v[best];
+      pk_out[sel] = pk;
+      ys_out[sel] = y;
+      tok[inst * beam + sel] = y;
+      cand_i[best] = 0x7fffffff;
+      if (sel == 0 && y == eos) done[inst] = 1;
+    }
+    nsteps[inst] = step + 1;
+  }
+}
+
 inline unsigned nblocks(long long n, int per) { return static_cast<unsigned>((n + per - 1) / per); }
 
 }  // namespace
@@ -337,6 +487,34 @@ int ms_step_launch(const float* logits, long long* moment_mask, long long* bound
 int trim_feats_launch(const float* x, const long long* mask, float* out, int B, int T, int C, int F, cudaStream_t s) {
   if (F > 64) return -7;
   trim_feats_kernel<<<B, 256, 0, s>>>(x, mask, out, T, C, F);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int dec_embed_launch(const long long* tok, const float* word_emb, const float* pos_emb, const float* lnw, const float* lnb, int pos,
+                     float* x, int R, int Hd, cudaStream_t s) {
+  if (Hd > 1024) return -7;
+  dec_embed_kernel<<<nblocks(R, 8), 256, 0, s>>>(tok, word_emb, pos_emb, lnw, lnb, pos, x, R, Hd);
+  return static_cast<int>(cudaGetLastError());
+}
+int dec_cache_append_launch(const float* qkv, float* kc, float* vc, int pos, int R, int Tmax, int Hd, cudaStream_t s) {
+  dec_cache_append_kernel<<<nblocks(static_cast<long long>(R) * Hd, 256), 256, 0, s>>>(qkv, kc, vc, pos, R, Tmax, Hd);
+  return static_cast<int>(cudaGetLastError());
+}
+int dec_cache_reorder_launch(const float* ksrc, const float* vsrc, float* kdst, float* vdst, const int* prev_k, int len, int R,
+                             int beam, int Tmax, int Hd, cudaStream_t s) {
+  if (len <= 0) return 0;
+  dec_cache_reorder_kernel<<<nblocks(static_cast<long long>(R) * len * (Hd / 4), 256), 256, 0, s>>>(ksrc, vsrc, kdst, vdst, prev_k, len,
+                                                                                                    R, beam, Tmax, Hd);
+  return static_cast<int>(cudaGetLastError());
+}
+int gelu_f32_launch(float* x, long long n, cudaStream_t s) {
+  gelu_f32_kernel<<<nblocks(n, 256), 256, 0, s>>>(x, n);
+  return static_cast<int>(cudaGetLastError());
+}
+int beam_advance_launch(const float* logits, int ldl, int V, float* scores, int* done, int* nsteps, int* prev_k_rec, int* ys_rec,
+                        long long* tok, int step, int n_inst, int beam, int eos, cudaStream_t s) {
+  if (beam < 1 || beam > BEAM_MAX) return -7;
+  beam_advance_kernel<<<n_inst, 256, 0, s>>>(logits, ldl, V, scores, done, nsteps, prev_k_rec, ys_rec, tok, step, n_inst, beam, eos);
   return static_cast<int>(cudaGetLastError());
 }
 

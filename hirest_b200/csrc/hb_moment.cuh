@@ -37,4 +37,21 @@ int ms_step_launch(const float* logits, long long* moment_mask, long long* bound
 // trim_feats (modeling.py:529-554): frames with mask==1, truncated to F or repeat-padded -> out fp32 [B, F, C]
 int trim_feats_launch(const float* x, const long long* mask, float* out, int B, int T, int C, int F, cudaStream_t s);
 
+
+// ---- caption decoder (clip4caption/modules/module_decoder.py:294-406, beam.py:70-123, train.py:547-599) ----------------
+// x[r,:] = TF_LN(word_emb[tok[r]] + pos_emb[pos]; w, b, 1e-12)                       (module_decoder.py:309-320)
+int dec_embed_launch(const long long* tok, const float* word_emb, const float* pos_emb, const float* lnw, const float* lnb, int pos,
+                     float* x, int R, int Hd, cudaStream_t s);
+// append this step's self-attention key / value (columns [Hd,2Hd) / [2Hd,3Hd) of qkv) at position `pos` of the caches
+int dec_cache_append_launch(const float* qkv, float* kc, float* vc, int pos, int R, int Tmax, int Hd, cudaStream_t s);
+// beams re-order: dst[r, 0..len) = src[(r / beam) * beam + prev_k[r], 0..len) for both caches of one layer
+int dec_cache_reorder_launch(const float* ksrc, const float* vsrc, float* kdst, float* vdst, const int* prev_k, int len, int R,
+                             int beam, int Tmax, int Hd, cudaStream_t s);
+int gelu_f32_launch(float* x, long long n, cudaStream_t s);
+// Beam.advance for every still-active instance (one CTA each): log_softmax over V per beam row, + beam scores (row 0 only
+// at the first step), flat top-`beam` (sorted), prev_k = id / V, y = id % V; instance done when the best beam emits `eos`.
+// step is 0-based.  Records prev_k / ys of this step at [step, inst, :]; for finished instances prev_k is the identity.
+int beam_advance_launch(const float* logits, int ldl, int V, float* scores, int* done, int* nsteps, int* prev_k_rec, int* ys_rec,
+                        long long* tok, int step, int n_inst, int beam, int eos, cudaStream_t s);
+
 }  // namespace hb

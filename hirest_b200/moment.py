@@ -6,8 +6,8 @@ the non-CLIP keys of SURVEY.md Appendix B, so ``HiREST_BEST.pth`` loads with ``s
 does).  Batches are the collate dicts of hirest_dataset.py:409-531 (CPU tensors; moved to the model's device here, as
 modeling.py:275-286 does).
 
-Round 1 covers moment retrieval and moment segmentation (shared encoder, heads, both decoders, trim_feats); step captioning
-(beam decoder) and training are not implemented and raise.  No CPU / eager fallback.
+Covers moment retrieval, moment segmentation and step captioning (KV-cached beam decoder on the device); training is out of
+scope and raises.  No CPU / eager fallback.
 """
 from __future__ import annotations
 
@@ -142,7 +142,7 @@ class MomentModel(nn.Module):
         elif task == "moment_segmentation":
             return self.test_moment_segmentation(batch, **kwargs)
         elif task == "step_captioning":
-            raise NotImplementedError("step captioning (beam decoder) is not implemented yet in hirest_b200")
+            return self.test_step_captioning(batch, **kwargs)
         else:
             raise NotImplementedError
 
@@ -286,6 +286,132 @@ class MomentModel(nn.Module):
             sp = [[starts[b], starts[b]]] + [list(x) for x in steps_h[b][:n_h[b]]]
             preds.append(_postprocess_steps(sp, lasts[b]))
         return {"raw_predictions": deepcopy(preds), "prediction": preds}
+
+    # ------------------------------------------------------------------ step captioning
+    def _get_decoder(self, n_inst: int, beam: int):
+        ps = self._own_params()
+        key = (self._device(), ps[0].data_ptr(), tuple(q._version for q in ps))
+        cap = getattr(self, "_dec_cap", (0, 0))
+        if getattr(self, "_dec_engine", None) is not None and key == self._dec_key and n_inst <= cap[0] and beam <= cap[1]:
+            return self._dec_engine
+        cap = (max(cap[0], n_inst, 16), max(cap[1], beam, 5))
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("hirest_b200: the caption decoder runs on a B200 only (no CPU fallback)")
+        lib = _lib.init(dev.index or 0)
+        sd = {k: v.detach().float().contiguous() for k, v in self.state_dict().items() if k.startswith("clip4cap_model.decoder.")}
+        L = getattr(self.args, "decoder_num_hidden_layers", 2)
+        keep = []
+
+        def per_layer(fmt):
+            arr = _lib.ptr_array([sd[fmt.format(i)] for i in range(L)])
+            keep.append(arr)
+            return C.cast(arr, C.c_void_p)
+
+        d = "clip4cap_model.decoder."
+        l_ = d + "decoder.layer.{}."
+        c_ = d + "classifier.cls.predictions."
+        fields = [sd[d + "embeddings.word_embeddings.weight"].data_ptr(), sd[d + "embeddings.position_embeddings.weight"].data_ptr(),
+                  sd[d + "embeddings.LayerNorm.weight"].data_ptr(), sd[d + "embeddings.LayerNorm.bias"].data_ptr()]
+        for att in ("slf_attn", "enc_attn"):
+            for n in ("query", "key", "value"):
+                fields += [per_layer(f"{l_}{att}.att.{n}.weight"), per_layer(f"{l_}{att}.att.{n}.bias")]
+            fields += [per_layer(f"{l_}{att}.output.dense.weight"), per_layer(f"{l_}{att}.output.dense.bias"),
+                       per_layer(f"{l_}{att}.output.LayerNorm.weight"), per_layer(f"{l_}{att}.output.LayerNorm.bias")]
+        fields += [per_layer(l_ + "intermediate.dense.weight"), per_layer(l_ + "intermediate.dense.bias"),
+                   per_layer(l_ + "output.dense.weight"), per_layer(l_ + "output.dense.bias"),
+                   per_layer(l_ + "output.LayerNorm.weight"), per_layer(l_ + "output.LayerNorm.bias"),
+                   sd[c_ + "transform.dense.weight"].data_ptr(), sd[c_ + "transform.dense.bias"].data_ptr(),
+                   sd[c_ + "transform.LayerNorm.weight"].data_ptr(), sd[c_ + "transform.LayerNorm.bias"].data_ptr(), sd[c_ + "bias"].data_ptr()]
+        w = _lib.HbDecoderWeights(*fields)
+        dd = _DEFAULTS
+        cfg = _lib.HbDecoderConfig(dd["hidden"], dd["heads"], dd["ffn"], L, dd["vocab"], dd["max_pos_decoder"], int(self.args.max_words),
+                                   self.BOS, self.EOS)
+        handle = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(lib.hb_decoder_create(C.byref(cfg), C.byref(w), cap[0], cap[1], int(self.args.max_frames), _lib.stream_ptr(dev),
+                                             C.byref(handle)), "hb_decoder_create")
+        self._dec_engine = _Engine(handle, lib.hb_decoder_destroy)
+        self._dec_key, self._dec_cap = key, cap
+        return self._dec_engine
+
+    BOS, EOS, PAD = 101, 102, 0  # [CLS] / [SEP] / [PAD] of the BERT vocabulary (beam.py:22-29 via the tokenizer)
+
+    @torch.no_grad()
+    def generate_caption_ids(self, feats: torch.Tensor, num_beams: int):
+        """Beam search of modeling.py:575-613 over encoder features [B, F, 768]; returns the best hypothesis' token ids per sample.
+        The whole loop stays on the device (finished instances are frozen instead of compacted); one D2H at the end."""
+        dev = self._device()
+        B, Fr, _ = feats.shape
+        eng = self._get_decoder(B, num_beams)
+        lib = _lib.load()
+        W = int(self.args.max_words)
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            _lib.check(lib.hb_decoder_begin(eng.handle, feats.float().contiguous().data_ptr(), B, Fr, num_beams, st), "hb_decoder_begin")
+            done = torch.zeros((B,), dtype=torch.int32, device=dev)
+            for step in range(W):
+                _lib.check(lib.hb_decoder_step(eng.handle, st), "hb_decoder_step")
+                if step % 8 == 7 and step + 1 < W:   # cheap early exit: all instances finished?
+                    _lib.check(lib.hb_decoder_read(eng.handle, None, None, None, done.data_ptr(), None, st), "hb_decoder_read")
+                    if bool(done.all()):
+                        break
+            pk = torch.empty((W, B, num_beams), dtype=torch.int32, device=dev)
+            ys = torch.empty((W, B, num_beams), dtype=torch.int32, device=dev)
+            ns = torch.empty((B,), dtype=torch.int32, device=dev)
+            _lib.check(lib.hb_decoder_read(eng.handle, pk.data_ptr(), ys.data_ptr(), ns.data_ptr(), None, None, st), "hb_decoder_read")
+        pk, ys, ns = pk.cpu().tolist(), ys.cpu().tolist(), ns.cpu().tolist()
+        out = []
+        for b in range(B):   # Beam.get_hypothesis(0): scores are kept sorted, so the best tail is beam 0 (beam.py:103-123)
+            k, hyp = 0, []
+            for j in range(ns[b] - 1, -1, -1):
+                hyp.append(ys[j][b][k])
+                k = pk[j][b][k]
+            out.append(hyp[::-1])
+        return out
+
+    def _vocab(self):
+        v = getattr(self, "_vocab_list", None)
+        if v is None:
+            import os
+
+            path = getattr(self.args, "bert_vocab_path", None)
+            cands = [path] if path else []
+            cands += ["./clip4caption/modules/bert-base-uncased/vocab.txt", os.path.expanduser("~/.pytorch_pretrained_bert/vocab.txt")]
+            for c in cands:
+                if c and os.path.exists(c):
+                    with open(c, encoding="utf-8") as f:
+                        v = [ln.rstrip("\n") for ln in f]
+                    break
+            if v is None:
+                raise RuntimeError("BERT vocab.txt not found (set args.bert_vocab_path); needed to turn token ids into text")
+            self._vocab_list = v
+        return v
+
+    def ids_to_text(self, ids):
+        """modeling.py:615-626."""
+        vocab = self._vocab()
+        toks = [vocab[i] for i in ids]
+        if "[SEP]" in toks:
+            toks = toks[:toks.index("[SEP]")]
+        if "[PAD]" in toks:
+            toks = toks[:toks.index("[PAD]")]
+        return str(" ".join(toks).replace(" ##", "").strip("##").strip())
+
+    @torch.no_grad()
+    def test_step_captioning(self, batch, **kwargs):
+        """modeling.py:556-632."""
+        dev = self._device()
+        video, vmask, asr, text_feat = self._inputs(batch)
+        mmask = batch["moment_mask"].to(dev).long().contiguous()
+        B = video.shape[0]
+        video = self.trim_feats(video, mmask)
+        asr = self.trim_feats(asr, mmask)
+        ones = torch.ones((B, self.args.max_frames), dtype=torch.long, device=dev)
+        _, feats = self._forward(video, text_feat, asr, ones, ones, want_feats=True)
+        beam_size = kwargs.get("num_beams", 5)
+        ids = self.generate_caption_ids(feats, beam_size)
+        return {"prediction": [self.ids_to_text(x) for x in ids], "token_ids": ids}
 
     @torch.no_grad()
     def trim_feats(self, visual_output, moment_mask, B=None, device=None):

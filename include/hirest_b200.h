@@ -180,6 +180,46 @@ HB_API int hb_moment_ms_step(const float* logits, int64_t* moment_mask, int64_t*
 /* trim_feats (modeling.py:529-554): x fp32 [B,T,C], mask int64 [B,T] -> out fp32 [B,F,C]. */
 HB_API int hb_trim_feats(const float* x, const int64_t* mask, float* out, int B, int T, int C, int F, void* stream);
 
+/* ---- caption decoder + beam search (module_decoder.py:372-406, beam.py:70-123, train.py:547-599, modeling.py:575-613) -- */
+typedef struct {
+  int hidden;     /* 768 */
+  int heads;      /* 12 */
+  int ffn;        /* 3072 */
+  int layers;     /* 2 (args.py:54) */
+  int vocab;      /* 30522 */
+  int max_pos;    /* 512 rows of decoder position embeddings */
+  int max_words;  /* 48 (args.py:52) */
+  int bos;        /* [CLS] = 101 */
+  int eos;        /* [SEP] = 102 */
+} HbDecoderConfig;
+
+/* fp32 device pointers (clip4cap_model.decoder.* of the reference state_dict).  Per-layer members: host arrays of device pointers. */
+typedef struct {
+  const float* word_emb; const float* pos_emb; const float* emb_ln_w; const float* emb_ln_b;
+  const float* const* sq_w; const float* const* sq_b; const float* const* sk_w; const float* const* sk_b;
+  const float* const* sv_w; const float* const* sv_b; const float* const* so_w; const float* const* so_b;
+  const float* const* so_ln_w; const float* const* so_ln_b;
+  const float* const* eq_w; const float* const* eq_b; const float* const* ek_w; const float* const* ek_b;
+  const float* const* ev_w; const float* const* ev_b; const float* const* eo_w; const float* const* eo_b;
+  const float* const* eo_ln_w; const float* const* eo_ln_b;
+  const float* const* i_w; const float* const* i_b; const float* const* o_w; const float* const* o_b;
+  const float* const* o_ln_w; const float* const* o_ln_b;
+  const float* cls_dense_w; const float* cls_dense_b; const float* cls_ln_w; const float* cls_ln_b; const float* cls_bias;
+} HbDecoderWeights;
+
+typedef struct HbDecoder HbDecoder;
+HB_API int hb_decoder_create(const HbDecoderConfig* cfg, const HbDecoderWeights* w, int max_inst, int max_beam, int max_enc_len,
+                             void* stream, HbDecoder** out);
+/* Start a beam search: enc fp32 [n_inst, enc_len, hidden] (shared-encoder output of the trimmed clip).  Projects the
+ * cross-attention keys / values once (the reference re-projects them every step) and resets the beams. */
+HB_API int hb_decoder_begin(HbDecoder* d, const float* enc, int n_inst, int enc_len, int beam, void* stream);
+/* One decode step for all instances: KV-cached self-attention, cross-attention with the reference's -10000-on-every-key mask,
+ * last-position classifier, log_softmax, Beam.advance, cache re-order.  Finished instances are frozen. No host sync. */
+HB_API int hb_decoder_step(HbDecoder* d, void* stream);
+/* Copy out: prev_k / ys int32 [max_words, n_inst, beam], nsteps int32 [n_inst], done int32 [n_inst], scores fp32 [n_inst, beam]. */
+HB_API int hb_decoder_read(HbDecoder* d, int32_t* prev_k, int32_t* ys, int32_t* nsteps, int32_t* done, float* scores, void* stream);
+HB_API void hb_decoder_destroy(HbDecoder* d);
+
 /* ---- retrieval scoring ------------------------------------------------------------------------ */
 /* out[v,:] = l2norm(mean_f emb[v,f,:]); emb fp32 [V,F,E]; out fp32 [V,E].  F = 1 gives plain L2 normalise. */
 HB_API int hb_pool_normalize(const float* emb, int64_t V, int F, int E, float* out, void* stream);

@@ -40,6 +40,43 @@ if __name__ == "__main__":
         out[name] = {"shared": feats.clone(), "start_logits": mr["start_logits"].clone(), "end_logits": mr["end_logits"].clone(),
                      "mr_pred": mr_pred, "ms_pred": ms_pred, "ms_logits": ms_logits.clone(), "trimmed_sum": trimmed.sum(-1).clone()}
         print(name, "mr", mr_pred, "ms", ms_pred)
+    # step captioning (beam 3) on the small batch: best-hypothesis token ids + strings
+    import modeling as ref_modeling
+    captured = {}
+    orig = ref_modeling.collect_hypothesis_and_scores
+
+    def capture(beams, n_best):
+        hyp, sc = orig(beams, n_best)
+        captured["hyp"] = [h[0] for h in hyp]
+        captured["scores"] = [float(x[0]) for x in sc]
+        return hyp, sc
+
+    ref_modeling.collect_hypothesis_and_scores = capture
+    batch = synthetic.make_moment_batch(3, 40, seed=5)
+    tf = batch["text_feat"]
+    model.clip_model.encode_text = lambda ids, tf=tf: tf
+    b4 = dict(batch)
+    b4["tasks"] = ["step_captioning"] * 3
+    with torch.no_grad():
+        cap = model.test_step(b4, num_beams=3)["prediction"]
+    out["caption"] = {"text": cap, "ids": captured["hyp"], "scores": captured["scores"]}
+    print("captions", cap, [len(h) for h in captured["hyp"]], captured["scores"])
+    # same, with the [SEP] logit boosted so that beams finish early at different steps (exercises the "done" path)
+    sd2 = dict(sd)
+    bias = sd["clip4cap_model.decoder.classifier.cls.predictions.bias"].clone()
+    bias[102] += 2.0
+    sd2["clip4cap_model.decoder.classifier.cls.predictions.bias"] = bias
+    model.load_state_dict(sd2, strict=True)
+    batch = synthetic.make_moment_batch(4, 40, seed=7)
+    tf = batch["text_feat"]
+    model.clip_model.encode_text = lambda ids, tf=tf: tf
+    b5 = dict(batch)
+    b5["tasks"] = ["step_captioning"] * 4
+    with torch.no_grad():
+        cap = model.test_step(b5, num_beams=3)["prediction"]
+    out["caption_eos"] = {"text": cap, "ids": captured["hyp"], "scores": captured["scores"]}
+    print("captions (eos boosted)", [len(h) for h in captured["hyp"]], captured["scores"])
+    model.load_state_dict(sd, strict=True)
     # keep the fixture small: shared features only for the small case, logits for both
     out["t300"]["shared"] = out["t300"]["shared"][:, :8].clone()
     torch.save(out, os.path.join(ROOT, "tests", "golden", "moment.pt"))

@@ -150,3 +150,48 @@ def test_rejects_long_clips(model):
     b = synthetic.make_moment_batch(1, 401, seed=1, ragged=False)
     with pytest.raises(RuntimeError, match="> 400 frames"):
         m.foward_moment_shared(b["vis_feats"], b["text_feat"], b["vis_mask"], moment_mask=b["moment_mask"], asr_feats=b["asr_feats"])
+
+
+def _write_vocab(tmp_path):
+    vocab = [f"[unused{i}]" for i in range(30522)]
+    vocab[0], vocab[100], vocab[101], vocab[102], vocab[103] = "[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"
+    for i in range(1000, 30522):
+        vocab[i] = f"w{i}"
+    p = tmp_path / "vocab.txt"
+    p.write_text("\n".join(vocab) + "\n")
+    return str(p)
+
+
+def test_step_captioning_token_ids_match_reference(model, golden, tmp_path):
+    """Beam-3 decode of the small batch: KV-cached on-device beam search vs the reference's full-prefix recompute
+    (modeling.py:556-632): identical best-hypothesis token ids and strings."""
+    m, clip = model
+    b = synthetic.make_moment_batch(3, 40, seed=5)
+    clip.feat = b["text_feat"]
+    b["tasks"] = ["step_captioning"] * 3
+    m.args.bert_vocab_path = _write_vocab(tmp_path)
+    m._vocab_list = None
+    out = m.test_step(b, num_beams=3)
+    g = golden["caption"]
+    assert out["token_ids"] == g["ids"]
+    assert out["prediction"] == g["text"]
+
+
+def test_step_captioning_early_finish(hb, golden, tmp_path):
+    """[SEP] logit boosted: instances finish at different steps (48, 48, 2, 17 tokens in the reference) and are frozen."""
+    clip = FixedText()
+    m = moment.MomentModel(-1, 384, moment.default_args(bert_vocab_path=_write_vocab(tmp_path)), clip_model=clip, max_rows=1024, max_batch=8)
+    sd = synthetic.make_moment_state_dict(seed=3)
+    bias = sd["clip4cap_model.decoder.classifier.cls.predictions.bias"].clone()
+    bias[102] += 2.0
+    sd["clip4cap_model.decoder.classifier.cls.predictions.bias"] = bias
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    b = synthetic.make_moment_batch(4, 40, seed=7)
+    clip.feat = b["text_feat"]
+    b["tasks"] = ["step_captioning"] * 4
+    out = m.test_step(b, num_beams=3)
+    g = golden["caption_eos"]
+    assert [len(x) for x in g["ids"]] == [48, 48, 2, 17]
+    assert out["token_ids"] == g["ids"]
+    assert out["prediction"] == g["text"]

@@ -76,8 +76,6 @@ def test_moment_model_state_dict_layout_and_errors():
     assert m.args.max_frames == 20 and m.args.d_model == 512  # args mutated like modeling.py:103-105
     with pytest.raises(NotImplementedError):
         m.train_step({"tasks": ["moment_retrieval"]})
-    with pytest.raises(NotImplementedError):
-        m.test_step({"tasks": ["step_captioning"]})
     b = synthetic.make_moment_batch(1, 16, seed=1)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.foward_moment_shared(b["vis_feats"], b["text_feat"], b["vis_mask"], moment_mask=b["moment_mask"], asr_feats=b["asr_feats"])
