@@ -744,7 +744,6 @@ int hb_moment_forward(HbMoment* m, const float* video, const float* text_feat, c
   const HbMomentConfig& c = m->cfg;
   if (R > m->max_rows || B > m->max_batch) return fail(HB_ERR_INVALID, "batch of %d x %d frames exceeds the handle's capacity", B, T);
   if (T > c.max_pos) return fail(HB_ERR_INVALID, "T = %d exceeds max_position_embeddings %d", T, c.max_pos);
-  if (T > 400) return fail(HB_ERR_INVALID, "T = %d > 400 frames is not supported yet (fp32 attention keeps K/V of one head in smem)", T);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int E = c.embed_dim, Hd = c.hidden, Ff = c.ffn, A = c.asr_dim, Cd = c.clip_dim;
   int r;
@@ -847,7 +846,7 @@ int hb_decoder_create(const HbDecoderConfig* cfg, const HbDecoderWeights* w, int
   if (!g_inited) return fail(HB_ERR_INVALID, "hb_init() not called");
   if (!cfg || !w || !out || max_inst <= 0 || max_beam <= 0 || max_beam > 8 || max_enc_len <= 0) return fail(HB_ERR_INVALID, "bad argument");
   const int Hd = cfg->hidden, Ff = cfg->ffn, V = cfg->vocab;
-  if (Hd != cfg->heads * 64 || Hd % 32 || Ff % 32 || cfg->max_words > cfg->max_pos || cfg->max_words > 400)
+  if (Hd != cfg->heads * 64 || Hd % 32 || Ff % 32 || cfg->max_words > cfg->max_pos)
     return fail(HB_ERR_INVALID, "unsupported decoder dims");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   std::unique_ptr<HbDecoder> d(new (std::nothrow) HbDecoder);

@@ -38,7 +38,8 @@ struct SmallAttnParams {
 };
 int small_attn_launch(const SmallAttnParams& p, cudaStream_t stream);
 
-// fp32 in / fp32 out variant (Tk <= 400), same semantics; used by the MomentModel's fp32-accurate path.
+// fp32 in / fp32 out variant (keys streamed in tiles of 256 with an online softmax: any length), same mask semantics;
+// used by the MomentModel / caption decoder fp32-accurate path.
 struct SmallAttnF32Params {
   const float* q = nullptr;
   const float* k = nullptr;

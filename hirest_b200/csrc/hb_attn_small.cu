@@ -115,42 +115,61 @@ __global__ void __launch_bounds__(SA_THREADS) small_attn_kernel(const SmallAttnP
   }
 }
 
-// ---- fp32 variant (MomentModel "precise" path): q/k/v/out fp32, K/V of one head in smem (Tk <= 400) -------------------
-constexpr int KF_STRIDE = 272;  // 256 + 16 pad
+// ---- fp32 variant (MomentModel / caption decoder "precise" path) ----------------------------------------------------------
+// q/k/v/out fp32.  One CTA per (batch, head, block of 64 queries); keys are streamed through shared memory in tiles of 256
+// with an online softmax (running max / sum / output per query in registers), so any sequence length works.
+constexpr int KF_STRIDE = 272;  // 256 B + 16 B pad: conflict-free 16-byte reads with lanes on consecutive keys
 constexpr int VF_STRIDE = 256;
-constexpr int MAX_TK_F32 = 400;
-constexpr int MAXJ_F32 = (MAX_TK_F32 + 31) / 32;
+constexpr int KT_F32 = 256;     // keys per tile
+constexpr int QB_F32 = 64;      // queries per CTA (8 per warp)
 
-__global__ void __launch_bounds__(SA_THREADS) small_attn_f32_kernel(const SmallAttnF32Params p) {
+__global__ void __launch_bounds__(SA_THREADS) small_attn_f32_kernel(const SmallAttnF32Params p, int q_blocks) {
   extern __shared__ __align__(16) uint8_t smem[];
   uint8_t* sk = smem;
-  uint8_t* sv = smem + static_cast<size_t>(p.Tk) * KF_STRIDE;
-  const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
+  uint8_t* sv = smem + static_cast<size_t>(KT_F32) * KF_STRIDE;
+  const int qb = blockIdx.x % q_blocks;
+  const int bh = blockIdx.x / q_blocks;
+  const int b = bh / p.H, h = bh - b * p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* qg = p.q + b * p.bsq + h * DH;
   const float* kg = p.k + (b / p.kv_div) * p.bsk + h * DH;
   const float* vg = p.v + (b / p.kv_div) * p.bsv + h * DH;
   float* og = p.out + b * p.bso + h * DH;
-  for (int c = threadIdx.x; c < p.Tk * 16; c += SA_THREADS) {
-    const int row = c >> 4, ch = c & 15;
-    *reinterpret_cast<float4*>(sk + row * KF_STRIDE + ch * 16) = __ldg(reinterpret_cast<const float4*>(kg + static_cast<size_t>(row) * p.ldk + ch * 4));
-    *reinterpret_cast<float4*>(sv + row * VF_STRIDE + ch * 16) = __ldg(reinterpret_cast<const float4*>(vg + static_cast<size_t>(row) * p.ldv + ch * 4));
-  }
-  __syncthreads();
-  for (int i = warp; i < p.Tq; i += SA_THREADS / 32) {
-    float q[DH];
+  const int q0 = qb * QB_F32 + warp * 8;  // this warp's queries: q0 .. q0+7
+  float m[8], sum[8], o0[8], o1[8];
 #pragma unroll
-    for (int ch = 0; ch < 16; ++ch) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(qg + static_cast<size_t>(i) * p.ldq) + ch);
-      q[ch * 4] = v.x; q[ch * 4 + 1] = v.y; q[ch * 4 + 2] = v.z; q[ch * 4 + 3] = v.w;
+  for (int i = 0; i < 8; ++i) { m[i] = -INFINITY; sum[i] = 0.f; o0[i] = 0.f; o1[i] = 0.f; }
+  // keys needed by this CTA (hard-causal: nothing beyond its last query)
+  const int q_last = min(p.Tq, qb * QB_F32 + QB_F32) - 1;
+  const int tk_cta = (p.mask_mode == 1) ? min(p.Tk, q_last + 1) : p.Tk;
+  for (int t0 = 0; t0 < tk_cta; t0 += KT_F32) {
+    const int tn = min(KT_F32, tk_cta - t0);
+    __syncthreads();  // previous tile fully consumed
+    for (int c = threadIdx.x; c < tn * 16; c += SA_THREADS) {
+      const int row = c >> 4, ch = c & 15;
+      *reinterpret_cast<float4*>(sk + row * KF_STRIDE + ch * 16) =
+          __ldg(reinterpret_cast<const float4*>(kg + static_cast<size_t>(t0 + row) * p.ldk + ch * 4));
+      *reinterpret_cast<float4*>(sv + row * VF_STRIDE + ch * 16) =
+          __ldg(reinterpret_cast<const float4*>(vg + static_cast<size_t>(t0 + row) * p.ldv + ch * 4));
     }
-    const int tk_eff = (p.mask_mode == 1) ? min(p.Tk, i + 1) : p.Tk;
-    float s[MAXJ_F32];
-    float m = -INFINITY;
+    __syncthreads();
 #pragma unroll
-    for (int jj = 0; jj < MAXJ_F32; ++jj) {
-      s[jj] = -INFINITY;
-      if (jj * 32 < tk_eff) {
+    for (int qi = 0; qi < 8; ++qi) {
+      const int i = q0 + qi;
+      if (i >= p.Tq) continue;  // warp-uniform
+      const int tk_eff = (p.mask_mode == 1) ? min(tn, i + 1 - t0) : tn;  // keys of this tile visible to query i
+      if (tk_eff <= 0) continue;
+      float q[DH];
+#pragma unroll
+      for (int ch = 0; ch < 16; ++ch) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(qg + static_cast<size_t>(i) * p.ldq) + ch);
+        q[ch * 4] = v.x; q[ch * 4 + 1] = v.y; q[ch * 4 + 2] = v.z; q[ch * 4 + 3] = v.w;
+      }
+      float s[KT_F32 / 32];
+      float tm = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < KT_F32 / 32; ++jj) {
+        s[jj] = -INFINITY;
         const int key = jj * 32 + lane;
         if (key < tk_eff) {
           const uint8_t* kr = sk + key * KF_STRIDE;
@@ -164,37 +183,50 @@ __global__ void __launch_bounds__(SA_THREADS) small_attn_f32_kernel(const SmallA
           float acc = ((a0 + a1) + (a2 + a3)) * p.scale;
           if (p.mask_mode == 2) {
             acc = acc + p.mask_const;   // fp32 add: quantises the logit exactly as the reference's mask add does
-            if (p.causal_soft && key > i) acc = acc + (-10000.0f);
+            if (p.causal_soft && (t0 + key) > i) acc = acc + (-10000.0f);
           }
           s[jj] = acc;
-          m = fmaxf(m, acc);
+          tm = fmaxf(tm, acc);
         }
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float sum = 0.f;
+      for (int o = 16; o > 0; o >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, o));
+      const float m_new = fmaxf(m[qi], tm);
+      const float corr = expf(m[qi] - m_new);  // 0 on the first tile (m = -inf)
+      float ts = 0.f;
 #pragma unroll
-    for (int jj = 0; jj < MAXJ_F32; ++jj) {
-      if (jj * 32 < tk_eff) { s[jj] = expf(s[jj] - m); sum += s[jj]; }
-    }
+      for (int jj = 0; jj < KT_F32 / 32; ++jj) {
+        s[jj] = expf(s[jj] - m_new);  // exp(-inf) = 0 for masked / absent keys
+        ts += s[jj];
+      }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.0f / sum;
-    float o0 = 0.f, o1 = 0.f;
+      for (int o = 16; o > 0; o >>= 1) ts += __shfl_xor_sync(0xffffffffu, ts, o);
+      float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-    for (int jj = 0; jj < MAXJ_F32; ++jj) {
-      if (jj * 32 < tk_eff) {
-        const int nk = min(32, tk_eff - jj * 32);
-        for (int j = 0; j < nk; ++j) {
-          const float pj = __shfl_sync(0xffffffffu, s[jj], j);
-          const float2 vv = *reinterpret_cast<const float2*>(sv + (jj * 32 + j) * VF_STRIDE + lane * 8);
-          o0 = fmaf(pj, vv.x, o0);
-          o1 = fmaf(pj, vv.y, o1);
+      for (int jj = 0; jj < KT_F32 / 32; ++jj) {
+        if (jj * 32 < tk_eff) {
+          const int nk = min(32, tk_eff - jj * 32);
+          for (int j = 0; j < nk; ++j) {
+            const float pj = __shfl_sync(0xffffffffu, s[jj], j);
+            const float2 vv = *reinterpret_cast<const float2*>(sv + (jj * 32 + j) * VF_STRIDE + lane * 8);
+            a0 = fmaf(pj, vv.x, a0);
+            a1 = fmaf(pj, vv.y, a1);
+          }
         }
       }
+      m[qi] = m_new;
+      sum[qi] = sum[qi] * corr + ts;
+      o0[qi] = o0[qi] * corr + a0;
+      o1[qi] = o1[qi] * corr + a1;
     }
-    *reinterpret_cast<float2*>(og + static_cast<size_t>(i) * p.ldo + lane * 2) = make_float2(o0 * inv, o1 * inv);
+  }
+#pragma unroll
+  for (int qi = 0; qi < 8; ++qi) {
+    const int i = q0 + qi;
+    if (i < p.Tq) {
+      const float inv = 1.0f / sum[qi];
+      *reinterpret_cast<float2*>(og + static_cast<size_t>(i) * p.ldo + lane * 2) = make_float2(o0[qi] * inv, o1[qi] * inv);
+    }
   }
 }
 
@@ -202,16 +234,15 @@ __global__ void __launch_bounds__(SA_THREADS) small_attn_f32_kernel(const SmallA
 
 int small_attn_f32_launch(const SmallAttnF32Params& p, cudaStream_t stream) {
   if (p.B <= 0 || p.H <= 0 || p.Tq <= 0 || p.Tk <= 0) return -3;
-  if (p.Tk > MAX_TK_F32) return -6;
-  const size_t smem = static_cast<size_t>(p.Tk) * (KF_STRIDE + VF_STRIDE);
+  const size_t smem = static_cast<size_t>(KT_F32) * (KF_STRIDE + VF_STRIDE);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(small_attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         MAX_TK_F32 * (KF_STRIDE + VF_STRIDE));
+    cudaError_t e = cudaFuncSetAttribute(small_attn_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  small_attn_f32_kernel<<<p.B * p.H, SA_THREADS, smem, stream>>>(p);
+  const int q_blocks = (p.Tq + QB_F32 - 1) / QB_F32;
+  small_attn_f32_kernel<<<p.B * p.H * q_blocks, SA_THREADS, smem, stream>>>(p, q_blocks);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -166,7 +166,7 @@ HB_API int hb_moment_create(const HbMomentConfig* cfg, const HbMomentWeights* w,
  * output); asr fp32 [B,T,asr_dim]; masks int64 [B,T] (boundary_mask may be NULL, as in moment retrieval).
  * out_feats fp32 [B,T,hidden] (may be NULL); out_logits fp32 [B,T,3] = (start, end, segment).  All GEMMs run as 3-term
  * split-bf16 tcgen05 GEMMs (fp32-accurate) and attention in fp32, so that the integer outputs of the MR / MS decoders
- * match the fp32 reference.  T <= 400 and T <= max_pos. */
+ * match the fp32 reference.  T <= max_pos (2048, the reference's position-embedding cap, modeling.py:110). */
 HB_API int hb_moment_forward(HbMoment* m, const float* video, const float* text_feat, const float* asr,
                              const int64_t* video_mask, const int64_t* moment_mask, const int64_t* boundary_mask, int B, int T,
                              int flags, float* out_feats, float* out_logits, void* stream);

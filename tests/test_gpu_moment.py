@@ -145,11 +145,32 @@ def test_trim_feats(model):
     assert torch.equal(got, mo.trim_feats(x, mask, 20))
 
 
-def test_rejects_long_clips(model):
+def test_long_clip_matches_oracle(hb):
+    """T = 700 frames (> one 256-key attention tile, ragged second sample): shared features and MR prediction vs the CPU oracle."""
+    clip = FixedText()
+    m = moment.MomentModel(-1, 384, moment.default_args(), clip_model=clip, max_rows=1400, max_batch=2)
+    sd = synthetic.make_moment_state_dict(seed=3)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    b = synthetic.make_moment_batch(2, 700, seed=21)
+    clip.feat = b["text_feat"]
+    with torch.no_grad():
+        ref = mo.moment_shared(sd, b["vis_feats"], b["text_feat"], b["vis_mask"], b["moment_mask"], b["asr_feats"])
+        ref_pred, _, _ = mo.test_moment_retrieval(sd, b, b["text_feat"])
+    got = m.foward_moment_shared(b["vis_feats"], b["text_feat"], b["vis_mask"], moment_mask=b["moment_mask"], asr_feats=b["asr_feats"])
+    assert rel(got, ref) < 2e-4
+    b["tasks"] = ["moment_retrieval"] * 2
+    assert m.test_step(b)["prediction"] == ref_pred
+
+
+def test_rejects_clips_beyond_position_embeddings(model):
     m, _ = model
-    b = synthetic.make_moment_batch(1, 401, seed=1, ragged=False)
-    with pytest.raises(RuntimeError, match="> 400 frames"):
-        m.foward_moment_shared(b["vis_feats"], b["text_feat"], b["vis_mask"], moment_mask=b["moment_mask"], asr_feats=b["asr_feats"])
+    b = synthetic.make_moment_batch(1, 2049, seed=1, ragged=False)
+    m2 = moment.MomentModel(-1, 384, moment.default_args(), clip_model=FixedText(), max_rows=2049, max_batch=1)
+    m2.load_state_dict(synthetic.make_moment_state_dict(seed=3), strict=True)
+    m2 = m2.to(DEV)
+    with pytest.raises(RuntimeError, match="max_position_embeddings"):
+        m2.foward_moment_shared(b["vis_feats"], b["text_feat"], b["vis_mask"], moment_mask=b["moment_mask"], asr_feats=b["asr_feats"])
 
 
 def _write_vocab(tmp_path):
