@@ -25,6 +25,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 int g_cg = 2;
+int g_attn_version = 2;
 int g_num_sms = 148;
 bool g_inited = false;
 
@@ -226,6 +227,12 @@ const char* hb_strerror(int code) {
 
 int64_t hb_launch_count(void) { return g_launches.load(); }
 
+int hb_set_attention_version(int v) {
+  if (v != 1 && v != 2) return fail(HB_ERR_INVALID, "attention version must be 1 or 2");
+  g_attn_version = v;
+  return HB_OK;
+}
+
 int hb_set_gemm_cta_group(int cg) {
   if (cg != 1 && cg != 2) return fail(HB_ERR_INVALID, "cta group must be 1 or 2");
   g_cg = cg;
@@ -342,7 +349,7 @@ static int vit_encode_chunk(HbVit* m, const float* frames, int B, float* out, cu
     if ((r = run_gemm(m->h.tm, L.qkv, M, qkv, 3 * D, hb::EPI_BF16, s, nullptr, qscale, D))) return r;
     hb::AttnParams ap;
     ap.qkv = qkv; ap.out = m->h.ptr(); ap.B = B; ap.H = c.heads;
-    HB_LAUNCH_P(CAT_VIT_ATTN, 4.0 * B * c.heads * 257.0 * 257.0 * 88.0, s, hb::vit_attn_launch(ap, s));
+    HB_LAUNCH_P(CAT_VIT_ATTN, 4.0 * B * c.heads * 257.0 * 257.0 * 88.0, s, g_attn_version == 1 ? hb::vit_attn_launch(ap, s) : hb::vit_attn2_launch(ap, s));
     if ((r = run_gemm(m->h.tm, L.proj, M, x, D, hb::EPI_F32, s, x))) return r;
     ln.w = L.n2w.ptr(); ln.b = L.n2b.ptr();
     HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, true, s));
@@ -578,7 +585,7 @@ int hb_vit_attention(const void* qkv, void* out, int64_t B, int H, void* stream)
   hb::AttnParams ap;
   ap.qkv = static_cast<const __nv_bfloat16*>(qkv); ap.out = static_cast<__nv_bfloat16*>(out);
   ap.B = static_cast<int>(B); ap.H = H;
-  HB_LAUNCH(hb::vit_attn_launch(ap, static_cast<cudaStream_t>(stream)));
+  HB_LAUNCH(g_attn_version == 1 ? hb::vit_attn_launch(ap, static_cast<cudaStream_t>(stream)) : hb::vit_attn2_launch(ap, static_cast<cudaStream_t>(stream)));
   return HB_OK;
 }
 

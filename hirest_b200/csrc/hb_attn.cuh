@@ -16,7 +16,8 @@ struct AttnParams {
   int H = 0;
   long long* timing = nullptr;  // debug (HB_ATTN_TIMING builds): 16 clock64 stamps per CTA
 };
-int vit_attn_launch(const AttnParams& p, cudaStream_t stream);
+int vit_attn_launch(const AttnParams& p, cudaStream_t stream);   // v1: one CTA per (frame, head), P through smem
+int vit_attn2_launch(const AttnParams& p, cudaStream_t stream);  // v2: one CTA per 128-query tile, 2 CTAs/SM, P in TMEM
 
 // Generic small-sequence attention on CUDA cores (text tower, MomentModel encoder, caption decoder):
 //   q: bf16 [B, Tq, ldq] (+ head*64), k/v: bf16 [B, Tk, ldk], head_dim 64, scores = q.k * scale

@@ -81,8 +81,15 @@ def test_layernorm(hb, D, eps):
     assert rel(y16, ref) < 3e-3
 
 
+@pytest.fixture(params=[2, 1], ids=["attn_v2", "attn_v1"])
+def attn_version(request, hb):
+    _lib.check(hb.hb_set_attention_version(request.param))
+    yield request.param
+    _lib.check(hb.hb_set_attention_version(2))
+
+
 @pytest.mark.parametrize("B,H", [(1, 1), (3, 4), (2, 16)])
-def test_vit_attention(hb, B, H):
+def test_vit_attention(hb, attn_version, B, H):
     """vit_model.py:127-147 on [B,257,3*H*88] (q pre-scaled): all three code paths — tensor-core rows, extra key, extra query."""
     torch.manual_seed(B * 100 + H)
     D = H * 88
@@ -97,7 +104,7 @@ def test_vit_attention(hb, B, H):
     assert err[:, :256].max() < 0.02 and err[:, 256].max() < 0.02
 
 
-def test_vit_attention_peaked_softmax(hb):
+def test_vit_attention_peaked_softmax(hb, attn_version):
     """Large logits: one key dominates, including the extra key (token 256) — exercises the max/rescale path."""
     torch.manual_seed(7)
     B, H, D = 2, 2, 176
