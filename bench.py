@@ -29,6 +29,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "frames/sec encoded+scored (EVA-CLIP-g/14 224px)"
+# dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, mean over the four GEMMs of one ViT layer at 1024 frames
+# (QKV 2.93, proj 4.30, fc1 3.99, fc2 10.07 GB) from the `ncu --set full` capture in profiles/r01_one_layer_ncu_full.txt;
+# algorithmic bytes of the same four launches: 2.96 + 3.70 + 3.99 + 6.19 GB (fc2 re-reads its A operand).
+GEMM_TRAFFIC_BYTES_PER_LAUNCH = 5.32e9
 UNIT = "frames/s"
 
 
@@ -239,32 +243,56 @@ def main():
         # ---------------- e2e through the public API with host buffers
         e2e = None
         if not args.no_e2e:
-            frames_host = torch.empty((B, 3, S, S), dtype=torch.float32).pin_memory()
-            frames_host.copy_(frames_dev)
+            # raw uint8 frames in pinned host memory: ToTensor + Normalize run on the GPU inside the patch gather
+            # (encode_image accepts uint8), so a step moves 154 MB over PCIe instead of 617 MB of fp32 frames
+            gen = torch.Generator().manual_seed(200 + rank)
+            frames_host = torch.randint(0, 256, (B, 3, S, S), generator=gen, dtype=torch.uint8).pin_memory()
             tokens_host = tokens_step.cpu().pin_memory()
             scores_host = torch.empty((Q, world * (B // Fv)), dtype=torch.float32).pin_memory()
 
-            def step_e2e():
-                f = frames_host.to(dev, non_blocking=True)
-                tk = tokens_host.to(dev, non_blocking=True)
-                t_new = retrieval.normalize(model.encode_text(tk))
-                text_hat[:new_q].copy_(t_new)
-                sc, _ = retrieval.encode_and_score(model, f, Fv, text_hat, exact=True)
-                scores_host.copy_(sc, non_blocking=True)
-                torch.cuda.current_stream().synchronize()  # the caller holds the scores on the host after every step
-                return scores_host
+            # Streaming pipeline a user would write: the H2D copy of step i+1 (pinned host -> device, side stream) overlaps
+            # the compute of step i; every step's copy and its D2H result read are inside the timed region.
+            copy_stream = torch.cuda.Stream(device=dev)
+            dev_bufs = [torch.empty((B, 3, S, S), dtype=torch.uint8, device=dev) for _ in range(2)]
+            copied = [torch.cuda.Event(), torch.cuda.Event()]
+            consumed = [None, None]
 
-            for _ in range(max(1, min(args.warmup, 2))):
-                step_e2e()
+            def issue_copy(i):
+                with torch.cuda.stream(copy_stream):
+                    if consumed[i % 2] is not None:
+                        copy_stream.wait_event(consumed[i % 2])
+                    dev_bufs[i % 2].copy_(frames_host, non_blocking=True)
+                    copied[i % 2].record(copy_stream)
+
+            def run_e2e(n):
+                for k in range(2):
+                    consumed[k] = None
+                issue_copy(0)
+                for i in range(n):
+                    if i + 1 < n:
+                        issue_copy(i + 1)
+                    cur = torch.cuda.current_stream()
+                    cur.wait_event(copied[i % 2])
+                    tk = tokens_host.to(dev, non_blocking=True)
+                    t_new = retrieval.normalize(model.encode_text(tk))
+                    text_hat[:new_q].copy_(t_new)
+                    sc, _ = retrieval.encode_and_score(model, dev_bufs[i % 2], Fv, text_hat, exact=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    consumed[i % 2] = ev
+                    scores_host.copy_(sc, non_blocking=True)
+                    cur.synchronize()  # the caller holds this step's scores on the host before the next step starts
+
+            run_e2e(max(1, min(args.warmup, 2)))
             barrier()
             e0.record()
-            for _ in range(args.steps):
-                step_e2e()
+            run_e2e(args.steps)
             e1.record()
             barrier()
             ms_e2e = max_over_ranks(e0.elapsed_time(e1))
             e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                   "h2d_bytes_per_step": frames_host.numel() * 4 + tokens_host.numel() * 8,
+                   "h2d_bytes_per_step": frames_host.numel() * frames_host.element_size() + tokens_host.numel() * 8,
+                   "input": "uint8 frames [B,3,224,224] in pinned host memory, normalised on the GPU; H2D double-buffered on a side stream",
                    "d2h_bytes_per_step": scores_host.numel() * 4, "ms_per_step": ms_e2e / args.steps}
 
     if rank != 0:
@@ -293,7 +321,7 @@ def main():
                    "residual_stream": "fp32", "gemm_operands": "bf16, fp32 accumulate", "l2": "inputs_larger_than_l2",
                    "parallelism": f"frame-shard dp{world}" if world > 1 else "single GPU"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                     "frac": achieved / peaks["bf16_tflops"], "traffic": GEMM_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peaks["source"],
                      "kernel": "hb::gemm_kernel<CG=2,*> (all tcgen05 GEMM launches)", "launches_per_step": gemm_launches / args.steps,
                      "gemm_share_of_kernel_time": gemm_ms / kernel_ms_total if kernel_ms_total else None,
                      "whole_step_tflops": flops_frame * B / (ms_total / args.steps * 1e-3) / 1e12,

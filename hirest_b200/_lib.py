@@ -92,6 +92,7 @@ SIGNATURES = {
     "hb_vit_create": (C.c_int, [C.POINTER(HbVitConfig), C.POINTER(HbVitWeights), C.c_int, C.c_void_p,
                                 C.POINTER(C.c_void_p)]),
     "hb_vit_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "hb_vit_encode_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p, C.c_void_p]),
     "hb_vit_set_tap": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "hb_vit_destroy": (None, [C.c_void_p]),
     "hb_text_create": (C.c_int, [C.POINTER(HbTextConfig), C.POINTER(HbTextWeights), C.c_int, C.c_void_p,

@@ -324,7 +324,8 @@ int hb_vit_set_tap(HbVit* m, int layer, float* dst) {
   return HB_OK;
 }
 
-static int vit_encode_chunk(HbVit* m, const float* frames, int B, float* out, cudaStream_t s) {
+static int vit_encode_chunk(HbVit* m, const float* frames, const uint8_t* frames_u8, const float* mean, const float* stdv, int B,
+                            float* out, cudaStream_t s) {
   const HbVitConfig& c = m->cfg;
   const int D = c.width, T = m->T, F = c.mlp_hidden, E = c.embed_dim;
   const long long M = static_cast<long long>(B) * T;
@@ -332,7 +333,10 @@ static int vit_encode_chunk(HbVit* m, const float* frames, int B, float* out, cu
   __nv_bfloat16* qkv = m->qkv.as<__nv_bfloat16>();
   int r;
   // patch embed: gather -> GEMM (+bias +pos, rows remapped past the cls slot); cls row separately
-  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::im2col_patch_launch(frames, m->col.ptr(), B, c.image_size, c.patch_size, m->patch.Kpad, s));
+  if (frames_u8 != nullptr)
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::im2col_patch_u8_launch(frames_u8, m->col.ptr(), B, c.image_size, c.patch_size, m->patch.Kpad, mean, stdv, s));
+  else
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::im2col_patch_launch(frames, m->col.ptr(), B, c.image_size, c.patch_size, m->patch.Kpad, s));
   if ((r = run_gemm(m->col.tm, m->patch, static_cast<long long>(B) * (T - 1), x, D, hb::EPI_F32_ROWADD, s, nullptr, 1.f, 0,
                     m->pos.ptr() + D, T - 1, T, 1)))
     return r;
@@ -375,7 +379,21 @@ int hb_vit_encode(HbVit* m, const float* frames, int64_t B, float* out, void* st
   const size_t frame_elems = static_cast<size_t>(3) * m->cfg.image_size * m->cfg.image_size;
   for (int64_t b0 = 0; b0 < B; b0 += m->max_batch) {
     const int nb = static_cast<int>(std::min<int64_t>(m->max_batch, B - b0));
-    int r = vit_encode_chunk(m, frames + b0 * frame_elems, nb, out + b0 * m->cfg.embed_dim, s);
+    int r = vit_encode_chunk(m, frames + b0 * frame_elems, nullptr, nullptr, nullptr, nb, out + b0 * m->cfg.embed_dim, s);
+    if (r) return r;
+  }
+  return HB_OK;
+}
+
+int hb_vit_encode_u8(HbVit* m, const uint8_t* frames, int64_t B, const float* mean, const float* stdv, float* out, void* stream) {
+  if (B == 0 && m) return HB_OK;
+  if (!m || !frames || !out || !mean || !stdv) return fail(HB_ERR_INVALID, "null argument");
+  if (B < 0) return fail(HB_ERR_INVALID, "negative batch");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t frame_elems = static_cast<size_t>(3) * m->cfg.image_size * m->cfg.image_size;
+  for (int64_t b0 = 0; b0 < B; b0 += m->max_batch) {
+    const int nb = static_cast<int>(std::min<int64_t>(m->max_batch, B - b0));
+    int r = vit_encode_chunk(m, nullptr, frames + b0 * frame_elems, mean, stdv, nb, out + b0 * m->cfg.embed_dim, s);
     if (r) return r;
   }
   return HB_OK;

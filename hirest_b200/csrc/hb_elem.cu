@@ -107,6 +107,36 @@ __global__ void __launch_bounds__(256) im2col_patch_kernel(const float* __restri
   }
 }
 
+// Same gather from raw uint8 frames [B,3,S,S] with the CPU preprocessing folded in: ToTensor (x / 255) and
+// Normalize ((x - mean[c]) / std[c]) of EVA_clip/eva_clip.py:144-153, computed in fp32 exactly as torchvision does.
+__global__ void __launch_bounds__(256) im2col_patch_u8_kernel(const uint8_t* __restrict__ img, __nv_bfloat16* __restrict__ out,
+                                                              int B, int S, int P, int ldo, float m0, float m1, float m2,
+                                                              float s0, float s1, float s2) {
+  const int G = S / P;
+  const long long total = static_cast<long long>(B) * G * G * 3 * P;
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int pw = static_cast<int>(t % G);
+  long long r = t / G;
+  const int kh = static_cast<int>(r % P); r /= P;
+  const int c = static_cast<int>(r % 3); r /= 3;
+  const int ph = static_cast<int>(r % G);
+  const int b = static_cast<int>(r / G);
+  const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2);
+  const float sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+  const uint8_t* src = img + ((static_cast<long long>(b) * 3 + c) * S + (ph * P + kh)) * S + pw * P;
+  __nv_bfloat16* dst = out + (static_cast<long long>(b) * G * G + ph * G + pw) * ldo + (c * P + kh) * P;
+  for (int i = 0; i < P; i += 2) {
+    const uint16_t two = *reinterpret_cast<const uint16_t*>(src + i);
+    const float a = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(two & 0xFF), 255.0f), mean), sd);
+    const float bq = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(two >> 8), 255.0f), mean), sd);
+    *reinterpret_cast<uint32_t*>(dst + i) = pack2(a, bq);
+  }
+  if (c == 2 && kh == P - 1) {
+    for (int i = 3 * P * P; i < ldo; i += 2) *reinterpret_cast<uint32_t*>(dst + (i - (c * P + kh) * P)) = 0u;
+  }
+}
+
 // x[b*T + 0, :] = cls + pos[0]   (vit_model.py:330-333)
 __global__ void cls_row_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos, int B,
                                int T, int D) {
@@ -239,6 +269,15 @@ int im2col_patch_launch(const float* img, __nv_bfloat16* out, int B, int S, int 
   if (S % P != 0 || P % 2 != 0 || ldo < 3 * P * P || ldo % 2 != 0) return -7;
   const long long total = static_cast<long long>(B) * (S / P) * (S / P) * 3 * P;
   im2col_patch_kernel<<<blocks_for(total, 256), 256, 0, s>>>(img, out, B, S, P, ldo);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int im2col_patch_u8_launch(const uint8_t* img, __nv_bfloat16* out, int B, int S, int P, int ldo, const float mean[3],
+                           const float stdv[3], cudaStream_t s) {
+  if (S % P != 0 || P % 2 != 0 || S % 2 != 0 || ldo < 3 * P * P || ldo % 2 != 0) return -7;
+  const long long total = static_cast<long long>(B) * (S / P) * (S / P) * 3 * P;
+  im2col_patch_u8_kernel<<<blocks_for(total, 256), 256, 0, s>>>(img, out, B, S, P, ldo, mean[0], mean[1], mean[2], stdv[0], stdv[1],
+                                                                stdv[2]);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <cstdint>
 
 namespace hb {
 
@@ -19,6 +20,8 @@ struct LayerNormParams {
 };
 int layernorm_launch(const LayerNormParams& p, bool out_bf16, cudaStream_t s);
 int im2col_patch_launch(const float* img, __nv_bfloat16* out, int B, int S, int P, int ldo, cudaStream_t s);
+int im2col_patch_u8_launch(const uint8_t* img, __nv_bfloat16* out, int B, int S, int P, int ldo, const float mean[3],
+                           const float stdv[3], cudaStream_t s);
 int cls_row_launch(float* x, const float* cls, const float* pos, int B, int T, int D, cudaStream_t s);
 int text_embed_launch(const long long* ids, const float* tok, const float* pos, float* x, int* eot_row, int Q, int C, int W,
                       int V, cudaStream_t s);

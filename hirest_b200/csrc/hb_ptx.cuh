@@ -113,6 +113,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, uint64_
       : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// L2 eviction-priority policies for TMA loads (same encodings as CUTLASS' TMA::CacheHintSm90)
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, uint64_t hint) {
+  const uint32_t bar_leader = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, "
+      "%4}], [%2], %5;"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_leader), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
 // 3D tiled load, CTA-local destination + barrier.
 __device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(

@@ -3,6 +3,7 @@
 Same names, argument meaning and error behaviour as the reference for this path:
   * ``EVA_CLIP(embed_dim, vision_cfg, text_cfg)``             EVA_clip/eva_model.py:273-315
   * ``.encode_image(image)`` / ``.encode_text(text)``          EVA_clip/eva_model.py:317-321
+    (encode_image additionally accepts raw uint8 frames [B,3,224,224]; ToTensor + Normalize then run on the GPU)
   * ``.visual.image_size / image_mean / image_std``            EVA_clip/eva_clip.py:117-118,170
   * ``state_dict()`` keys ``visual.*`` / ``text.*``            SURVEY.md Appendix B (strict load works)
   * ``build_eva_model_and_transforms(model_name, pretrained, precision, device, ...)``  eva_clip.py:155-171
@@ -191,13 +192,21 @@ class VisionTransformer(_ParamTree):
         dev = self.cls_token.device
         if x.device != dev:
             raise RuntimeError(f"input is on {x.device}, model on {dev}")
-        x = x.float().contiguous()
         out = torch.empty((B, self.embed_dim), dtype=torch.float32, device=dev)
         lib = _lib.load()
         with torch.cuda.device(dev):
             if tap is not None:
                 _lib.check(lib.hb_vit_set_tap(eng.handle, int(tap[0]), tap[1].data_ptr()), "hb_vit_set_tap")
-            _lib.check(lib.hb_vit_encode(eng.handle, x.data_ptr(), B, out.data_ptr(), _lib.stream_ptr(dev)), "hb_vit_encode")
+            if x.dtype == torch.uint8:
+                # raw frames: ToTensor + Normalize(image_mean, image_std) happen inside the patch-gather kernel
+                x = x.contiguous()
+                mean = (C.c_float * 3)(*self.image_mean)
+                std = (C.c_float * 3)(*self.image_std)
+                _lib.check(lib.hb_vit_encode_u8(eng.handle, x.data_ptr(), B, mean, std, out.data_ptr(), _lib.stream_ptr(dev)),
+                           "hb_vit_encode_u8")
+            else:
+                x = x.float().contiguous()
+                _lib.check(lib.hb_vit_encode(eng.handle, x.data_ptr(), B, out.data_ptr(), _lib.stream_ptr(dev)), "hb_vit_encode")
             if tap is not None:
                 lib.hb_vit_set_tap(eng.handle, -1, None)
         return out

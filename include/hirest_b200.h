@@ -97,6 +97,10 @@ typedef struct HbVit HbVit;
 HB_API int hb_vit_create(const HbVitConfig* cfg, const HbVitWeights* w, int max_batch, void* stream, HbVit** out);
 /* frames: fp32 [B,3,S,S] NCHW; out: fp32 [B, embed_dim] (un-normalised, like encode_image). */
 HB_API int hb_vit_encode(HbVit* m, const float* frames, int64_t B, float* out, void* stream);
+/* Same from raw uint8 frames [B,3,S,S] (0..255): the ToTensor + Normalize(mean, std) steps of the reference's CPU
+ * preprocessing (EVA_clip/eva_clip.py:144-153) are folded into the patch gather; mean / std are HOST arrays of 3 floats.
+ * 4x fewer host->device bytes than fp32 frames. */
+HB_API int hb_vit_encode_u8(HbVit* m, const uint8_t* frames, int64_t B, const float* mean, const float* stdv, float* out, void* stream);
 /* Debug / parity taps: copy the fp32 residual stream [B*T, D] after `layer` blocks (0 = after patch embed)
  * of the most recent chunk into `dst`.  Must be requested before encode via hb_vit_set_tap(layer, dst). */
 HB_API int hb_vit_set_tap(HbVit* m, int layer, float* dst);

@@ -137,3 +137,17 @@ def test_g14_encode_vs_reference_golden(hb, golden_dir):
         stock = eva_oracle.encode_image(sdb, frames.to(DEV).bfloat16(), cfg)
     print(f"g14: stock torch bf16 rel {rel(stock, g['image']):.3e}")
     assert e_img <= rel(stock, g["image"]) * 1.05
+
+
+def test_uint8_frames_match_cpu_preprocessing(tiny):
+    """Raw uint8 frames: ToTensor + Normalize(mean, std) folded into the patch gather == the reference's CPU transform
+    (EVA_clip/eva_clip.py:144-153) followed by encode_image — bit-identical embeddings."""
+    cfg, sd, model = tiny
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (3, 3, 224, 224), generator=g, dtype=torch.uint8)
+    mean = torch.tensor(model.visual.image_mean).view(1, 3, 1, 1)
+    std = torch.tensor(model.visual.image_std).view(1, 3, 1, 1)
+    f32 = (u8.float() / 255.0 - mean) / std          # ToTensor, then Normalize
+    a = model.encode_image(u8.to(DEV))
+    b = model.encode_image(f32.to(DEV))
+    assert torch.equal(a, b)
