@@ -43,7 +43,8 @@ struct Cfg {
 
 // Static persistent tile schedule shared by the three roles of a worker: tiles are visited n-fastest, worker w takes
 // tiles w, w + W, w + 2W, ...  (Tried and dropped: merging the narrow N-tail tiles of consecutive M-blocks into equal-cost
-// work units to keep workers in lockstep — fc2's DRAM reads went UP, 3.4 -> 6.5 GB at M = 131584, and it ran 9 % slower.)
+// work units to keep workers in lockstep — fc2's DRAM reads went UP, 3.4 -> 6.5 GB at M = 131584, and it ran 9 % slower;
+// a worker count coprime to the number of N tiles, so every worker meets the tail tile equally often — no effect.)
 struct TileIter {
   int t, stride, total, n_tiles;
   __device__ TileIter(int worker, int num_workers, int m_tiles, int n_tiles_) {
