@@ -38,7 +38,8 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
   static constexpr int STAGES = (CG == 1) ? 4 : 6;    // 192 KiB either way
   static constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per epilogue warp: one 32x32 fp32 transpose buffer
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + NUM_EPI_WARPS * EPI_STAGE_BYTES;
+  static constexpr int BIAS_BYTES = 2 * BN * 4;        // the tile's bias slice, one copy per accumulator buffer
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + NUM_EPI_WARPS * EPI_STAGE_BYTES + BIAS_BYTES;
 };
 
 // Static persistent tile schedule shared by the three roles of a worker: tiles are visited n-fastest, worker w takes
@@ -61,22 +62,20 @@ struct TileIter {
 // bf16-output epilogues (thread-per-row): r = 32 consecutive fp32 accumulator columns [col0, col0+32) of one row.
 template <int EPI>
 __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const uint32_t (&r)[32], long long row_out,
-                                                     int row_in, int col0, int n_valid) {
+                                                     int row_in, int col0, int n_valid, const float* sb /*smem bias of this chunk*/) {
   (void)row_in;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-  if (p.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+  {  // bias comes from the per-tile smem copy (zeros when the layer has none): broadcast LDS, no global-load latency here
+    const float4* b4 = reinterpret_cast<const float4*>(sb);
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
-      if (g * 4 < n_valid) {
-        const float4 b = __ldg(b4 + g);
-        v[4 * g + 0] += b.x;
-        v[4 * g + 1] += b.y;
-        v[4 * g + 2] += b.z;
-        v[4 * g + 3] += b.w;
-      }
+      const float4 b = b4[g];
+      v[4 * g + 0] += b.x;
+      v[4 * g + 1] += b.y;
+      v[4 * g + 2] += b.z;
+      v[4 * g + 3] += b.w;
     }
   }
   if constexpr (EPI == EPI_GELU_BF16) {
@@ -107,7 +106,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
   using C = Cfg<CG>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw;  // no static smem in this kernel: the dynamic window starts 1024-byte aligned (checked below)
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]
@@ -115,6 +115,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tmem_full_bar = bars + 2 * C::STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* sbias = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256 + NUM_EPI_WARPS * C::EPI_STAGE_BYTES);  // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -161,6 +162,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n_eff = min(BN, p.N - n0);
       const int row_a = m_blk * tile_m + static_cast<int>(cta_rank) * BM;
       const int row_w = n0 + static_cast<int>(cta_rank) * (n_eff / CG);
+      // (Tried and dropped: TMA L2-prefetch of the A boxes 8 k-blocks ahead — no measurable change; the ring is not latency-starved.)
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sa = smem + stage * C::STAGE_BYTES;
@@ -231,6 +233,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (p.remap_in > 0) row_out = static_cast<long long>(row_in / p.remap_in) * p.remap_out + (row_in % p.remap_in) + p.remap_off;
       const int c_begin = half * (BN / 2);
       const int c_end = min(n_eff, (half + 1) * (BN / 2));
+      // Stage this tile's bias slice in smem before the accumulator is ready (one element per epilogue thread): the
+      // per-chunk global bias loads were consumed immediately and left the epilogue warps waiting on L2 latency
+      // (fc1: 64 % tensor-pipe active with `stall_long_sb` on the bias FADDs, profiles/r01_one_layer_ncu_full.txt).
+      float* sb_tile = sbias + acc * BN;
+      {
+        const int et = (warp - 4) * 32 + lane;
+        sb_tile[et] = (p.bias != nullptr && et < n_eff) ? __ldg(p.bias + n0 + et) : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       if constexpr (EPI == EPI_F32 || EPI == EPI_F32_ROWADD) {
         // fp32 output (+ fp32 residual / row-add): the accumulator chunk is transposed through a per-warp swizzled smem
         // buffer so that every global access is a full 128-byte row segment (thread-per-row access costs 32 L1
@@ -304,7 +315,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           __syncwarp();
           const int col0 = n0 + c, n_valid = n_eff - c;
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias != nullptr && cc * 4 < n_valid) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + cc * 4));
+          if (cc * 4 < n_valid) b4 = *reinterpret_cast<const float4*>(sb_tile + c + cc * 4);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = 4 * i + rr_base;
@@ -344,7 +355,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c), r);
           tmem_ld_wait();
-          if (row_ok) epilogue_store_chunk<EPI>(p, r, row_out, row_in, n0 + c, n_eff - c);
+          if (row_ok) epilogue_store_chunk<EPI>(p, r, row_out, row_in, n0 + c, n_eff - c, sb_tile + c);
         }
       }
       tc_fence_before();
