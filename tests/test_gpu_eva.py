@@ -151,3 +151,29 @@ def test_uint8_frames_match_cpu_preprocessing(tiny):
     a = model.encode_image(u8.to(DEV))
     b = model.encode_image(f32.to(DEV))
     assert torch.equal(a, b)
+
+
+def test_g14_full_size_properties(hb):
+    """BASELINE configs[1] size (EVA-CLIP-g/14, 1024 frames) through size-independent properties: the 1024-frame batch in one
+    chunk, in chunks of 384 (ragged last chunk) and a sample of single frames give bit-identical embeddings; the retrieval
+    scores of the pooled videos equal the CPU scoring of the same embeddings; uint8 input equals CPU preprocessing."""
+    cfg = synthetic.EVA_G14
+    sd = synthetic.make_eva_state_dict(cfg, seed=0, device=DEV)
+    big = eva_clip.EVA_CLIP(**cfg, max_image_batch=1024, max_text_batch=8)
+    big.load_state_dict(sd, strict=True)
+    big = big.to(DEV).eval()
+    frames = synthetic.make_frames(1024, 224, seed=77, device=DEV)
+    full = big.encode_image(frames)
+    assert torch.isfinite(full).all()
+    small = eva_clip.EVA_CLIP(**cfg, max_image_batch=384, max_text_batch=8)
+    small.load_state_dict(sd, strict=True)
+    small = small.to(DEV).eval()
+    del sd
+    assert torch.equal(small.encode_image(frames), full)
+    for i in (0, 383, 384, 1023):
+        assert torch.equal(small.encode_image(frames[i:i + 1]), full[i:i + 1])
+    v_hat = retrieval.pool_normalize(full, 32)
+    t_hat = eva_oracle.normalize_text(torch.randn(64, cfg["embed_dim"], generator=torch.Generator().manual_seed(5)))
+    scores = retrieval.similarity(t_hat.to(DEV), v_hat)
+    ref = eva_oracle.similarity(t_hat, eva_oracle.pool_normalize_video(full.cpu(), 32))
+    assert float((scores.cpu() - ref).abs().max()) < 5e-7

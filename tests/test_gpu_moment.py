@@ -216,3 +216,26 @@ def test_step_captioning_early_finish(hb, golden, tmp_path):
     assert [len(x) for x in g["ids"]] == [48, 48, 2, 17]
     assert out["token_ids"] == g["ids"]
     assert out["prediction"] == g["text"]
+
+
+def test_config4_size_determinism_and_oracle_subset(hb):
+    """BASELINE configs[3] size (64 clips x 300 frames): two runs are bit-identical, each clip's result is independent of the batch
+    it is in, and the first two clips match the CPU oracle's moment-retrieval prediction."""
+    clip = FixedText()
+    m = moment.MomentModel(-1, 384, moment.default_args(), clip_model=clip, max_rows=64 * 300, max_batch=64)
+    sd = synthetic.make_moment_state_dict(seed=3)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    b = synthetic.make_moment_batch(64, 300, seed=31)
+    a1 = m.foward_moment_shared(b["vis_feats"], b["text_feat"], b["vis_mask"], moment_mask=b["moment_mask"], asr_feats=b["asr_feats"])
+    a2 = m.foward_moment_shared(b["vis_feats"], b["text_feat"], b["vis_mask"], moment_mask=b["moment_mask"], asr_feats=b["asr_feats"])
+    assert torch.equal(a1, a2)
+    sub = {k: (v[:2] if torch.is_tensor(v) else v) for k, v in b.items()}
+    a3 = m.foward_moment_shared(sub["vis_feats"], sub["text_feat"], sub["vis_mask"], moment_mask=sub["moment_mask"], asr_feats=sub["asr_feats"])
+    assert torch.equal(a3, a1[:2])
+    clip.feat = b["text_feat"]
+    b["tasks"] = ["moment_retrieval"] * 64
+    pred = m.test_step(b)["prediction"]
+    with torch.no_grad():
+        ref_pred, _, _ = mo.test_moment_retrieval(sd, sub, sub["text_feat"])
+    assert pred[:2] == ref_pred

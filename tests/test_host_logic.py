@@ -79,3 +79,27 @@ def test_moment_model_state_dict_layout_and_errors():
     b = synthetic.make_moment_batch(1, 16, seed=1)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.foward_moment_shared(b["vis_feats"], b["text_feat"], b["vis_mask"], moment_mask=b["moment_mask"], asr_feats=b["asr_feats"])
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (CPU oracle port) prints one JSON line with the contract keys; tiny config keeps it fast."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--tiny", "--steps", "2", "--warmup", "1",
+                          "--cpu-frames", "4"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype",
+              "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    # non-zero ranks of a torchrun launch exit quietly
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--tiny"], capture_output=True, text=True,
+                         timeout=120, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
