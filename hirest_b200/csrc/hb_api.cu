@@ -26,6 +26,7 @@ thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 int g_cg = 2;
 int g_attn_version = 2;
+int g_ln_fold = 1;   // fold the ViT block LayerNorms into the QKV / fc1 GEMM epilogues (no LayerNorm kernel)
 int g_num_sms = 148;
 bool g_inited = false;
 
@@ -90,13 +91,38 @@ struct DevBuf {
 
 // fp32 [N,K] (optionally transposed source [K,N]) -> bf16 [N,Kpad], zero padded.
 __global__ void repack_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int K, int Kpad,
-                                     int transposed) {
+                                     int transposed, const float* __restrict__ gamma) {
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<long long>(N) * Kpad) return;
   const int n = static_cast<int>(t / Kpad), k = static_cast<int>(t % Kpad);
   float v = 0.f;
   if (k < K) v = transposed ? src[static_cast<long long>(k) * N + n] : src[static_cast<long long>(n) * K + k];
+  if (gamma != nullptr && k < K) v *= gamma[k];   // LayerNorm fold: W' = W * diag(gamma)
   dst[t] = __float2bfloat16(v);
+}
+
+// LayerNorm-fold vectors of one Linear (one warp per output feature n):
+//   c1[n] = sum_k W'[n,k]  with the bf16-ROUNDED folded weight (exactly what the tensor core multiplies, so a constant row
+//           still normalises to beta W^T), c2[n] = sum_k beta_k W[n,k] + bias[n]
+__global__ void ln_fold_vectors_kernel(const __nv_bfloat16* __restrict__ wq, int Kpad, const float* __restrict__ w,
+                                       const float* __restrict__ beta, const float* __restrict__ bias, float* __restrict__ c1,
+                                       float* __restrict__ c2, int N, int K) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float a = 0.f, b = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    a += __bfloat162float(wq[static_cast<long long>(n) * Kpad + k]);
+    b = fmaf(beta[k], w[static_cast<long long>(n) * K + k], b);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane == 0) {
+    c1[n] = a;
+    c2[n] = b + (bias != nullptr ? bias[n] : 0.f);
+  }
 }
 
 // A Linear layer held by a handle: bf16 weight [N,Kpad] + fp32 bias + TMA map.
@@ -106,14 +132,15 @@ struct Linear {
   int N = 0, K = 0, Kpad = 0, cg = 2;
   bool has_bias = false;
   // bias may be assembled from up to three pieces (q_bias | zeros | v_bias), each of length N/3.
+  DevBuf c1;  // LayerNorm fold (see GemmEpilogue): c1 here, c2 replaces the bias
   int init(const float* w_src, int N_, int K_, const float* bias, bool transposed, cudaStream_t s, const float* bias_q = nullptr,
-           const float* bias_v = nullptr) {
+           const float* bias_v = nullptr, const float* ln_gamma = nullptr, const float* ln_beta = nullptr) {
     N = N_; K = K_; cg = (N_ % 32 == 0) ? g_cg : 1;  // CTA pairs need N % 32 == 0
     Kpad = (K + 7) / 8 * 8;
     if (int r = w.alloc(static_cast<size_t>(N) * Kpad * 2)) return r;
     const long long total = static_cast<long long>(N) * Kpad;
     repack_weight_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w_src, w.as<__nv_bfloat16>(), N, K, Kpad,
-                                                                                     transposed ? 1 : 0);
+                                                                                     transposed ? 1 : 0, ln_gamma);
     HB_CUDA(cudaGetLastError());
     if (bias != nullptr || bias_q != nullptr) {
       has_bias = true;
@@ -126,6 +153,19 @@ struct Linear {
         HB_CUDA(cudaMemcpyAsync(b.p, bias_q, static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice, s));
         HB_CUDA(cudaMemcpyAsync(b.as<float>() + 2 * D, bias_v, static_cast<size_t>(D) * 4, cudaMemcpyDeviceToDevice, s));
       }
+    }
+    if (ln_gamma != nullptr) {   // replace the bias by c2 and build c1 (needs the plain bias first, done above)
+      if (transposed) return fail(HB_ERR_INVALID, "LayerNorm fold on a transposed weight is not supported");
+      if (int r = c1.alloc(static_cast<size_t>(N) * 4)) return r;
+      DevBuf c2;
+      if (int r = c2.alloc(static_cast<size_t>(N) * 4)) return r;
+      ln_fold_vectors_kernel<<<static_cast<unsigned>((N + 7) / 8), 256, 0, s>>>(w.as<__nv_bfloat16>(), Kpad, w_src, ln_beta,
+                                                                                has_bias ? b.as<float>() : nullptr, c1.as<float>(),
+                                                                                c2.as<float>(), N, K);
+      HB_CUDA(cudaGetLastError());
+      if (!has_bias) { if (int r = b.alloc(static_cast<size_t>(N) * 4)) return r; has_bias = true; }
+      HB_CUDA(cudaMemcpyAsync(b.p, c2.p, static_cast<size_t>(N) * 4, cudaMemcpyDeviceToDevice, s));
+      HB_CUDA(cudaStreamSynchronize(s));  // c2 is a temporary
     }
     int r = hb::make_tmap_bf16(&tm, w.p, N, Kpad, Kpad, hb::gemm_w_box_rows(cg));
     if (r) return fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled(weight %dx%d) failed: %d", N, Kpad, r);
@@ -160,15 +200,30 @@ struct F32Vec {
   const float* ptr() const { return d.as<float>(); }
 };
 
+struct LnFold {
+  const float* stats_in = nullptr;  // consumer side
+  float eps = 1e-6f;
+  int dim = 0;
+  void* xb_out = nullptr;           // producer side
+  int ld_xb = 0;
+  float* stats_out = nullptr;
+  int slots = 1;                    // partial-sum slots per row = ceil(D / 128)
+};
+
 int run_gemm(const CUtensorMap& tmA, const Linear& L, long long M, void* out, int ldo, int epi, cudaStream_t s,
              const float* resid = nullptr, float qscale = 1.f, int qcols = 0, const float* rowadd = nullptr, int remap_in = 0,
-             int remap_out = 0, int remap_off = 0) {
+             int remap_out = 0, int remap_off = 0, const LnFold* lf = nullptr) {
   hb::GemmParams p;
+  if (lf != nullptr) {
+    p.stats_in = lf->stats_in; p.ln_eps = lf->eps; p.ln_dim = lf->dim; p.c1 = L.c1.as<float>();
+    p.xb_out = lf->xb_out; p.ld_xb = lf->ld_xb; p.stats_out = lf->stats_out; p.ln_slots = lf->slots;
+  }
   p.M = static_cast<int>(M); p.N = L.N; p.K = L.Kpad;
   p.bias = L.bias(); p.out = out; p.ldo = ldo; p.resid = resid;
   p.qscale = qscale; p.qcols = qcols;
   p.rowadd = rowadd; p.remap_in = remap_in; p.remap_out = remap_out; p.remap_off = remap_off;
-  HB_LAUNCH_P(epi == hb::EPI_BF16 ? CAT_GEMM_BF16 : (epi == hb::EPI_GELU_BF16 ? CAT_GEMM_GELU : CAT_GEMM_F32),
+  HB_LAUNCH_P((epi == hb::EPI_BF16 || epi == hb::EPI_BF16_LN) ? CAT_GEMM_BF16
+                  : ((epi == hb::EPI_GELU_BF16 || epi == hb::EPI_GELU_BF16_LN) ? CAT_GEMM_GELU : CAT_GEMM_F32),
               2.0 * static_cast<double>(M) * L.N * L.K, s, hb::gemm_launch(tmA, L.tm, p, epi, L.cg, g_num_sms, s));
   return 0;
 }
@@ -190,8 +245,9 @@ struct HbVit {
   std::vector<std::unique_ptr<Layer>> layers;
   F32Vec nw, nb;
   Linear head;
-  Act col, h, hid, clsn;
-  DevBuf x, qkv, cls_idx;
+  Act col, h, hid, clsn, xb;
+  DevBuf x, qkv, cls_idx, stats1, stats2;
+  bool ln_fold = false;
   int tap_layer = -1;
   float* tap_dst = nullptr;
 };
@@ -226,6 +282,11 @@ const char* hb_strerror(int code) {
 }
 
 int64_t hb_launch_count(void) { return g_launches.load(); }
+
+int hb_set_ln_fold(int on) {
+  g_ln_fold = on ? 1 : 0;
+  return HB_OK;
+}
 
 int hb_set_attention_version(int v) {
   if (v != 1 && v != 2) return fail(HB_ERR_INVALID, "attention version must be 1 or 2");
@@ -279,6 +340,7 @@ int hb_vit_create(const HbVitConfig* cfg, const HbVitWeights* w, int max_batch, 
   m->T = (S / P) * (S / P) + 1;
   m->Kpatch = 3 * P * P;
   m->max_batch = max_batch;
+  m->ln_fold = (g_ln_fold != 0);
   int r;
   if ((r = m->cls.init(w->cls_token, D, s))) return r;
   if ((r = m->pos.init(w->pos_embed, static_cast<size_t>(m->T) * D, s))) return r;
@@ -290,9 +352,13 @@ int hb_vit_create(const HbVitConfig* cfg, const HbVitWeights* w, int max_batch, 
     if ((r = L->n2w.init(w->norm2_w[i], D, s))) return r;
     if ((r = L->n2b.init(w->norm2_b[i], D, s))) return r;
     // qkv bias = cat(q_bias, zeros, v_bias), built once instead of every forward (vit_model.py:124)
-    if ((r = L->qkv.init(w->qkv_w[i], 3 * D, D, nullptr, false, s, w->q_bias[i], w->v_bias[i]))) return r;
+    if ((r = L->qkv.init(w->qkv_w[i], 3 * D, D, nullptr, false, s, w->q_bias[i], w->v_bias[i], m->ln_fold ? w->norm1_w[i] : nullptr,
+                         m->ln_fold ? w->norm1_b[i] : nullptr)))
+      return r;
     if ((r = L->proj.init(w->proj_w[i], D, D, w->proj_b[i], false, s))) return r;
-    if ((r = L->fc1.init(w->fc1_w[i], F, D, w->fc1_b[i], false, s))) return r;
+    if ((r = L->fc1.init(w->fc1_w[i], F, D, w->fc1_b[i], false, s, nullptr, nullptr, m->ln_fold ? w->norm2_w[i] : nullptr,
+                         m->ln_fold ? w->norm2_b[i] : nullptr)))
+      return r;
     if ((r = L->fc2.init(w->fc2_w[i], D, F, w->fc2_b[i], false, s))) return r;
     m->layers.push_back(std::move(L));
   }
@@ -304,6 +370,12 @@ int hb_vit_create(const HbVitConfig* cfg, const HbVitWeights* w, int max_batch, 
   if ((r = m->h.init(rows, D))) return r;
   if ((r = m->hid.init(rows, F))) return r;
   if ((r = m->clsn.init(max_batch, D))) return r;
+  if (m->ln_fold) {
+    if ((r = m->xb.init(rows, D))) return r;
+    const size_t slots = static_cast<size_t>((D + 127) / 128);
+    if ((r = m->stats1.alloc(static_cast<size_t>(rows) * slots * 8))) return r;
+    if ((r = m->stats2.alloc(static_cast<size_t>(rows) * slots * 8))) return r;
+  }
   if ((r = m->x.alloc(static_cast<size_t>(rows) * D * 4))) return r;
   if ((r = m->qkv.alloc(static_cast<size_t>(rows) * 3 * D * 2))) return r;
   if ((r = m->cls_idx.alloc(static_cast<size_t>(max_batch) * 4))) return r;
@@ -344,6 +416,31 @@ static int vit_encode_chunk(HbVit* m, const float* frames, const uint8_t* frames
   if (m->tap_layer == 0 && m->tap_dst)
     HB_CUDA(cudaMemcpyAsync(m->tap_dst, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, s));
   const float qscale = 1.0f / sqrtf(88.0f);
+  if (m->ln_fold) {
+    // LayerNorm folded into the GEMMs: the residual stream travels as fp32 x + a bf16 copy xb + per-row (sum, sumsq)
+    // partials, one slot per 128 columns, each written by exactly one warp (no atomics: bit-reproducible, batch-independent).
+    // QKV / fc1 read xb and apply rstd / mean in their epilogue, proj / fc2 refresh xb and the statistics in theirs.
+    const int slots = (D + 127) / 128;
+    HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::row_stats_launch(x, m->xb.ptr(), m->stats1.as<float>(), M, D, slots, s));
+    LnFold lf1, lf2, lp1, lp2;
+    lf1.slots = lf2.slots = lp1.slots = lp2.slots = slots;
+    lf1.stats_in = m->stats1.as<float>(); lf1.eps = c.ln_eps; lf1.dim = D;
+    lf2.stats_in = m->stats2.as<float>(); lf2.eps = c.ln_eps; lf2.dim = D;
+    lp2.xb_out = m->xb.ptr(); lp2.ld_xb = D; lp2.stats_out = m->stats2.as<float>();   // proj  -> statistics for LN2
+    lp1.xb_out = m->xb.ptr(); lp1.ld_xb = D; lp1.stats_out = m->stats1.as<float>();   // fc2   -> statistics for the next LN1
+    for (int i = 0; i < c.layers; ++i) {
+      HbVit::Layer& L = *m->layers[i];
+      if ((r = run_gemm(m->xb.tm, L.qkv, M, qkv, 3 * D, hb::EPI_BF16_LN, s, nullptr, qscale, D, nullptr, 0, 0, 0, &lf1))) return r;
+      hb::AttnParams ap;
+      ap.qkv = qkv; ap.out = m->h.ptr(); ap.B = B; ap.H = c.heads;
+      HB_LAUNCH_P(CAT_VIT_ATTN, 4.0 * B * c.heads * 257.0 * 257.0 * 88.0, s, g_attn_version == 1 ? hb::vit_attn_launch(ap, s) : hb::vit_attn2_launch(ap, s));
+      if ((r = run_gemm(m->h.tm, L.proj, M, x, D, hb::EPI_F32_STATS, s, x, 1.f, 0, nullptr, 0, 0, 0, &lp2))) return r;
+      if ((r = run_gemm(m->xb.tm, L.fc1, M, m->hid.ptr(), F, hb::EPI_GELU_BF16_LN, s, nullptr, 1.f, 0, nullptr, 0, 0, 0, &lf2))) return r;
+      if ((r = run_gemm(m->hid.tm, L.fc2, M, x, D, hb::EPI_F32_STATS, s, x, 1.f, 0, nullptr, 0, 0, 0, &lp1))) return r;
+      if (m->tap_layer == i + 1 && m->tap_dst)
+        HB_CUDA(cudaMemcpyAsync(m->tap_dst, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, s));
+    }
+  } else
   for (int i = 0; i < c.layers; ++i) {
     HbVit::Layer& L = *m->layers[i];
     hb::LayerNormParams ln;

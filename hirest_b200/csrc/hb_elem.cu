@@ -79,6 +79,31 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const LayerNormParams p)
   }
 }
 
+// Row statistics + bf16 copy for the LayerNorm-folded GEMMs (entry of the ViT block stack): stats[r, 0] = (sum, sum of squares),
+// stats[r, 1..slots) = 0 (the GEMM epilogues fill one slot per 128 columns), xb[r,:] = bf16(x[r,:]).  One warp per row.
+__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xb,
+                                                        float* __restrict__ stats, long long rows, int D, int slots) {
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float4* x4 = reinterpret_cast<const float4*>(x + warp * D);
+  uint2* o2 = reinterpret_cast<uint2*>(xb + warp * D);
+  float s = 0.f, ss = 0.f;
+  for (int i = lane; i < (D >> 2); i += 32) {
+    const float4 v = x4[i];
+    s += (v.x + v.y) + (v.z + v.w);
+    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    uint2 o;
+    o.x = pack2(v.x, v.y);
+    o.y = pack2(v.z, v.w);
+    o2[i] = o;
+  }
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  float2* st = reinterpret_cast<float2*>(stats) + warp * slots;
+  if (lane < slots) st[lane] = lane == 0 ? make_float2(s, ss) : make_float2(0.f, 0.f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Patch gather for Conv2d(3, D, k=14, s=14) as a GEMM (vit_model.py:198,205): row = b*256 + ph*16 + pw,
 // column = c*196 + kh*14 + kw (the conv weight's own (c,kh,kw) flattening), padded to ldo columns with zeros.
@@ -262,6 +287,13 @@ int layernorm_launch(const LayerNormParams& p, bool out_bf16, cudaStream_t s) {
   const unsigned blocks = blocks_for(p.rows, 8);
   if (out_bf16) layernorm_kernel<true><<<blocks, 256, 0, s>>>(p);
   else layernorm_kernel<false><<<blocks, 256, 0, s>>>(p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int row_stats_launch(const float* x, __nv_bfloat16* xb, float* stats, long long rows, int D, int slots, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  if (D % 4 != 0 || slots < 1 || slots > 32) return -7;
+  row_stats_kernel<<<blocks_for(rows, 8), 256, 0, s>>>(x, xb, stats, rows, D, slots);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -19,6 +19,7 @@ struct LayerNormParams {
   int D = 0;
 };
 int layernorm_launch(const LayerNormParams& p, bool out_bf16, cudaStream_t s);
+int row_stats_launch(const float* x, __nv_bfloat16* xb, float* stats, long long rows, int D, int slots, cudaStream_t s);
 int im2col_patch_launch(const float* img, __nv_bfloat16* out, int B, int S, int P, int ldo, cudaStream_t s);
 int im2col_patch_u8_launch(const uint8_t* img, __nv_bfloat16* out, int B, int S, int P, int ldo, const float mean[3],
                            const float stdv[3], cudaStream_t s);

@@ -38,7 +38,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;
   static constexpr int STAGES = (CG == 1) ? 4 : 6;    // 192 KiB either way
   static constexpr int EPI_STAGE_BYTES = 32 * 32 * 4;  // per epilogue warp: one 32x32 fp32 transpose buffer
-  static constexpr int BIAS_BYTES = 2 * BN * 4;        // the tile's bias slice, one copy per accumulator buffer
+  static constexpr int BIAS_BYTES = 2 * BN * 4;        // the tile's bias slice and its LayerNorm-fold c1 slice
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + NUM_EPI_WARPS * EPI_STAGE_BYTES + BIAS_BYTES;
 };
 
@@ -62,23 +62,34 @@ struct TileIter {
 // bf16-output epilogues (thread-per-row): r = 32 consecutive fp32 accumulator columns [col0, col0+32) of one row.
 template <int EPI>
 __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const uint32_t (&r)[32], long long row_out,
-                                                     int row_in, int col0, int n_valid, const float* sb /*smem bias of this chunk*/) {
+                                                     int row_in, int col0, int n_valid, const float* sb /*smem bias of this chunk*/,
+                                                     const float* sc1, float ln_a, float ln_b) {
   (void)row_in;
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
   {  // bias comes from the per-tile smem copy (zeros when the layer has none): broadcast LDS, no global-load latency here
     const float4* b4 = reinterpret_cast<const float4*>(sb);
+    const float4* c4 = reinterpret_cast<const float4*>(sc1);
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const float4 b = b4[g];
-      v[4 * g + 0] += b.x;
-      v[4 * g + 1] += b.y;
-      v[4 * g + 2] += b.z;
-      v[4 * g + 3] += b.w;
+      if constexpr (EPI == EPI_BF16_LN || EPI == EPI_GELU_BF16_LN) {
+        // LayerNorm fold: ln_a = rstd, ln_b = -rstd * mean of this row
+        const float4 c = c4[g];
+        v[4 * g + 0] = fmaf(v[4 * g + 0], ln_a, fmaf(ln_b, c.x, b.x));
+        v[4 * g + 1] = fmaf(v[4 * g + 1], ln_a, fmaf(ln_b, c.y, b.y));
+        v[4 * g + 2] = fmaf(v[4 * g + 2], ln_a, fmaf(ln_b, c.z, b.z));
+        v[4 * g + 3] = fmaf(v[4 * g + 3], ln_a, fmaf(ln_b, c.w, b.w));
+      } else {
+        v[4 * g + 0] += b.x;
+        v[4 * g + 1] += b.y;
+        v[4 * g + 2] += b.z;
+        v[4 * g + 3] += b.w;
+      }
     }
   }
-  if constexpr (EPI == EPI_GELU_BF16) {
+  if constexpr (EPI == EPI_GELU_BF16 || EPI == EPI_GELU_BF16_LN) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
   } else {
@@ -236,13 +247,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // Stage this tile's bias slice in smem before the accumulator is ready (one element per epilogue thread): the
       // per-chunk global bias loads were consumed immediately and left the epilogue warps waiting on L2 latency
       // (fc1: 64 % tensor-pipe active with `stall_long_sb` on the bias FADDs, profiles/r01_one_layer_ncu_full.txt).
-      float* sb_tile = sbias + acc * BN;
+      float* sb_tile = sbias;
+      float* sc1_tile = sbias + BN;
       {
         const int et = (warp - 4) * 32 + lane;
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // every epilogue warp is done with the previous tile's slices
         sb_tile[et] = (p.bias != nullptr && et < n_eff) ? __ldg(p.bias + n0 + et) : 0.f;
+        if constexpr (EPI == EPI_BF16_LN || EPI == EPI_GELU_BF16_LN) sc1_tile[et] = (et < n_eff) ? __ldg(p.c1 + n0 + et) : 0.f;
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      if constexpr (EPI == EPI_F32 || EPI == EPI_F32_ROWADD) {
+      if constexpr (EPI == EPI_F32 || EPI == EPI_F32_ROWADD || EPI == EPI_F32_STATS) {
         // fp32 output (+ fp32 residual / row-add): the accumulator chunk is transposed through a per-warp swizzled smem
         // buffer so that every global access is a full 128-byte row segment (thread-per-row access costs 32 L1
         // wavefronts per instruction and made this epilogue the bottleneck of the K=1408 proj GEMM).  Residual values
@@ -302,6 +316,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         };
+        float psum[8], psq[8];   // EPI_F32_STATS: per-row partial (sum, sum of squares) over this warp's column span
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { psum[i] = 0.f; psq[i] = 0.f; }
         auto do_chunk = [&](int c, const float4 (&res)[8]) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c), r);
@@ -326,6 +343,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (((okmask >> i) & 1u) && cc * 4 < n_valid) {
               int radd;
               __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row_off(i, radd) + col0 + cc * 4), v);
+              if constexpr (EPI == EPI_F32_STATS) {
+                psum[i] += (v.x + v.y) + (v.z + v.w);
+                psq[i] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                uint2 pk;
+                pk.x = pack_bf16x2(v.x, v.y);
+                pk.y = pack_bf16x2(v.z, v.w);
+                const long long rowi = row_base + 4 * i + rr_base;
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.xb_out) + rowi * p.ld_xb + col0 + cc * 4) = pk;
+              }
             }
           }
           __syncwarp();
@@ -346,8 +372,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             do_chunk(c + 32, res_b);
           }
         }
+        if constexpr (EPI == EPI_F32_STATS) {
+          // the 8 lanes that share a row (same lane >> 3) combine their partials in a fixed order and one lane writes them to
+          // this warp's slot (one per 128-column span): no atomics, so the statistics — and everything downstream — are
+          // bit-reproducible and independent of which other rows share the launch.
+          const int slot = (n0 + c_begin) >> 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float a = psum[i], b = psq[i];
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+              a += __shfl_xor_sync(0xffffffffu, a, o);
+              b += __shfl_xor_sync(0xffffffffu, b, o);
+            }
+            if (cc == 0 && ((okmask >> i) & 1u) && c_begin < c_end) {
+              const long long rowi = row_base + 4 * i + rr_base;
+              *reinterpret_cast<float2*>(p.stats_out + 2 * (rowi * p.ln_slots + slot)) = make_float2(a, b);
+            }
+          }
+        }
       } else {
         const bool row_ok = row_in < p.M;
+        float ln_a = 1.f, ln_b = 0.f;
+        if constexpr (EPI == EPI_BF16_LN || EPI == EPI_GELU_BF16_LN) {
+          if (row_ok) {   // row statistics of the A operand's fp32 source (accumulated by the producing GEMM's epilogue)
+            float2 st = make_float2(0.f, 0.f);
+            const float2* sp = reinterpret_cast<const float2*>(p.stats_in) + static_cast<long long>(row_in) * p.ln_slots;
+            for (int sl = 0; sl < p.ln_slots; ++sl) { const float2 t = sp[sl]; st.x += t.x; st.y += t.y; }
+            const float inv_d = 1.0f / static_cast<float>(p.ln_dim);
+            const float mean = st.x * inv_d;
+            const float var = fmaxf(st.y * inv_d - mean * mean, 0.f);
+            ln_a = rsqrtf(var + p.ln_eps);
+            ln_b = -ln_a * mean;
+          }
+        }
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
@@ -355,7 +413,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c), r);
           tmem_ld_wait();
-          if (row_ok) epilogue_store_chunk<EPI>(p, r, row_out, row_in, n0 + c, n_eff - c, sb_tile + c);
+          if (row_ok) epilogue_store_chunk<EPI>(p, r, row_out, row_in, n0 + c, n_eff - c, sb_tile + c, sc1_tile + c, ln_a, ln_b);
         }
       }
       tc_fence_before();
@@ -474,6 +532,9 @@ int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams
       case EPI_GELU_BF16: return launch_impl<1, EPI_GELU_BF16>(tmA, tmW, p, num_sms, stream);
       case EPI_F32: return launch_impl<1, EPI_F32>(tmA, tmW, p, num_sms, stream);
       case EPI_F32_ROWADD: return launch_impl<1, EPI_F32_ROWADD>(tmA, tmW, p, num_sms, stream);
+      case EPI_F32_STATS: return launch_impl<1, EPI_F32_STATS>(tmA, tmW, p, num_sms, stream);
+      case EPI_BF16_LN: return launch_impl<1, EPI_BF16_LN>(tmA, tmW, p, num_sms, stream);
+      case EPI_GELU_BF16_LN: return launch_impl<1, EPI_GELU_BF16_LN>(tmA, tmW, p, num_sms, stream);
     }
   } else if (cg == 2) {
     switch (epi) {
@@ -481,6 +542,9 @@ int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams
       case EPI_GELU_BF16: return launch_impl<2, EPI_GELU_BF16>(tmA, tmW, p, num_sms, stream);
       case EPI_F32: return launch_impl<2, EPI_F32>(tmA, tmW, p, num_sms, stream);
       case EPI_F32_ROWADD: return launch_impl<2, EPI_F32_ROWADD>(tmA, tmW, p, num_sms, stream);
+      case EPI_F32_STATS: return launch_impl<2, EPI_F32_STATS>(tmA, tmW, p, num_sms, stream);
+      case EPI_BF16_LN: return launch_impl<2, EPI_BF16_LN>(tmA, tmW, p, num_sms, stream);
+      case EPI_GELU_BF16_LN: return launch_impl<2, EPI_GELU_BF16_LN>(tmA, tmW, p, num_sms, stream);
     }
   }
   return -5;

@@ -17,6 +17,11 @@ enum GemmEpilogue : int {
   EPI_GELU_BF16 = 1,  // out bf16 = gelu_erf(acc + bias)
   EPI_F32 = 2,        // out f32  = acc + bias [+ resid[row_out, col]]
   EPI_F32_ROWADD = 3, // out f32  = acc + bias + rowadd[row % remap_in, col], rows remapped (patch embed + pos embed)
+  // LayerNorm folded into the GEMMs (no LayerNorm kernel, no normalised copy of the residual stream in HBM):
+  //   LN(x) W^T = rstd * (x (gamma*W)^T) - rstd*mean * c1 + c2,   c1[n] = sum_k gamma_k W[n,k],  c2[n] = sum_k beta_k W[n,k] + b[n]
+  EPI_F32_STATS = 4,  // EPI_F32 + writes a bf16 copy of the new residual row and accumulates its (sum, sum of squares)
+  EPI_BF16_LN = 5,    // out bf16 = (rstd*acc - rstd*mean*c1 + c2) * (col < qcols ? qscale : 1)   (A operand = raw bf16 residual)
+  EPI_GELU_BF16_LN = 6,  // out bf16 = gelu_erf(rstd*acc - rstd*mean*c1 + c2)
 };
 
 struct GemmParams {
@@ -29,8 +34,17 @@ struct GemmParams {
   int remap_in = 0;               // if > 0: out_row = (row / remap_in) * remap_out + row % remap_in + remap_off
   int remap_out = 0;
   int remap_off = 0;
-  float qscale = 1.0f;            // EPI_BF16 only
+  float qscale = 1.0f;            // EPI_BF16 / EPI_BF16_LN only
   int qcols = 0;
+  // LayerNorm fold
+  void* xb_out = nullptr;         // EPI_F32_STATS: bf16 copy of out, leading dim ld_xb
+  int ld_xb = 0;
+  float* stats_out = nullptr;     // EPI_F32_STATS: [M, ln_slots, 2] (sum, sumsq) per 128-column span, slot = column / 128
+  const float* stats_in = nullptr;  // *_LN kinds: [M, ln_slots, 2] row statistics of the A operand's fp32 source
+  const float* c1 = nullptr;      // *_LN kinds: [N]; `bias` carries c2
+  float ln_eps = 1e-6f;
+  int ln_dim = 0;                 // number of features the statistics were taken over
+  int ln_slots = 1;               // partial-sum slots per row (producer: ceil(N / 128))
 };
 
 // Resolve cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency).

@@ -49,6 +49,9 @@ HB_API int hb_set_gemm_cta_group(int cg);
 /* ViT attention kernel: 2 (default: one CTA per 128-query tile, two CTAs per SM, P kept in TMEM) or 1 (one CTA per
  * (frame, head), P staged through shared memory). Same results up to bf16 rounding of the output. */
 HB_API int hb_set_attention_version(int v);
+/* ViT handles created after this call fold the block LayerNorms into the QKV / fc1 GEMM epilogues (1, default) or run
+ * separate LayerNorm kernels (0). */
+HB_API int hb_set_ln_fold(int on);
 
 /* Per-launch timing for bench.py's roofline: while enabled every kernel launch of this library is bracketed
  * by CUDA events on its own stream.  hb_profile_stop synchronises the device and sums per category:

@@ -177,3 +177,24 @@ def test_g14_full_size_properties(hb):
     scores = retrieval.similarity(t_hat.to(DEV), v_hat)
     ref = eva_oracle.similarity(t_hat, eva_oracle.pool_normalize_video(full.cpu(), 32))
     assert float((scores.cpu() - ref).abs().max()) < 5e-7
+
+
+def test_layernorm_fold_matches_separate_layernorm(hb, golden_dir):
+    """LayerNorm folded into the QKV / fc1 GEMM epilogues (default) vs separate LayerNorm kernels: both within tolerance of the
+    reference golden, and the folded path is not less accurate (tiny config and EVA-CLIP-g/14)."""
+    for cfg, gname, n in ((synthetic.EVA_TINY, "eva_tiny.pt", 4), (synthetic.EVA_G14, "eva_g14.pt", 8)):
+        g = torch.load(os.path.join(golden_dir, gname))
+        sd = synthetic.make_eva_state_dict(cfg, seed=0)
+        frames = synthetic.make_frames(n, 224, seed=1).to(DEV)
+        errs = {}
+        for fold in (1, 0):
+            _lib.check(hb.hb_set_ln_fold(fold))
+            model = eva_clip.EVA_CLIP(**cfg, max_image_batch=8, max_text_batch=8)
+            model.load_state_dict(sd, strict=True)
+            model = model.to(DEV).eval()
+            errs[fold] = rel(model.encode_image(frames), g["image"])
+            del model
+        _lib.check(hb.hb_set_ln_fold(1))
+        print(f"{gname}: rel err folded {errs[1]:.3e}, separate LayerNorm {errs[0]:.3e}")
+        assert errs[1] < (TOL_TINY_IMAGE if cfg is synthetic.EVA_TINY else TOL_G14_IMAGE)
+        assert errs[1] <= errs[0] * 1.25 + 1e-4
