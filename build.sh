@@ -1,7 +1,17 @@
 #!/bin/bash
 # Build libhirest_b200.so (sm_100a only) in-tree: hirest_b200/libhirest_b200.so
+# Sources compile in parallel into build/ (git-ignored); extra arguments go to every nvcc compile.
 set -e
 cd "$(dirname "$0")"
-SRC="hirest_b200/csrc/hb_gemm.cu hirest_b200/csrc/hb_attn.cu hirest_b200/csrc/hb_attn2.cu hirest_b200/csrc/hb_attn_small.cu hirest_b200/csrc/hb_elem.cu hirest_b200/csrc/hb_moment.cu hirest_b200/csrc/hb_api.cu"
-nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -shared -Xcompiler -fPIC -Xcompiler -fvisibility=hidden \
-  -o hirest_b200/libhirest_b200.so $SRC "$@"
+SRC="hb_gemm hb_attn hb_attn2 hb_attn_small hb_elem hb_moment hb_preproc hb_api"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden"
+mkdir -p build
+pids=""
+for f in $SRC; do
+  nvcc $FLAGS -c hirest_b200/csrc/$f.cu -o build/$f.o "$@" &
+  pids="$pids $!"
+done
+for p in $pids; do wait $p; done
+OBJS=""
+for f in $SRC; do OBJS="$OBJS build/$f.o"; done
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o hirest_b200/libhirest_b200.so $OBJS

@@ -10,15 +10,19 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "hb_attn.cuh"
 #include "hb_elem.cuh"
 #include "hb_gemm.cuh"
 #include "hb_moment.cuh"
+#include "hb_preproc.cuh"
 
 namespace {
 
@@ -622,6 +626,64 @@ int hb_pool_normalize(const float* emb, int64_t V, int F, int E, float* out, voi
   if (!emb || !out) return fail(HB_ERR_INVALID, "null argument");
   if (V == 0) return HB_OK;
   HB_LAUNCH(hb::pool_normalize_launch(emb, out, V, F, E, true, false, static_cast<cudaStream_t>(stream)));
+  return HB_OK;
+}
+
+// ---- frame preprocessing: plans (host tables + device copy) cached per (device, H, W, S) ----
+namespace {
+struct ResizeEntry { hb::ResizePlanHost plan; DevBuf tables; };
+std::mutex g_resize_mu;
+std::map<std::tuple<int, int, int, int>, std::unique_ptr<ResizeEntry>> g_resize_plans;
+}  // namespace
+
+int hb_resize_geometry(int H, int W, int S, int* new_h, int* new_w, int* top, int* left) {
+  if (!new_h || !new_w || !top || !left) return fail(HB_ERR_INVALID, "null argument");
+  hb::ResizePlanHost plan;
+  const int r = hb::resize_plan_build(&plan, H, W, S);
+  if (r == -3) return fail(HB_ERR_INVALID, "invalid frame size %dx%d -> %d (need H, W >= 1 and 1 <= S <= 256)", H, W, S);
+  *new_h = plan.nh; *new_w = plan.nw; *top = plan.top; *left = plan.left;
+  return HB_OK;
+}
+
+int64_t hb_resize_tables(int H, int W, int S, int info[6], int* tables, int64_t cap) {
+  if (!info) return fail(HB_ERR_INVALID, "null argument");
+  hb::ResizePlanHost plan;
+  const int r = hb::resize_plan_build(&plan, H, W, S);
+  if (r) return fail(HB_ERR_INVALID, "resize plan for %dx%d -> %d failed (%d)", H, W, S, r);
+  info[0] = plan.kh; info[1] = plan.kv; info[2] = plan.x0; info[3] = plan.span_bytes; info[4] = plan.ty; info[5] = plan.smem_bytes;
+  const int64_t n = static_cast<int64_t>(hb::resize_plan_table_ints(plan));
+  if (tables && cap >= n) hb::resize_plan_pack(plan, tables);
+  return n;
+}
+
+int hb_resize_crop_u8(const uint8_t* src, int64_t B, int H, int W, int S, uint8_t* dst, void* stream) {
+  if (!g_inited) return fail(HB_ERR_INVALID, "hb_init() not called");
+  if (B == 0) return HB_OK;
+  if (!src || !dst) return fail(HB_ERR_INVALID, "null argument");
+  if (B < 0) return fail(HB_ERR_INVALID, "negative batch");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int dev = 0;
+  HB_CUDA(cudaGetDevice(&dev));
+  ResizeEntry* e = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_resize_mu);
+    auto key = std::make_tuple(dev, H, W, S);
+    auto it = g_resize_plans.find(key);
+    if (it == g_resize_plans.end()) {
+      std::unique_ptr<ResizeEntry> ne(new ResizeEntry);
+      const int r = hb::resize_plan_build(&ne->plan, H, W, S);
+      if (r == -3) return fail(HB_ERR_INVALID, "invalid frame size %dx%d -> %d (need H, W >= 1 and 1 <= S <= 256)", H, W, S);
+      if (r == -6) return fail(HB_ERR_INVALID, "frame %dx%d is too large for the shared-memory row window of the resize kernel", H, W);
+      if (r) return fail(HB_ERR_INVALID, "resize plan failed (%d)", r);
+      std::vector<int> packed(hb::resize_plan_table_ints(ne->plan));
+      hb::resize_plan_pack(ne->plan, packed.data());
+      if (int a = ne->tables.alloc(packed.size() * sizeof(int))) return a;
+      HB_CUDA(cudaMemcpy(ne->tables.p, packed.data(), packed.size() * sizeof(int), cudaMemcpyHostToDevice));  // first use of this size only
+      it = g_resize_plans.emplace(key, std::move(ne)).first;
+    }
+    e = it->second.get();
+  }
+  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::resize_crop_launch(e->plan, e->tables.as<int>(), src, dst, B, s));
   return HB_OK;
 }
 

@@ -1,0 +1,274 @@
+// hb_preproc.cu — frame preprocessing on the GPU: Resize(S, BICUBIC) + CenterCrop(S) of decoded
+// uint8 RGB frames, bit-identical to the reference's CPU pipeline
+//   torchvision Resize/CenterCrop on PIL images  (EVA_clip/eva_clip.py:144-147, used at inference_video_retrieval.py:43-49
+//   and extract_features.py:48-50)
+// whose arithmetic is Pillow's 8-bit ImagingResample: separable, horizontal pass first into an 8-bit intermediate, bicubic
+// (a = -0.5) weights evaluated in double, normalised, converted to 22-bit fixed point, accumulated in int32 from 1 << 21 and
+// shifted back with saturation.  The weights are computed on the host in double exactly as Pillow does (integer tables, cached
+// per source size); the kernel does only integer work.  ToTensor + Normalize stay folded into the patch gather
+// (hb_vit_encode_u8), so a decoded frame goes H2D once as bytes and is never materialised in fp32.
+//
+// One fused kernel: a CTA owns TY output rows of one frame.  It streams the source rows those output rows need through
+// shared memory (coalesced 4-byte loads of only the column span the crop needs), resamples each horizontally into an
+// 8-bit smem intermediate, then resamples vertically out of smem and writes the planar [3,S,S] crop.  The intermediate
+// image of the two-pass reference never touches HBM.  HBM-bound: algorithmic bytes = needed source region + output.
+#include "hb_preproc.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace hb {
+
+namespace {
+
+constexpr int PRECISION_BITS = 32 - 8 - 2;
+constexpr int G = 4;  // source rows resampled per smem stage
+
+double bicubic_filter(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+// Pillow precompute_coeffs + normalize_coeffs_8bpc for the full-image box; only outputs [first, first + count) are kept.
+void axis_tables(int in_size, int out_size, int first, int count, std::vector<int>& bounds, std::vector<int>& coeffs, int& ksize) {
+  if (in_size == out_size) {  // Pillow skips the pass; the identity table gives the same bytes
+    ksize = 1;
+    bounds.resize(static_cast<size_t>(count) * 2);
+    coeffs.resize(count);
+    for (int i = 0; i < count; ++i) { bounds[2 * i] = first + i; bounds[2 * i + 1] = 1; coeffs[i] = 1 << PRECISION_BITS; }
+    return;
+  }
+  double scale, filterscale;
+  filterscale = scale = static_cast<double>(in_size) / out_size;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = 2.0 * filterscale;
+  ksize = static_cast<int>(std::ceil(support)) * 2 + 1;
+  bounds.assign(static_cast<size_t>(count) * 2, 0);
+  coeffs.assign(static_cast<size_t>(count) * ksize, 0);
+  std::vector<double> w(ksize);
+  for (int i = 0; i < count; ++i) {
+    const int xx = first + i;
+    const double center = (xx + 0.5) * scale;
+    const double ss = 1.0 / filterscale;
+    int xmin = static_cast<int>(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = static_cast<int>(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      w[x] = bicubic_filter((x + xmin - center + 0.5) * ss);
+      ww += w[x];
+    }
+    for (int x = 0; x < xmax; ++x) {
+      double k = w[x];
+      if (ww != 0.0) k /= ww;
+      coeffs[static_cast<size_t>(i) * ksize + x] =
+          (k < 0) ? static_cast<int>(-0.5 + k * (1 << PRECISION_BITS)) : static_cast<int>(0.5 + k * (1 << PRECISION_BITS));
+    }
+    bounds[2 * i] = xmin;
+    bounds[2 * i + 1] = xmax;
+  }
+}
+
+__device__ __forceinline__ int clip8(int v) {
+  v >>= PRECISION_BITS;
+  return min(max(v, 0), 255);
+}
+
+struct KParams {
+  const uint8_t* src;  // [B, H, W, 3]
+  uint8_t* dst;        // [B, 3, S, S]
+  const int* hb;       // [S, 2]  (first source column - x0, taps)
+  const int* hk;       // [S, kh]
+  const int* vb;       // [S, 2]  (first source row, taps)
+  const int* vk;       // [S, kv]
+  int H, W, S, kh, kv, x0, span_bytes, row_pitch /*smem bytes per staged source row*/, ty, max_rows, tmp_pitch;
+};
+
+__global__ void __launch_bounds__(256) resize_crop_kernel(const KParams p) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  uint8_t* stage = sm;                           // [G][row_pitch]
+  uint8_t* tmp = sm + G * p.row_pitch;           // [max_rows][tmp_pitch]  horizontally resampled rows (x-major, channel-minor)
+  const int b = blockIdx.y;
+  const int y0 = blockIdx.x * p.ty;
+  const int ny = min(p.ty, p.S - y0);
+  const int r0 = p.vb[2 * y0];
+  const int r1 = p.vb[2 * (y0 + ny - 1)] + p.vb[2 * (y0 + ny - 1) + 1];
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const uint8_t* frame = p.src + static_cast<size_t>(b) * p.H * p.W * 3;
+
+  // this thread's output column
+  const int x = tid;
+  int hx0 = 0, hn = 0;
+  const int* hkx = nullptr;
+  if (x < p.S) { hx0 = p.hb[2 * x] * 3; hn = p.hb[2 * x + 1]; hkx = p.hk + static_cast<size_t>(x) * p.kh; }
+
+  for (int r = r0; r < r1; r += G) {
+    const int nr = min(G, r1 - r);
+    // ---- stage nr source rows (only the byte span the crop needs); words inside the span go as 4-byte loads ----
+    for (int j = 0; j < nr; ++j) {
+      const uint8_t* g = frame + (static_cast<size_t>(r + j) * p.W + p.x0) * 3;
+      const int mis = static_cast<int>(reinterpret_cast<uintptr_t>(g) & 3u);
+      uint8_t* s = stage + j * p.row_pitch + mis;  // s[i] = g[i]; s + head is 4-byte aligned
+      const int len = p.span_bytes;
+      int head = mis ? 4 - mis : 0;
+      if (head > len) head = len;
+      const int nw = (len - head) >> 2;
+      if (tid < head) s[tid] = g[tid];
+      const uint32_t* gw = reinterpret_cast<const uint32_t*>(g + head);
+      uint32_t* sw = reinterpret_cast<uint32_t*>(s + head);
+      for (int i = tid; i < nw; i += nthr) sw[i] = __ldg(gw + i);
+      const int done = head + 4 * nw;
+      if (tid < len - done) s[done + tid] = g[done + tid];
+    }
+    __syncthreads();
+    // ---- horizontal pass: thread x produces 3 channels of nr rows; each weight is loaded once for 3 * nr products ----
+    if (x < p.S) {
+      int acc[G][3];
+#pragma unroll
+      for (int j = 0; j < G; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 1 << (PRECISION_BITS - 1);
+      const uint8_t* srow[G];
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const uint8_t* g = frame + (static_cast<size_t>(r + min(j, nr - 1)) * p.W + p.x0) * 3;
+        srow[j] = stage + min(j, nr - 1) * p.row_pitch + static_cast<int>(reinterpret_cast<uintptr_t>(g) & 3u) + hx0;
+      }
+      for (int k = 0; k < hn; ++k) {
+        const int w = __ldg(hkx + k);
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          acc[j][0] += static_cast<int>(srow[j][3 * k + 0]) * w;
+          acc[j][1] += static_cast<int>(srow[j][3 * k + 1]) * w;
+          acc[j][2] += static_cast<int>(srow[j][3 * k + 2]) * w;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        if (j < nr) {
+          uint8_t* t = tmp + static_cast<size_t>(r - r0 + j) * p.tmp_pitch + 3 * x;
+          t[0] = static_cast<uint8_t>(clip8(acc[j][0]));
+          t[1] = static_cast<uint8_t>(clip8(acc[j][1]));
+          t[2] = static_cast<uint8_t>(clip8(acc[j][2]));
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- vertical pass out of smem; planar output, coalesced along x ----
+  if (x < p.S) {
+    for (int yy = 0; yy < ny; ++yy) {
+      const int y = y0 + yy;
+      const int v0 = p.vb[2 * y] - r0, vn = p.vb[2 * y + 1];
+      const int* vky = p.vk + static_cast<size_t>(y) * p.kv;
+      int a0 = 1 << (PRECISION_BITS - 1), a1 = a0, a2 = a0;
+      const uint8_t* t = tmp + static_cast<size_t>(v0) * p.tmp_pitch + 3 * x;
+      for (int k = 0; k < vn; ++k) {
+        const int w = __ldg(vky + k);
+        a0 += static_cast<int>(t[0]) * w;
+        a1 += static_cast<int>(t[1]) * w;
+        a2 += static_cast<int>(t[2]) * w;
+        t += p.tmp_pitch;
+      }
+      uint8_t* d = p.dst + (static_cast<size_t>(b) * 3 * p.S + y) * p.S + x;
+      const size_t plane = static_cast<size_t>(p.S) * p.S;
+      d[0] = static_cast<uint8_t>(clip8(a0));
+      d[plane] = static_cast<uint8_t>(clip8(a1));
+      d[2 * plane] = static_cast<uint8_t>(clip8(a2));
+    }
+  }
+}
+
+}  // namespace
+
+void resized_output_size(int H, int W, int S, int* nh, int* nw) {
+  // torchvision _compute_resized_output_size(size=[S]): shorter edge -> S, longer -> int(S * long / short)
+  const int shortv = (W <= H) ? W : H, longv = (W <= H) ? H : W;
+  const int new_long = static_cast<int>(static_cast<double>(S) * longv / shortv);
+  if (W <= H) { *nw = S; *nh = new_long; } else { *nh = S; *nw = new_long; }
+}
+
+static int round_half_even(double v) { return static_cast<int>(std::nearbyint(v)); }  // Python round() (default FE_TONEAREST)
+
+int resize_plan_build(ResizePlanHost* plan, int H, int W, int S) {
+  if (H <= 0 || W <= 0 || S <= 0 || S > 256) return -3;
+  plan->H = H; plan->W = W; plan->S = S;
+  resized_output_size(H, W, S, &plan->nh, &plan->nw);
+  if (plan->nh < S || plan->nw < S) return -3;
+  plan->top = round_half_even((plan->nh - S) / 2.0);   // torchvision center_crop
+  plan->left = round_half_even((plan->nw - S) / 2.0);
+  axis_tables(W, plan->nw, plan->left, S, plan->hb, plan->hk, plan->kh);
+  axis_tables(H, plan->nh, plan->top, S, plan->vb, plan->vk, plan->kv);
+  // column span the crop needs; horizontal bounds become relative to it
+  plan->x0 = plan->hb[0];
+  int x1 = 0;
+  for (int i = 0; i < S; ++i) x1 = std::max(x1, plan->hb[2 * i] + plan->hb[2 * i + 1]);
+  for (int i = 0; i < S; ++i) plan->hb[2 * i] -= plan->x0;
+  plan->span_bytes = (x1 - plan->x0) * 3;
+  plan->row_pitch = (plan->span_bytes + 3 + 15) / 16 * 16;
+  plan->tmp_pitch = (3 * S + 15) / 16 * 16;
+  // rows per CTA: the largest tile whose source-row window fits in shared memory
+  const int smem_cap = 200 * 1024;
+  plan->ty = 0;
+  for (int ty : {8, 4, 2, 1}) {
+    int max_rows = 0;
+    for (int y0 = 0; y0 < S; y0 += ty) {
+      const int y1 = std::min(S, y0 + ty) - 1;
+      max_rows = std::max(max_rows, plan->vb[2 * y1] + plan->vb[2 * y1 + 1] - plan->vb[2 * y0]);
+    }
+    const long long smem = static_cast<long long>(G) * plan->row_pitch + static_cast<long long>(max_rows) * plan->tmp_pitch;
+    if (smem <= smem_cap) { plan->ty = ty; plan->max_rows = max_rows; plan->smem_bytes = static_cast<int>(smem); break; }
+  }
+  if (plan->ty == 0) return -6;  // source too large for the shared-memory window
+  return 0;
+}
+
+int resize_crop_launch(const ResizePlanHost& plan, const int* d_tables, const uint8_t* src, uint8_t* dst, long long B, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(resize_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  KParams p;
+  p.src = src; p.dst = dst;
+  const int S = plan.S;
+  p.hb = d_tables;
+  p.hk = p.hb + 2 * S;
+  p.vb = p.hk + static_cast<size_t>(S) * plan.kh;
+  p.vk = p.vb + 2 * S;
+  p.H = plan.H; p.W = plan.W; p.S = S; p.kh = plan.kh; p.kv = plan.kv; p.x0 = plan.x0; p.span_bytes = plan.span_bytes;
+  p.row_pitch = plan.row_pitch; p.ty = plan.ty; p.max_rows = plan.max_rows; p.tmp_pitch = plan.tmp_pitch;
+  const int threads = (S + 31) / 32 * 32;
+  for (long long b0 = 0; b0 < B; b0 += 65535) {
+    const int nb = static_cast<int>(std::min<long long>(65535, B - b0));
+    p.src = src + static_cast<size_t>(b0) * plan.H * plan.W * 3;
+    p.dst = dst + static_cast<size_t>(b0) * 3 * S * S;
+    dim3 grid(static_cast<unsigned>((S + plan.ty - 1) / plan.ty), static_cast<unsigned>(nb));
+    resize_crop_kernel<<<grid, threads, plan.smem_bytes, s>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  return 0;
+}
+
+size_t resize_plan_table_ints(const ResizePlanHost& plan) {
+  return static_cast<size_t>(plan.S) * (4 + plan.kh + plan.kv);
+}
+
+void resize_plan_pack(const ResizePlanHost& plan, int* out) {
+  const int S = plan.S;
+  std::memcpy(out, plan.hb.data(), sizeof(int) * 2 * S);
+  out += 2 * S;
+  std::memcpy(out, plan.hk.data(), sizeof(int) * static_cast<size_t>(S) * plan.kh);
+  out += static_cast<size_t>(S) * plan.kh;
+  std::memcpy(out, plan.vb.data(), sizeof(int) * 2 * S);
+  out += 2 * S;
+  std::memcpy(out, plan.vk.data(), sizeof(int) * static_cast<size_t>(S) * plan.kv);
+}
+
+}  // namespace hb

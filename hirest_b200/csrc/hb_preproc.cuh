@@ -1,0 +1,28 @@
+// hb_preproc.cuh — GPU frame preprocessing: Resize(S, BICUBIC) + CenterCrop(S) on uint8 RGB frames, bit-identical to
+// torchvision-on-PIL (implementation and reference citations in hb_preproc.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <vector>
+
+namespace hb {
+
+// Host-side plan for one source size: torchvision's output size / crop offsets and Pillow's fixed-point weight tables
+// restricted to the S x S crop.
+struct ResizePlanHost {
+  int H = 0, W = 0, S = 0;
+  int nh = 0, nw = 0, top = 0, left = 0;  // resized size and crop offsets
+  int kh = 0, kv = 0;                     // taps per output column / row (table row strides)
+  int x0 = 0, span_bytes = 0;             // first source column the crop needs; bytes per source row it needs
+  int row_pitch = 0, tmp_pitch = 0, ty = 0, max_rows = 0, smem_bytes = 0;
+  std::vector<int> hb, hk, vb, vk;        // bounds [S,2] = (first tap, taps), weights [S,k] (22-bit fixed point)
+};
+
+void resized_output_size(int H, int W, int S, int* nh, int* nw);
+int resize_plan_build(ResizePlanHost* plan, int H, int W, int S);   // 0, -3 invalid size, -6 source too large
+size_t resize_plan_table_ints(const ResizePlanHost& plan);
+void resize_plan_pack(const ResizePlanHost& plan, int* out);        // hb | hk | vb | vk, as the kernel expects them
+// src [B,H,W,3] uint8 (device) -> dst [B,3,S,S] uint8 (device). d_tables = packed tables on the device.
+int resize_crop_launch(const ResizePlanHost& plan, const int* d_tables, const uint8_t* src, uint8_t* dst, long long B, cudaStream_t s);
+
+}  // namespace hb

@@ -239,6 +239,22 @@ HB_API int hb_pool_normalize(const float* emb, int64_t V, int F, int E, float* o
 HB_API int hb_similarity(const float* text, int64_t Q, const float* video, int64_t V, int E, float* scores,
                   int64_t ld_scores, int exact, void* stream);
 
+/* ---- frame preprocessing --------------------------------------------------- */
+/* Resize(S, BICUBIC) + CenterCrop(S) of decoded RGB frames, bit-identical to the reference's CPU transform
+ * (torchvision on PIL images: EVA_clip/eva_clip.py:144-147; callers inference_video_retrieval.py:43-49,
+ * extract_features.py:48-50).  src: uint8 [B,H,W,3] (device, all frames of one call share H x W);
+ * dst: uint8 [B,3,S,S] (device), ready for hb_vit_encode_u8 which folds ToTensor + Normalize.  S <= 256.
+ * The fixed-point weight tables (Pillow's, computed on the host in double) are cached per (device, H, W, S). */
+HB_API int hb_resize_crop_u8(const uint8_t* src, int64_t B, int H, int W, int S, uint8_t* dst, void* stream);
+/* Geometry of the above: resized size (torchvision Resize(int)) and crop offsets (CenterCrop). */
+HB_API int hb_resize_geometry(int H, int W, int S, int* new_h, int* new_w, int* top, int* left);
+
+/* Host-only (no device call): the integer tables hb_resize_crop_u8 uses, for verification against Pillow.
+ * info[0..5] = taps per column, taps per row, first source column, bytes per source row staged, rows per CTA, smem bytes;
+ * tables (capacity cap ints) = col bounds [S,2] (first tap relative to info[2], taps) | col weights [S,info[0]] |
+ * row bounds [S,2] | row weights [S,info[1]].  Returns the number of ints (written only if cap is large enough) or < 0. */
+HB_API int64_t hb_resize_tables(int H, int W, int S, int info[6], int* tables, int64_t cap);
+
 /* ---- generic fused linear (tcgen05 GEMM) ------------------------------------------------------ */
 #define HB_EPI_BF16 0       /* out bf16 = x W^T + b                      */
 #define HB_EPI_GELU_BF16 1  /* out bf16 = gelu_erf(x W^T + b)            */
