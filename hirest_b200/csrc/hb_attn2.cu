@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) vit_attn2_kernel(const __grid_c
   uint64_t* bar_o = bars + 5;      // O = P.V committed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int g = blockIdx.x & 1;
   const int bh = blockIdx.x >> 1;
   const int b = bh / p.H, h = bh - b * p.H;
@@ -132,9 +132,14 @@ __global__ void __launch_bounds__(A2_THREADS, 2) vit_attn2_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    // ------------------------------------------------------------------ TMA + MMA issue (one thread)
-    if (lane == 0) {
-      const int row0 = b * T_TOK;
+    // ------------------------------------------------------------------ TMA + MMA issue
+    // The whole warp walks this sequence and one elected lane issues; addresses routed through shfl(…, 0) are known to be
+    // warp-uniform, so descriptors live in uniform registers and every tcgen05.mma issues directly (with `if (lane == 0)`
+    // each one was wrapped in an ELECT + R2UR.BROADCAST waterfall of ~25 instructions on the CTA's critical path).
+    const uint32_t sb = __shfl_sync(0xffffffffu, sbase, 0);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int row0 = b * T_TOK;
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_qk, 6u * 16384u);
 #pragma unroll
       for (int slab = 0; slab < 2; ++slab) {
@@ -143,34 +148,43 @@ __global__ void __launch_bounds__(A2_THREADS, 2) vit_attn2_kernel(const __grid_c
         for (int half = 0; half < 2; ++half)
           tma_load_3d(smem + KV_OFF + slab * 32768 + half * 16384, &tmQKV, bar_qk, slab * 64, p.H + h, row0 + half * 128);
       }
-      mbar_wait(bar_qk, 0);
-      tc_fence_after();
+    }
+    __syncwarp();
+    mbar_wait(bar_qk, 0);
+    tc_fence_after();
+    if (elect_one()) {
       const uint32_t idesc_s = umma_idesc_bf16(128, 256);
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         const int slab = k >> 2, kk = k & 3;
-        const uint64_t ad = umma_desc_sw128(sbase + Q_OFF + static_cast<uint32_t>(slab) * 16384u + kk * 32);
-        const uint64_t bd = umma_desc_sw128(sbase + KV_OFF + static_cast<uint32_t>(slab) * 32768u + kk * 32);
-        umma_bf16<1>(tmem_base, ad, bd, idesc_s, k > 0 ? 1u : 0u);
+        const uint64_t ad = umma_desc_sw128(sb + Q_OFF + static_cast<uint32_t>(slab) * 16384u + kk * 32);
+        const uint64_t bd = umma_desc_sw128(sb + KV_OFF + static_cast<uint32_t>(slab) * 32768u + kk * 32);
+        umma_bf16<1>(tb, ad, bd, idesc_s, k > 0 ? 1u : 0u);
       }
       umma_commit<1>(bar_s);
-      // K is dead once the MMAs have retired and the extra-token dot products have read their rows: V takes its place
-      mbar_wait(bar_s, 0);
-      mbar_wait(bar_kfree, 0);
+    }
+    __syncwarp();
+    // K is dead once the MMAs have retired and the extra-token dot products have read their rows: V takes its place
+    mbar_wait(bar_s, 0);
+    mbar_wait(bar_kfree, 0);
+    if (elect_one()) {
       mbar_arrive_expect_tx(bar_v, 4u * 16384u);
 #pragma unroll
       for (int slab = 0; slab < 2; ++slab)
 #pragma unroll
         for (int half = 0; half < 2; ++half)
           tma_load_3d(smem + KV_OFF + slab * 32768 + half * 16384, &tmQKV, bar_v, slab * 64, 2 * p.H + h, row0 + half * 128);
-      mbar_wait(bar_p, 0);
-      mbar_wait(bar_v, 0);
-      tc_fence_after();
+    }
+    __syncwarp();
+    mbar_wait(bar_p, 0);
+    mbar_wait(bar_v, 0);
+    tc_fence_after();
+    if (elect_one()) {
       const uint32_t idesc_o = umma_idesc_bf16(128, 96) | (1u << 16);  // B (= V) is MN-major
 #pragma unroll
       for (int k = 0; k < 16; ++k) {   // 16 keys per step: 8 packed TMEM columns of P, 16 smem rows (2048 B) of V
-        const uint64_t bd = desc_sw128_mn(sbase + KV_OFF + static_cast<uint32_t>(k) * 2048u, 32768u);
-        umma_bf16_ts(tmem_base + 128, tmem_base + static_cast<uint32_t>(k * 8), bd, idesc_o, k > 0 ? 1u : 0u);
+        const uint64_t bd = desc_sw128_mn(sb + KV_OFF + static_cast<uint32_t>(k) * 2048u, 32768u);
+        umma_bf16_ts(tb + 128, tb + static_cast<uint32_t>(k * 8), bd, idesc_o, k > 0 ? 1u : 0u);
       }
       umma_commit<1>(bar_o);
     }

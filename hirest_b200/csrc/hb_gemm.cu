@@ -128,7 +128,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* sbias = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256 + NUM_EPI_WARPS * C::EPI_STAGE_BYTES);  // [2][BN]
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform values are routed through shfl(…, 0) so the compiler KNOWS they are uniform: the producer / MMA loops then
+  // live in uniform registers and tcgen05 / TMA instructions issue directly.  With `if (lane == 0)` around those loops every
+  // tcgen05.mma was wrapped in an ELECT + 7x R2UR.BROADCAST "waterfall" (136 instructions per k-block): the single issuing
+  // thread, not the tensor pipe, was the bottleneck (ncu: MMA warp never waits on a barrier, tensor pipe 60-72 % active).
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = (cta_rank == 0);
@@ -159,11 +163,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
 
   if (warp == 0) {
-   if (lane == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
     TileIter it(worker, num_workers, m_tiles, n_tiles);
@@ -176,31 +180,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // (Tried and dropped: TMA L2-prefetch of the A boxes 8 k-blocks ahead — no measurable change; the ring is not latency-starved.)
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
-        uint8_t* sa = smem + stage * C::STAGE_BYTES;
-        uint8_t* sw = sa + C::A_BYTES;
-        if constexpr (CG == 1) {
-          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, row_a);
-          tma_load_2d(sw, &tmW, &full_bar[stage], kb * BK, row_w);
-        } else {
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-          tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, row_a);  // (evict-first on A was 5 % slower: its k-blocks are shared by the N-tile workers)
-          tma_load_2d_pair_hint(sw, &tmW, &full_bar[stage], kb * BK, row_w, kEvictLast);  // weights are re-read by every M-block
+        if (elect_one()) {
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sw = sa + C::A_BYTES;
+          if constexpr (CG == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, row_a);
+            tma_load_2d(sw, &tmW, &full_bar[stage], kb * BK, row_w);
+          } else {
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, row_a);  // (evict-first on A was 5 % slower: its k-blocks are shared by the N-tile workers)
+            tma_load_2d_pair_hint(sw, &tmW, &full_bar[stage], kb * BK, row_w, kEvictLast);  // weights are re-read by every M-block
+          }
         }
+        __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-   }
-   __syncwarp();
   } else if (warp == 1) {
-   if (lane == 0 && leader) {
-    // ===================== MMA issuer =====================
+   if (leader) {
+    // ===================== MMA issuer (whole warp runs the loop, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     TileIter it(worker, num_workers, m_tiles, n_tiles);
     int m_blk, n_blk;
+    constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B (umma_desc_sw128)
     while (it.next(m_blk, n_blk)) {
       const int n_eff = min(BN, p.N - n_blk * BN);
       const uint32_t idesc = umma_idesc_bf16(BM * CG, static_cast<uint32_t>(n_eff));
@@ -210,23 +216,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
-        const uint32_t w_addr = a_addr + C::A_BYTES;
+        // descriptor low words: (address >> 4) | LBO(1) << 16; advancing K by 16 bf16 = 32 bytes adds 2
+        const uint32_t a_lo = (((smem_base + static_cast<uint32_t>(stage) * C::STAGE_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t w_lo = a_lo + (C::A_BYTES >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t adesc = umma_desc_sw128(a_addr + k * UMMA_K * 2);
-          const uint64_t wdesc = umma_desc_sw128(w_addr + k * UMMA_K * 2);
-          umma_bf16<CG>(d_tmem, adesc, wdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = (static_cast<uint64_t>(DESC_HI) << 32) | (a_lo + 2u * k);
+            const uint64_t wdesc = (static_cast<uint64_t>(DESC_HI) << 32) | (w_lo + 2u * k);
+            umma_bf16<CG>(d_tmem, adesc, wdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit<CG>(&empty_bar[stage]);  // smem slot free once these MMAs retire
+          if (kb == k_blocks - 1) umma_commit<CG>(&tmem_full_bar[acc]);
         }
-        umma_commit<CG>(&empty_bar[stage]);  // smem slot free once these MMAs retire
-        if (kb == k_blocks - 1) umma_commit<CG>(&tmem_full_bar[acc]);
+        __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
    }
-   __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = warp & 3;               // TMEM lane quarter this warp may access
