@@ -182,6 +182,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.init(local_rank)
+    if os.environ.get("HB_PLAIN_TILES") == "1":  # A/B switch for the GEMM column tiling (same results, see hb_set_gemm_balanced_tiles)
+        _lib.check(lib.hb_set_gemm_balanced_tiles(0))
 
     sd = synthetic.make_eva_state_dict(cfg, seed=0, device=dev)
     model = eva_clip.EVA_CLIP(**cfg, max_image_batch=args.frames, max_text_batch=max(args.queries, 8))

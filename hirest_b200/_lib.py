@@ -9,7 +9,8 @@ import ctypes as C
 import os
 import threading
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhirest_b200.so")
+# HIREST_B200_LIB selects another build of the same library (A/B experiments of kernel variants); never a different backend.
+_LIB_PATH = os.environ.get("HIREST_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libhirest_b200.so")
 _lib = None
 _lock = threading.Lock()
 _inited_device = None
@@ -88,6 +89,7 @@ SIGNATURES = {
     "hb_set_gemm_cta_group": (C.c_int, [C.c_int]),
     "hb_set_attention_version": (C.c_int, [C.c_int]),
     "hb_set_ln_fold": (C.c_int, [C.c_int]),
+    "hb_set_gemm_balanced_tiles": (C.c_int, [C.c_int]),
     "hb_profile_start": (C.c_int, []),
     "hb_profile_stop": (C.c_int, [C.POINTER(HbProfileSummary)]),
     "hb_vit_create": (C.c_int, [C.POINTER(HbVitConfig), C.POINTER(HbVitWeights), C.c_int, C.c_void_p,
@@ -120,6 +122,7 @@ SIGNATURES = {
     "hb_resize_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                      C.POINTER(C.c_int)]),
     "hb_resize_tables": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_int64]),
+    "hb_subsample_pool_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hb_similarity": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int,
                                 C.c_void_p]),
     "hb_linear": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

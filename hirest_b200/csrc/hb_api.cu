@@ -211,7 +211,7 @@ struct LnFold {
   void* xb_out = nullptr;           // producer side
   int ld_xb = 0;
   float* stats_out = nullptr;
-  int slots = 1;                    // partial-sum slots per row = ceil(D / 128)
+  int slots = 1;                    // partial-sum slots per row = 2 * ceil(D / 256)
 };
 
 int run_gemm(const CUtensorMap& tmA, const Linear& L, long long M, void* out, int ldo, int epi, cudaStream_t s,
@@ -289,6 +289,11 @@ int64_t hb_launch_count(void) { return g_launches.load(); }
 
 int hb_set_ln_fold(int on) {
   g_ln_fold = on ? 1 : 0;
+  return HB_OK;
+}
+
+int hb_set_gemm_balanced_tiles(int on) {
+  hb::gemm_set_balanced_tiles(on);
   return HB_OK;
 }
 
@@ -376,9 +381,12 @@ int hb_vit_create(const HbVitConfig* cfg, const HbVitWeights* w, int max_batch, 
   if ((r = m->clsn.init(max_batch, D))) return r;
   if (m->ln_fold) {
     if ((r = m->xb.init(rows, D))) return r;
-    const size_t slots = static_cast<size_t>((D + 127) / 128);
+    const size_t slots = static_cast<size_t>(2 * ((D + 255) / 256));   // one per (N tile, column half) of the producing GEMM
     if ((r = m->stats1.alloc(static_cast<size_t>(rows) * slots * 8))) return r;
     if ((r = m->stats2.alloc(static_cast<size_t>(rows) * slots * 8))) return r;
+    // a slot whose column half is empty (last tile narrower than 128) is never written: it must read as zero
+    HB_CUDA(cudaMemsetAsync(m->stats1.p, 0, m->stats1.bytes, s));
+    HB_CUDA(cudaMemsetAsync(m->stats2.p, 0, m->stats2.bytes, s));
   }
   if ((r = m->x.alloc(static_cast<size_t>(rows) * D * 4))) return r;
   if ((r = m->qkv.alloc(static_cast<size_t>(rows) * 3 * D * 2))) return r;
@@ -424,7 +432,7 @@ static int vit_encode_chunk(HbVit* m, const float* frames, const uint8_t* frames
     // LayerNorm folded into the GEMMs: the residual stream travels as fp32 x + a bf16 copy xb + per-row (sum, sumsq)
     // partials, one slot per 128 columns, each written by exactly one warp (no atomics: bit-reproducible, batch-independent).
     // QKV / fc1 read xb and apply rstd / mean in their epilogue, proj / fc2 refresh xb and the statistics in theirs.
-    const int slots = (D + 127) / 128;
+    const int slots = 2 * ((D + 255) / 256);
     HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::row_stats_launch(x, m->xb.ptr(), m->stats1.as<float>(), M, D, slots, s));
     LnFold lf1, lf2, lp1, lp2;
     lf1.slots = lf2.slots = lp1.slots = lp2.slots = slots;
@@ -626,6 +634,15 @@ int hb_pool_normalize(const float* emb, int64_t V, int F, int E, float* out, voi
   if (!emb || !out) return fail(HB_ERR_INVALID, "null argument");
   if (V == 0) return HB_OK;
   HB_LAUNCH(hb::pool_normalize_launch(emb, out, V, F, E, true, false, static_cast<cudaStream_t>(stream)));
+  return HB_OK;
+}
+
+int hb_subsample_pool_normalize(const float* feats, const int64_t* offsets, int64_t V, int n_sub, int E, float* out, void* stream) {
+  if (V == 0) return HB_OK;
+  if (!feats || !offsets || !out) return fail(HB_ERR_INVALID, "null argument");
+  if (V < 0 || E <= 0 || E > 4096) return fail(HB_ERR_INVALID, "need V >= 0 and 1 <= E <= 4096");
+  HB_LAUNCH(hb::subsample_pool_normalize_launch(feats, reinterpret_cast<const long long*>(offsets), out, V, n_sub, E,
+                                                static_cast<cudaStream_t>(stream)));
   return HB_OK;
 }
 

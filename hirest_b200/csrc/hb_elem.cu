@@ -240,6 +240,52 @@ __global__ void __launch_bounds__(256) pool_normalize_kernel(const float* __rest
   }
 }
 
+// Ragged variant for the cached-feature path (inference_video_retrieval.py:298-327): video v owns rows
+// [offsets[v], offsets[v+1]) of one packed [sum T, E] feature blob.  If n_sub > 0 the rows are first subsampled exactly like
+// `np.linspace(0, T - 1, n_sub).astype(int)` (:313: float64 `i * step`, last sample forced to T - 1, truncation), then
+// mean-pooled in fp32 and L2-normalised (:321-326).  One CTA per video; the gather indices are computed on the fly.
+__global__ void __launch_bounds__(256) subsample_pool_normalize_kernel(const float* __restrict__ feats, const long long* __restrict__ offsets,
+                                                                       float* __restrict__ out, int n_sub, int E) {
+  __shared__ float red[8];
+  const long long v = blockIdx.x;
+  const long long r0 = offsets[v];
+  const int T = static_cast<int>(offsets[v + 1] - r0);
+  const int F = (n_sub > 0) ? n_sub : T;
+  const double step = (n_sub > 1) ? static_cast<double>(T - 1) / static_cast<double>(n_sub - 1) : 0.0;
+  float acc[16];
+  float ss = 0.f;
+  const float invF = 1.0f / static_cast<float>(F);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  for (int f = 0; f < F; ++f) {
+    int row = f;
+    if (n_sub > 0) row = (f == n_sub - 1 && n_sub > 1) ? (T - 1) : static_cast<int>(static_cast<double>(f) * step);
+    const float* base = feats + (r0 + row) * E;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int e = threadIdx.x + i * 256;
+      if (e < E) acc[i] += base[e];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    acc[i] = (T > 0) ? acc[i] * invF : 0.f;
+    ss += acc[i] * acc[i];
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float inv = 1.0f / sqrtf(tot);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int e = threadIdx.x + i * 256;
+    if (e < E) out[v * E + e] = acc[i] * inv;
+  }
+}
+
 // Split fp32 rows into three bf16 parts (hi + mid + lo = the fp32 value exactly: 3 x 8 significant bits) and lay
 // them out so that ONE bf16 GEMM over K = 6E reproduces the fp32 dot product to ~2^-23 relative:
 //   mode 0 (text side):  [hi | lo | mid | mid | hi  | hi]
@@ -331,6 +377,14 @@ int pool_normalize_launch(const float* emb, void* out, long long V, int F, int E
   if (E > 4096 || F <= 0) return -7;
   if (out_bf16) pool_normalize_kernel<true><<<static_cast<unsigned>(V), 256, 0, s>>>(emb, out, F, E, normalize ? 1 : 0);
   else pool_normalize_kernel<false><<<static_cast<unsigned>(V), 256, 0, s>>>(emb, out, F, E, normalize ? 1 : 0);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int subsample_pool_normalize_launch(const float* feats, const long long* offsets, float* out, long long V, int n_sub, int E,
+                                    cudaStream_t s) {
+  if (V <= 0) return 0;
+  if (E > 4096) return -7;
+  subsample_pool_normalize_kernel<<<static_cast<unsigned>(V), 256, 0, s>>>(feats, offsets, out, n_sub, E);
   return static_cast<int>(cudaGetLastError());
 }
 

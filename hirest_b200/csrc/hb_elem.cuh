@@ -28,6 +28,8 @@ int text_embed_launch(const long long* ids, const float* tok, const float* pos, 
                       int V, cudaStream_t s);
 int pool_normalize_launch(const float* emb, void* out, long long V, int F, int E, bool normalize, bool out_bf16,
                           cudaStream_t s);
+int subsample_pool_normalize_launch(const float* feats, const long long* offsets, float* out, long long V, int n_sub, int E,
+                                    cudaStream_t s);
 int split_bf16_launch(const float* x, __nv_bfloat16* out, long long rows, int E, int mode, cudaStream_t s);
 int f32_to_bf16_launch(const float* x, __nv_bfloat16* y, long long n, cudaStream_t s);
 

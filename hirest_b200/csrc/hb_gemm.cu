@@ -59,6 +59,30 @@ struct TileIter {
   }
 };
 
+// Column tiling of N.  Plain: tiles of 256 with a narrow tail (1408 = 5 x 256 + 128).  Balanced (default): the same NUMBER of
+// tiles, widths differing by at most one 32-column unit (1408 = 2 x 256 + 4 x 224, 4224 = 13 x 256 + 4 x 224): every tile costs
+// about the same, so the workers that share an M-block's A operand through L2 stay in step (with a half-width tail, and a
+// worker count that is even, the odd workers got all the tails, ran ~17 % faster and pulled the A k-blocks through DRAM twice).
+struct NTiling {
+  int n_tiles, base, rem, unit;
+  __host__ __device__ NTiling(int N, int cg, int balanced) {
+    n_tiles = (N + BN - 1) / BN;
+    unit = 16 * cg;
+    if (balanced && N % unit == 0) {
+      base = (N / n_tiles) / unit * unit;
+      rem = (N - base * n_tiles) / unit;
+    } else {
+      base = BN; rem = 0; unit = 0;
+    }
+  }
+  __host__ __device__ int n0(int n) const { return n * base + (n < rem ? n : rem) * unit; }
+  __host__ __device__ int width(int n, int N) const {
+    const int w = base + (n < rem ? unit : 0);
+    const int left = N - n0(n);
+    return w < left ? w : left;
+  }
+};
+
 // bf16-output epilogues (thread-per-row): r = 32 consecutive fp32 accumulator columns [col0, col0+32) of one row.
 template <int EPI>
 __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const uint32_t (&r)[32], long long row_out,
@@ -139,7 +163,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int tile_m = BM * CG;
   const int m_tiles = (p.M + tile_m - 1) / tile_m;
-  const int n_tiles = (p.N + BN - 1) / BN;
+  const NTiling nt(p.N, CG, p.balanced_n);
+  const int n_tiles = nt.n_tiles;
   const int k_blocks = (p.K + BK - 1) / BK;
   const int worker = blockIdx.x / CG;
   const int num_workers = gridDim.x / CG;
@@ -173,8 +198,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     TileIter it(worker, num_workers, m_tiles, n_tiles);
     int m_blk, n_blk;
     while (it.next(m_blk, n_blk)) {
-      const int n0 = n_blk * BN;
-      const int n_eff = min(BN, p.N - n0);
+      const int n0 = nt.n0(n_blk);
+      const int n_eff = nt.width(n_blk, p.N);
       const int row_a = m_blk * tile_m + static_cast<int>(cta_rank) * BM;
       const int row_w = n0 + static_cast<int>(cta_rank) * (n_eff / CG);
       // (Tried and dropped: TMA L2-prefetch of the A boxes 8 k-blocks ahead — no measurable change; the ring is not latency-starved.)
@@ -189,7 +214,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_load_2d(sw, &tmW, &full_bar[stage], kb * BK, row_w);
           } else {
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, row_a);  // (evict-first on A was 5 % slower: its k-blocks are shared by the N-tile workers)
+              tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, row_a);  // (evict-first on A was 5 % slower: its k-blocks are shared by the N-tile workers; evict-last on fc2's A: no change)
             tma_load_2d_pair_hint(sw, &tmW, &full_bar[stage], kb * BK, row_w, kEvictLast);  // weights are re-read by every M-block
           }
         }
@@ -208,7 +233,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int m_blk, n_blk;
     constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B (umma_desc_sw128)
     while (it.next(m_blk, n_blk)) {
-      const int n_eff = min(BN, p.N - n_blk * BN);
+      const int n_eff = nt.width(n_blk, p.N);
       const uint32_t idesc = umma_idesc_bf16(BM * CG, static_cast<uint32_t>(n_eff));
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
@@ -246,8 +271,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int m_blk, n_blk;
     bool first_tile = true;
     while (it.next(m_blk, n_blk)) {
-      const int n0 = n_blk * BN;
-      const int n_eff = min(BN, p.N - n0);
+      const int n0 = nt.n0(n_blk);
+      const int n_eff = nt.width(n_blk, p.N);
       const int row_in = m_blk * tile_m + static_cast<int>(cta_rank) * BM + q * 32 + lane;
       long long row_out = row_in;
       if (p.remap_in > 0) row_out = static_cast<long long>(row_in / p.remap_in) * p.remap_out + (row_in % p.remap_in) + p.remap_off;
@@ -295,11 +320,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const bool has_add = ROWADD ? (p.rowadd != nullptr) : (p.resid != nullptr);
         // DRAM latency under load (~2-3k cycles) is far longer than one chunk of epilogue work, so the residual of the
         // NEXT tile is pulled into L2 a whole tile ahead; the register prefetch below then only has to cover L2 latency.
-        if (!ROWADD && p.resid != nullptr) {
+        // (long-K tiles last ~50 us, far longer than a line survives in L2 under this kernel's ~3.3 TB/s of DRAM traffic: the
+        //  prefetched residual was evicted before use and read twice, fc2 12.1 -> 10.3 GB of DRAM reads per launch without it)
+        if (!ROWADD && p.resid != nullptr && p.K < 4096) {
           const int et = (warp - 4) * 32 + lane;  // 0..255: row et/2 of the tile, half et%2 of its column span
           auto prefetch_tile = [&](int pm, int pn) {
             const int pri = pm * tile_m + static_cast<int>(cta_rank) * BM + (et >> 1);
-            const int pn0 = pn * BN, pne = min(BN, p.N - pn0);
+            const int pn0 = nt.n0(pn), pne = nt.width(pn, p.N);
             if (pri < p.M) {
               const float* base = p.resid + static_cast<long long>(pri) * p.ldo + pn0;
               for (int cidx = (et & 1) * 128; cidx < min(pne, (et & 1) * 128 + 128); cidx += 32)
@@ -385,7 +412,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // the 8 lanes that share a row (same lane >> 3) combine their partials in a fixed order and one lane writes them to
           // this warp's slot (one per 128-column span): no atomics, so the statistics — and everything downstream — are
           // bit-reproducible and independent of which other rows share the launch.
-          const int slot = (n0 + c_begin) >> 7;
+          const int slot = 2 * n_blk + half;   // one slot per (N tile, column half): ln_slots >= 2 * n_tiles
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float a = psum[i], b = psq[i];
@@ -467,6 +494,7 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams
   const int tile_m = BM * CG;
   const int m_tiles = (p.M + tile_m - 1) / tile_m;
   const int n_tiles = (p.N + BN - 1) / BN;
+  if ((EPI == EPI_F32_STATS) && p.ln_slots < 2 * n_tiles) return -8;
   const int total = m_tiles * n_tiles;
   int workers = num_sms / CG;
   if (workers > total) workers = total;
@@ -530,8 +558,13 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, const uint64_t dims[3],
   return r == CUDA_SUCCESS ? 0 : -(1000 + static_cast<int>(r));
 }
 
-int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p, int epi, int cg, int num_sms,
+namespace { int g_balanced_n = 1; }
+void gemm_set_balanced_tiles(int on) { g_balanced_n = on ? 1 : 0; }
+
+int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p_in, int epi, int cg, int num_sms,
                 cudaStream_t stream) {
+  GemmParams p = p_in;
+  p.balanced_n = g_balanced_n;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return -3;
   if (p.N % 16 != 0) return -4;           // UMMA N granularity at M = 128/256 (and 16-byte stores)
   if (cg == 2 && p.N % 32 != 0) return -4;

@@ -39,12 +39,13 @@ struct GemmParams {
   // LayerNorm fold
   void* xb_out = nullptr;         // EPI_F32_STATS: bf16 copy of out, leading dim ld_xb
   int ld_xb = 0;
-  float* stats_out = nullptr;     // EPI_F32_STATS: [M, ln_slots, 2] (sum, sumsq) per 128-column span, slot = column / 128
+  float* stats_out = nullptr;     // EPI_F32_STATS: [M, ln_slots, 2] partial (sum, sumsq), one slot per (N tile, column half)
   const float* stats_in = nullptr;  // *_LN kinds: [M, ln_slots, 2] row statistics of the A operand's fp32 source
   const float* c1 = nullptr;      // *_LN kinds: [N]; `bias` carries c2
   float ln_eps = 1e-6f;
   int ln_dim = 0;                 // number of features the statistics were taken over
-  int ln_slots = 1;               // partial-sum slots per row (producer: ceil(N / 128))
+  int ln_slots = 1;               // partial-sum slots per row (producer writes slot 2 * n_tile + column half: >= 2 * ceil(N / 256))
+  int balanced_n = 1;             // N tiling: equal-cost tiles (see NTiling in hb_gemm.cu) instead of 256-wide tiles + narrow tail
 };
 
 // Resolve cuTensorMapEncodeTiled through the runtime (no link-time libcuda dependency).
@@ -62,6 +63,9 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, const uint64_t dims[3],
 // Rows of W one CTA loads per stage for cta-group size cg (box_rows for the W map).
 constexpr uint32_t gemm_w_box_rows(int cg) { return 256u / static_cast<uint32_t>(cg); }
 constexpr uint32_t gemm_a_box_rows() { return 128u; }
+
+// Process-wide switch between balanced N tiles (default) and 256-wide tiles + narrow tail (A/B measurements).
+void gemm_set_balanced_tiles(int on);
 
 // Launch. tmA must have box_rows = 128, tmW box_rows = gemm_w_box_rows(cg). cg in {1,2}.
 // Returns cudaError_t as int.

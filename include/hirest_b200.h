@@ -52,6 +52,9 @@ HB_API int hb_set_attention_version(int v);
 /* ViT handles created after this call fold the block LayerNorms into the QKV / fc1 GEMM epilogues (1, default) or run
  * separate LayerNorm kernels (0). */
 HB_API int hb_set_ln_fold(int on);
+/* GEMM column tiling: 1 (default) = equal-cost N tiles (1408 = 2 x 256 + 4 x 224), 0 = 256-wide tiles + narrow tail.
+ * Same results bit for bit; process-wide; exists for A/B measurements. */
+HB_API int hb_set_gemm_balanced_tiles(int on);
 
 /* Per-launch timing for bench.py's roofline: while enabled every kernel launch of this library is bracketed
  * by CUDA events on its own stream.  hb_profile_stop synchronises the device and sums per category:
@@ -233,6 +236,10 @@ HB_API void hb_decoder_destroy(HbDecoder* d);
 /* ---- retrieval scoring ------------------------------------------------------------------------ */
 /* out[v,:] = l2norm(mean_f emb[v,f,:]); emb fp32 [V,F,E]; out fp32 [V,E].  F = 1 gives plain L2 normalise. */
 HB_API int hb_pool_normalize(const float* emb, int64_t V, int F, int E, float* out, void* stream);
+/* Cached-feature path (inference_video_retrieval.py:298-327): feats fp32 [sum_T, E] = the per-video feature tensors packed
+ * back to back, offsets int64 [V+1] (device).  Per video: rows np.linspace(0, T-1, n_sub).astype(int) (all rows if
+ * n_sub <= 0) -> mean -> L2 normalise.  out fp32 [V,E].  Videos must have T >= 1. */
+HB_API int hb_subsample_pool_normalize(const float* feats, const int64_t* offsets, int64_t V, int n_sub, int E, float* out, void* stream);
 /* scores[q,v] = <text[q,:], video[v,:]>; text fp32 [Q,E], video fp32 [V,E], scores fp32 [Q, ld_scores].
  * exact != 0: one bf16 GEMM over 3-way split operands (hi+mid+lo = the fp32 value exactly), K = 6E: fp32-accurate
  * scores, so top-k matches the reference's fp32 matmul up to fp32 rounding ties; exact == 0: single plain bf16 GEMM. */

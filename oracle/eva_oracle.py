@@ -129,6 +129,15 @@ def subsample_cached_features(video_embeds, n_model_frames):
     return video_embeds[ids]
 
 
+def cached_video_embedding(video_embeds, n_model_frames):
+    """Loop body of the cached-feature path, inference_video_retrieval.py:306-326: subsample (if n_model_frames > 0),
+    .float(), mean(dim=0, keepdim=True), /= norm.  Returns [1, E]."""
+    if n_model_frames > 0:
+        video_embeds = subsample_cached_features(video_embeds, n_model_frames)
+    v = video_embeds.float().mean(dim=0, keepdim=True)
+    return v / v.norm(dim=-1, keepdim=True)
+
+
 def similarity(text_hat, video_hat):
     """inference_video_retrieval.py:334 — fp32 matmul, no logit scale."""
     return torch.matmul(text_hat, video_hat.T)
