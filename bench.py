@@ -30,9 +30,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "frames/sec encoded+scored (EVA-CLIP-g/14 224px)"
 # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, mean over the four GEMMs of one ViT layer at 1024 frames
-# (QKV 2.93, proj 4.30, fc1 3.99, fc2 10.07 GB) from the `ncu --set full` capture in profiles/r01_one_layer_ncu_full.txt;
-# algorithmic bytes of the same four launches: 2.96 + 3.70 + 3.99 + 6.19 GB (fc2 re-reads its A operand).
-GEMM_TRAFFIC_BYTES_PER_LAUNCH = 5.32e9
+# (QKV 2.95, proj 4.43, fc1 3.98, fc2 10.53 GB) from the `ncu --set full` capture in profiles/r01_one_layer_ncu_full.txt;
+# algorithmic bytes of the same four launches: 2.96 + 4.44 + 3.97 + 6.93 GB (fp32 residual in/out + bf16 copy counted for
+# proj / fc2; fc2 still re-reads part of its A operand through DRAM).
+GEMM_TRAFFIC_BYTES_PER_LAUNCH = 5.47e9
 UNIT = "frames/s"
 
 
@@ -108,8 +109,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm_sorted = sorted(sm)
-        return {"sm_mhz": sm_sorted[len(sm_sorted) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+        return {"sm_mhz": sm_sorted[len(sm_sorted) // 2], "sm_mhz_min": sm_sorted[0], "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def cpu_reference_run(cfg, n_frames, steps, warmup, frames_per_video, n_queries):
@@ -185,6 +186,9 @@ def main():
     if os.environ.get("HB_PLAIN_TILES") == "1":  # A/B switch for the GEMM column tiling (same results, see hb_set_gemm_balanced_tiles)
         _lib.check(lib.hb_set_gemm_balanced_tiles(0))
 
+    if os.environ.get("HB_PREFETCH_MAX_K"):
+        _lib.check(lib.hb_set_gemm_resid_prefetch_max_k(int(os.environ["HB_PREFETCH_MAX_K"])))
+
     sd = synthetic.make_eva_state_dict(cfg, seed=0, device=dev)
     model = eva_clip.EVA_CLIP(**cfg, max_image_batch=args.frames, max_text_batch=max(args.queries, 8))
     model.load_state_dict(sd, strict=True)
@@ -231,11 +235,16 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
+        marks = []
         for _ in range(args.steps):
             scores = step_device()
+            mk = torch.cuda.Event(enable_timing=True)
+            mk.record()
+            marks.append(mk)
         e1.record()
         barrier()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
+        ms_steps = [round((e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]), 1) for i in range(len(marks))]
         prof = _lib.HbProfileSummary()
         _lib.check(lib.hb_profile_stop(prof), "hb_profile_stop")
         launches = lib.hb_launch_count() - launches0
@@ -266,11 +275,17 @@ def main():
                     dev_bufs[i % 2].copy_(frames_host, non_blocking=True)
                     copied[i % 2].record(copy_stream)
 
+            step_events = []
+
             def run_e2e(n):
                 for k in range(2):
                     consumed[k] = None
+                step_events.clear()
                 issue_copy(0)
                 for i in range(n):
+                    ev0 = torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                    step_events.append(ev0)
                     if i + 1 < n:
                         issue_copy(i + 1)
                     cur = torch.cuda.current_stream()
@@ -285,15 +300,33 @@ def main():
                     scores_host.copy_(sc, non_blocking=True)
                     cur.synchronize()  # the caller holds this step's scores on the host before the next step starts
 
-            run_e2e(max(1, min(args.warmup, 2)))
+            # the clock sampler (an nvidia-smi child process) starts BEFORE the warm-up so that its start-up cost and the idle gap
+            # it would open (the GPU drops out of its boost state and the first timed step pays for the ramp) stay outside the
+            # timed region; the warm-up runs straight into the timed steps
+            sampler2 = ClockSampler(local_rank)
+            if rank == 0:
+                sampler2.start()
+            run_e2e(max(2, min(args.warmup, 3)))
             barrier()
+            sampler2.lines.clear()
             e0.record()
             run_e2e(args.steps)
             e1.record()
             barrier()
+            clocks_e2e = sampler2.stop() if rank == 0 else None
             ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+            ms_steps_e2e = [round(step_events[i].elapsed_time(step_events[i + 1]), 1) for i in range(len(step_events) - 1)]
+            # diagnostic: the bare pinned-host -> device copy of one step's frames, nothing else running
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            dev_bufs[0].copy_(frames_host, non_blocking=True)
+            h1.record()
+            torch.cuda.synchronize()
+            h2d_ms = h0.elapsed_time(h1)
             e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                    "h2d_bytes_per_step": frames_host.numel() * frames_host.element_size() + tokens_host.numel() * 8,
+                   "h2d_ms_alone": h2d_ms, "clocks": clocks_e2e,
+                   "ms_steps": ms_steps_e2e,
                    "input": "uint8 frames [B,3,224,224] in pinned host memory, normalised on the GPU; H2D double-buffered on a side stream",
                    "d2h_bytes_per_step": scores_host.numel() * 4, "ms_per_step": ms_e2e / args.steps}
 
@@ -315,7 +348,7 @@ def main():
     flops_frame = synthetic.encode_image_flops(cfg)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / args.steps, "ms_steps": ms_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{model_name} frame encoder, {B}-frame batch per GPU ({B // Fv} videos x {Fv} frames) + mean-pool/L2-norm"
                                f" + {'NCCL all-gather + ' if world > 1 else ''}cosine scores vs {Q} text queries ({new_q} re-encoded per step)",

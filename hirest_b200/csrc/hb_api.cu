@@ -297,6 +297,11 @@ int hb_set_gemm_balanced_tiles(int on) {
   return HB_OK;
 }
 
+int hb_set_gemm_resid_prefetch_max_k(int k) {
+  hb::gemm_set_resid_prefetch_max_k(k);
+  return HB_OK;
+}
+
 int hb_set_attention_version(int v) {
   if (v != 1 && v != 2) return fail(HB_ERR_INVALID, "attention version must be 1 or 2");
   g_attn_version = v;

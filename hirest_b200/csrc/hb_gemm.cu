@@ -197,6 +197,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t phase = 0;
     TileIter it(worker, num_workers, m_tiles, n_tiles);
     int m_blk, n_blk;
+    const uint64_t hint_a = p.a_hint == 1 ? kEvictFirst : (p.a_hint == 2 ? kEvictLast : kEvictNormal);
+    const uint64_t hint_w = p.w_hint == 1 ? kEvictFirst : (p.w_hint == 2 ? kEvictLast : kEvictNormal);
+    (void)hint_a; (void)hint_w;
     while (it.next(m_blk, n_blk)) {
       const int n0 = nt.n0(n_blk);
       const int n_eff = nt.width(n_blk, p.N);
@@ -214,8 +217,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             tma_load_2d(sw, &tmW, &full_bar[stage], kb * BK, row_w);
           } else {
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-              tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * BK, row_a);  // (evict-first on A was 5 % slower: its k-blocks are shared by the N-tile workers; evict-last on fc2's A: no change)
-            tma_load_2d_pair_hint(sw, &tmW, &full_bar[stage], kb * BK, row_w, kEvictLast);  // weights are re-read by every M-block
+            // default hints: A normal (evict-first was 5 % slower: its k-blocks are shared by the N-tile workers; evict-last on
+            // fc2's A: no change), W evict-last (weights are re-read by every M-block)
+            tma_load_2d_pair_hint(sa, &tmA, &full_bar[stage], kb * BK, row_a, hint_a);
+            tma_load_2d_pair_hint(sw, &tmW, &full_bar[stage], kb * BK, row_w, hint_w);
           }
         }
         __syncwarp();
@@ -320,9 +325,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const bool has_add = ROWADD ? (p.rowadd != nullptr) : (p.resid != nullptr);
         // DRAM latency under load (~2-3k cycles) is far longer than one chunk of epilogue work, so the residual of the
         // NEXT tile is pulled into L2 a whole tile ahead; the register prefetch below then only has to cover L2 latency.
-        // (long-K tiles last ~50 us, far longer than a line survives in L2 under this kernel's ~3.3 TB/s of DRAM traffic: the
-        //  prefetched residual was evicted before use and read twice, fc2 12.1 -> 10.3 GB of DRAM reads per launch without it)
-        if (!ROWADD && p.resid != nullptr && p.K < 4096) {
+        // Off by default (prefetch_max_k = 0): a tile lasts 15 us (proj) to 50 us (fc2), longer than a line survives in L2 under
+        // this kernel's 3-5 TB/s of DRAM traffic, so the prefetched residual was evicted and read twice (DRAM reads per launch
+        // fc2 12.1 -> 10.3 GB, proj 3.0 -> 2.25 GB = exactly A + residual); step time unchanged either way.
+        if (!ROWADD && p.resid != nullptr && p.K < p.prefetch_max_k) {
           const int et = (warp - 4) * 32 + lane;  // 0..255: row et/2 of the tile, half et%2 of its column span
           auto prefetch_tile = [&](int pm, int pn) {
             const int pri = pm * tile_m + static_cast<int>(cta_rank) * BM + (et >> 1);
@@ -558,13 +564,18 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, const uint64_t dims[3],
   return r == CUDA_SUCCESS ? 0 : -(1000 + static_cast<int>(r));
 }
 
-namespace { int g_balanced_n = 1; }
+namespace { int g_balanced_n = 1; int g_prefetch_max_k = 0; int g_a_hint = -1; int g_w_hint = -1; }
+void gemm_set_l2_hints(int a_hint, int w_hint) { g_a_hint = a_hint; g_w_hint = w_hint; }
 void gemm_set_balanced_tiles(int on) { g_balanced_n = on ? 1 : 0; }
+void gemm_set_resid_prefetch_max_k(int k) { g_prefetch_max_k = k; }
 
 int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p_in, int epi, int cg, int num_sms,
                 cudaStream_t stream) {
   GemmParams p = p_in;
   p.balanced_n = g_balanced_n;
+  p.prefetch_max_k = g_prefetch_max_k;
+  if (g_a_hint >= 0) p.a_hint = g_a_hint;
+  if (g_w_hint >= 0) p.w_hint = g_w_hint;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return -3;
   if (p.N % 16 != 0) return -4;           // UMMA N granularity at M = 128/256 (and 16-byte stores)
   if (cg == 2 && p.N % 32 != 0) return -4;

@@ -45,6 +45,8 @@ struct GemmParams {
   float ln_eps = 1e-6f;
   int ln_dim = 0;                 // number of features the statistics were taken over
   int ln_slots = 1;               // partial-sum slots per row (producer writes slot 2 * n_tile + column half: >= 2 * ceil(N / 256))
+  int prefetch_max_k = 0;         // EPI_F32*: the next tile's residual is L2-prefetched only when K < this (0 = never)
+  int a_hint = 0, w_hint = 2;     // L2 eviction priority of the TMA operand loads: 0 normal, 1 evict-first, 2 evict-last
   int balanced_n = 1;             // N tiling: equal-cost tiles (see NTiling in hb_gemm.cu) instead of 256-wide tiles + narrow tail
 };
 
@@ -66,6 +68,8 @@ constexpr uint32_t gemm_a_box_rows() { return 128u; }
 
 // Process-wide switch between balanced N tiles (default) and 256-wide tiles + narrow tail (A/B measurements).
 void gemm_set_balanced_tiles(int on);
+void gemm_set_resid_prefetch_max_k(int k);
+void gemm_set_l2_hints(int a_hint, int w_hint);   // -1 keeps the default (A normal, W evict-last)
 
 // Launch. tmA must have box_rows = 128, tmW box_rows = gemm_w_box_rows(cg). cg in {1,2}.
 // Returns cudaError_t as int.

@@ -1,0 +1,173 @@
+"""In-memory end-to-end chain: moment retrieval → moment segmentation → step captioning.
+
+Reference: ``run.py:383-490`` (``--end_to_end``) runs the three tasks one after the other and hands results from one to the
+next THROUGH DISK: it dumps each task's predictions to JSON, rewrites ``all_data_test.json`` with the predicted bounds /
+steps, and rebuilds dataset + loader for the next task (``hirest_dataset.py:150-300`` turns the timestamps back into frame
+masks, ``:409-531`` collates).  Here the same hand-off happens in memory: predictions stay Python lists for the few integers
+that cross task boundaries, features stay tensors, and each task is one ``MomentModel.test_step`` on the GPU.
+
+The glue below restates, with citations, exactly what the reference computes between the model calls:
+
+* timestamp ↔ frame conversions (``hirest_dataset.py:12-68``),
+* the per-task item construction and masks (``hirest_dataset.py:153-300``),
+* ``collate_fn`` padding (``hirest_dataset.py:409-531``),
+* the result dictionaries of ``evaluate`` (``run.py:704-830``) and the JSON updates of ``run.py:399-474``.
+
+Output: the structure the reference writes to ``final_end_to_end_results.json``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+import numpy as np
+import torch
+
+
+def timestamp_to_frame_index(timestamp, video_duration, n_frames: int = 32) -> int:
+    """hirest_dataset.py:12-40: index of the linspace bin that contains the timestamp (right-closed), clipped."""
+    video_duration = int(video_duration)
+    if n_frames < 0:
+        n_frames = video_duration
+    bins = np.linspace(0, video_duration - 1, n_frames)
+    return int(min(np.digitize(timestamp, bins, right=True), n_frames - 1))
+
+
+def frame_index_to_timestamp(frame_index: int, video_duration, n_frames: int = 32) -> int:
+    """hirest_dataset.py:42-68."""
+    video_duration = int(video_duration)
+    if n_frames < 0:
+        n_frames = video_duration
+    bins = np.linspace(0, video_duration - 1, n_frames)
+    return int(bins[frame_index])
+
+
+def _n_frames(video: dict, n_model_frames: int) -> int:
+    """hirest_dataset.py:149-152: fixed frame count, or one frame per second of video."""
+    return n_model_frames if n_model_frames > 0 else int(video["video_duration"])
+
+
+def collate(items: Sequence[dict], n_model_frames: int = -1) -> dict:
+    """``collate_fn`` (hirest_dataset.py:409-531) for inference items: zero-pad every per-frame tensor to the longest video."""
+    if n_model_frames > 0:
+        vis = torch.stack([d["vis_feats"] for d in items]).float()
+        vmask = torch.stack([d["video_mask"] for d in items])
+        mmask = torch.stack([d["moment_mask"] for d in items])
+        asr = torch.stack([d["asr_feats"] for d in items]).float()
+    else:
+        max_len = max(d["vis_feats"].shape[0] for d in items)
+
+        def pad(x, d):
+            n_pad = max_len - d["vis_feats"].shape[0]
+            return torch.cat([x, torch.zeros((n_pad,) + tuple(x.shape[1:]), dtype=x.dtype)], dim=0)
+
+        vis = torch.stack([pad(d["vis_feats"], d) for d in items])
+        vmask = torch.stack([pad(d["video_mask"], d) for d in items])
+        mmask = torch.stack([pad(d["moment_mask"], d) for d in items])
+        asr = torch.stack([pad(d["asr_feats"], d) for d in items]).float()
+    out = {"vis_feats": vis, "vis_mask": vmask.long(), "moment_mask": mmask.long(), "asr_feats": asr,
+           "video_duration": [d["video_duration"] for d in items], "video_fnames": [d["fname"] for d in items],
+           "tasks": [d["task"] for d in items], "prompts": [d["prompt"] for d in items],
+           "clip_text_ids": torch.stack([d["clip_text_ids"] for d in items])}
+    if "moment_bound_frames" in items[0]:
+        out["moment_bound_frames"] = torch.LongTensor([d["moment_bound_frames"] for d in items])
+    return out
+
+
+def _base_item(video: dict, task: str, n_frames: int) -> dict:
+    if video["vis_feats"].shape[0] != n_frames:
+        raise ValueError(f"{video['fname']}: {video['vis_feats'].shape[0]} feature rows for {n_frames} frames")
+    return {"task": task, "prompt": video["prompt"], "fname": video["fname"], "video_duration": video["video_duration"],
+            "vis_feats": video["vis_feats"], "asr_feats": video["asr_feats"], "clip_text_ids": video["clip_text_ids"],
+            "video_mask": torch.ones(n_frames, dtype=torch.long)}
+
+
+def _batches(items: List[dict], batch_size: int):
+    for i in range(0, len(items), batch_size):
+        yield items[i:i + batch_size]
+
+
+@torch.no_grad()
+def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beams: int = 5, n_model_frames: int = -1) -> Dict:
+    """Chain the three tasks over ``videos`` (dicts with ``prompt``, ``fname``, ``video_duration``, ``vis_feats [T,1024]``,
+    ``asr_feats [T,384]``, ``clip_text_ids [77]``; order = dataset order).  Returns
+    ``{"final": {prompt: {fname: {"bounds", "steps": [{"index", "heading", "absolute_bounds"}]}}},
+    "moment_retrieval": ..., "moment_segmentation": ..., "step_captioning": ...}`` with the per-task dictionaries the
+    reference dumps next to the final file."""
+    nmf = n_model_frames
+    # ---- 1. moment retrieval (dataset :153-183, evaluate :704-744) -------------------------------------------------
+    items = []
+    for v in videos:
+        n = _n_frames(v, nmf)
+        it = _base_item(v, "moment_retrieval", n)
+        it["moment_mask"] = torch.ones(n, dtype=torch.long)
+        items.append(it)
+    mr: Dict[str, Dict[str, dict]] = {}
+    for chunk in _batches(items, batch_size):
+        pred = model.test_step(collate(chunk, nmf))["prediction"]
+        for it, (s, e) in zip(chunk, pred):
+            d = it["video_duration"]
+            mr.setdefault(it["prompt"], {})[it["fname"]] = {
+                "bounds": [frame_index_to_timestamp(s, d, n_frames=nmf), frame_index_to_timestamp(e, d, n_frames=nmf)],
+                "video_duration": d}
+    # the rewritten test file (run.py:399-417): predicted bounds + five placeholder steps
+    state: Dict[str, Dict[str, dict]] = {}
+    for v in videos:
+        state.setdefault(v["prompt"], {})[v["fname"]] = {
+            "bounds": mr[v["prompt"]][v["fname"]]["bounds"],
+            "steps": [{"index": i, "heading": "", "absolute_bounds": [i, i + 1]} for i in range(5)]}
+    # ---- 2. moment segmentation (dataset :239-266 test branch, evaluate :746-782) ----------------------------------
+    items = []
+    for v in videos:
+        n = _n_frames(v, nmf)
+        d = v["video_duration"]
+        b0, b1 = state[v["prompt"]][v["fname"]]["bounds"]
+        f0 = timestamp_to_frame_index(b0, video_duration=d, n_frames=n)
+        f1 = timestamp_to_frame_index(b1, video_duration=d, n_frames=n)
+        it = _base_item(v, "moment_segmentation", n)
+        it["moment_bound_frames"] = [f0, f1]
+        mm = torch.zeros(n, dtype=torch.long)
+        mm[f0:f1 + 1] = 1
+        it["moment_mask"] = mm
+        items.append(it)
+    ms: Dict[str, dict] = {}
+    for chunk in _batches(items, batch_size):
+        pred = model.test_step(collate(chunk, nmf))["prediction"]
+        for it, raw in zip(chunk, pred):
+            d = it["video_duration"]
+            bounds = [[frame_index_to_timestamp(raw[j], d, n_frames=nmf), frame_index_to_timestamp(raw[j + 1], d, n_frames=nmf)]
+                      for j in range(len(raw) - 1)]
+            ms[it["fname"]] = {"bounds": bounds, "video_duration": d, "pred_bounds": raw}   # keyed by video only (run.py:757)
+    for prompt in state:                                                                     # run.py:437-452
+        for fname in state[prompt]:
+            state[prompt][fname]["steps"] = [{"index": i, "heading": "", "absolute_bounds": b}
+                                             for i, b in enumerate(ms[fname]["bounds"])] if fname in ms else []
+    # ---- 3. step captioning (dataset :268-312, evaluate :787-830) --------------------------------------------------
+    items = []
+    for v in videos:
+        steps = state[v["prompt"]][v["fname"]]["steps"]
+        n = _n_frames(v, nmf)
+        d = v["video_duration"]
+        for step in steps:   # a video whose segmentation produced no step contributes nothing (the reference indexes steps[0] and raises)
+            s, e = step["absolute_bounds"]
+            sf = timestamp_to_frame_index(s, video_duration=d, n_frames=n)
+            ef = timestamp_to_frame_index(e, video_duration=d, n_frames=n)
+            it = _base_item(v, "step_captioning", n)
+            mm = torch.zeros(n, dtype=torch.long)
+            mm[sf:ef] = 1
+            mm[ef] = 1
+            it["moment_mask"] = mm
+            items.append(it)
+    sc: Dict[str, dict] = {}
+    for chunk in _batches(items, batch_size):
+        pred = model.test_step(collate(chunk, nmf), num_beams=num_beams)["prediction"]
+        for it, sent in zip(chunk, pred):
+            e = sc.setdefault(it["fname"], {"captions": []})
+            e["captions"].append({"sentence": sent})
+            e["video_duration"] = it["video_duration"]
+    for prompt in state:                                                                     # run.py:466-472
+        for fname in state[prompt]:
+            if fname in sc:
+                for i, sent in enumerate(sc[fname]["captions"]):
+                    if i < len(state[prompt][fname]["steps"]):
+                        state[prompt][fname]["steps"][i]["heading"] = sent["sentence"]
+    return {"final": state, "moment_retrieval": mr, "moment_segmentation": ms, "step_captioning": sc}

@@ -55,6 +55,8 @@ HB_API int hb_set_ln_fold(int on);
 /* GEMM column tiling: 1 (default) = equal-cost N tiles (1408 = 2 x 256 + 4 x 224), 0 = 256-wide tiles + narrow tail.
  * Same results bit for bit; process-wide; exists for A/B measurements. */
 HB_API int hb_set_gemm_balanced_tiles(int on);
+/* fp32-residual epilogues L2-prefetch the next tile's residual only when K < k (default 0 = never). */
+HB_API int hb_set_gemm_resid_prefetch_max_k(int k);
 
 /* Per-launch timing for bench.py's roofline: while enabled every kernel launch of this library is bracketed
  * by CUDA events on its own stream.  hb_profile_stop synchronises the device and sums per category:

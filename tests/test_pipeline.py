@@ -1,0 +1,120 @@
+"""In-memory end-to-end chain: hirest_b200.pipeline on the GPU vs the CPU restatement of the reference's
+disk-based chain (oracle/pipeline_oracle.py, run.py:383-490).  Everything that crosses a task boundary is an integer or a
+string, so the bar is equality."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from hirest_b200 import pipeline, synthetic
+
+
+def test_frame_timestamp_conversions():
+    """hirest_dataset.py:12-68 semantics, including the float truncation of linspace bins the reference inherits."""
+    for dur in (1, 2, 40, 81, 200, 1234):
+        bins = np.linspace(0, dur - 1, dur)
+        for f in (0, dur // 3, dur - 1):
+            assert pipeline.frame_index_to_timestamp(f, dur, n_frames=-1) == int(bins[f])
+        for t in (0, 0.5, 3, dur / 2, dur - 1, dur + 5):
+            assert pipeline.timestamp_to_frame_index(t, dur, n_frames=-1) == int(min(np.digitize(t, bins, right=True), dur - 1))
+    # fixed 32-frame grid (README example in hirest_dataset.py:24-32)
+    assert pipeline.timestamp_to_frame_index(100, 200, n_frames=32) == 16
+    assert pipeline.frame_index_to_timestamp(31, 200, n_frames=32) == 199
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout only exists in the build container")
+def test_frame_conversions_match_reference():
+    import importlib.util
+    import sys
+    import types
+
+    # hirest_dataset.py imports heavy dependencies at module level; execute only its two pure functions
+    src = open("/root/reference/hirest_dataset.py").read()
+    start = src.index("def timestamp_to_frame_index")
+    end = src.index("class ", start)
+    mod = types.ModuleType("ref_conv")
+    mod.__dict__["np"] = np
+    exec(compile(src[start:end], "hirest_dataset_excerpt", "exec"), mod.__dict__)
+    for dur in (7, 81, 200, 999):
+        for n in (-1, 32):
+            nf = dur if n < 0 else n
+            for f in range(0, nf, max(1, nf // 9)):
+                assert pipeline.frame_index_to_timestamp(f, dur, n_frames=n) == mod.frame_index_to_timestamp(f, dur, n_frames=n)
+            for t in np.linspace(0, dur + 3, 23):
+                assert pipeline.timestamp_to_frame_index(float(t), dur, n_frames=n) == mod.timestamp_to_frame_index(float(t), dur, n_frames=n)
+
+
+def test_collate_pads_like_the_reference():
+    items = []
+    for i, T in enumerate((5, 9, 7)):
+        items.append({"task": "moment_retrieval", "prompt": "p", "fname": f"v{i}", "video_duration": T, "vis_feats": torch.ones(T, 4) * (i + 1),
+                      "asr_feats": torch.ones(T, 3), "clip_text_ids": torch.zeros(77, dtype=torch.long),
+                      "video_mask": torch.ones(T, dtype=torch.long), "moment_mask": torch.ones(T, dtype=torch.long)})
+    b = pipeline.collate(items)
+    assert b["vis_feats"].shape == (3, 9, 4) and b["asr_feats"].shape == (3, 9, 3)
+    assert b["vis_mask"].sum(1).tolist() == [5, 9, 7] and b["vis_mask"].dtype == torch.int64
+    assert float(b["vis_feats"][0, 5:].abs().sum()) == 0.0 and b["video_fnames"] == ["v0", "v1", "v2"]
+
+
+class TableText:
+    """clip_model stand-in: encode_text looks the prompt's feature up by the id stored in token slot 1."""
+
+    def __init__(self, table):
+        self.table = table
+
+    def encode_text(self, ids):
+        return self.table[ids[:, 1].cpu()].to(ids.device)
+
+
+def _write_vocab(tmp_path):
+    vocab = [f"[unused{i}]" for i in range(30522)]
+    vocab[0], vocab[100], vocab[101], vocab[102], vocab[103] = "[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"
+    for i in range(1000, 30522):
+        vocab[i] = f"w{i}"
+    p = tmp_path / "vocab.txt"
+    p.write_text("\n".join(vocab) + "\n")
+    return str(p), vocab
+
+
+@pytest.mark.gpu
+def test_end_to_end_chain_matches_reference_flow(hb, tmp_path):
+    from hirest_b200 import moment
+    from oracle import pipeline_oracle as po
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    prompts = ["make tea", "fix bike"]
+    table = torch.randn(len(prompts), 1024, generator=g)
+    test, feats, videos = {}, {}, []
+    k = 0
+    for pi, p in enumerate(prompts):
+        test[p] = {}
+        for _ in range(3):
+            T = int(torch.randint(40, 90, (1,), generator=g))
+            fn = f"vid{k}"
+            k += 1
+            vis = torch.randn(T, 1024, generator=g)
+            vis = vis / vis.norm(dim=-1, keepdim=True)
+            asr = torch.randn(T, 384, generator=g)
+            feats[fn] = {"vis_feats": vis, "asr_feats": asr, "text_feat": {p: table[pi]}}
+            test[p][fn] = {"video_duration": T}
+            ids = torch.zeros(77, dtype=torch.long)
+            ids[0], ids[1], ids[2] = 49406, pi, 49407
+            videos.append({"prompt": p, "fname": fn, "video_duration": T, "vis_feats": vis, "asr_feats": asr, "clip_text_ids": ids})
+    vocab_path, vocab = _write_vocab(tmp_path)
+    sd = synthetic.make_moment_state_dict(seed=3)
+    m = moment.MomentModel(-1, 384, moment.default_args(bert_vocab_path=vocab_path), clip_model=TableText(table), max_rows=4 * 96, max_batch=4)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev)
+    got = pipeline.run_end_to_end(m, videos, batch_size=4, num_beams=3)
+    with torch.no_grad():
+        ref = po.run_end_to_end(sd, test, feats, vocab, batch_size=4, num_beams=3)
+    assert got["moment_retrieval"] == ref["moment_retrieval"]
+    assert {k: v["pred_bounds"] for k, v in got["moment_segmentation"].items()} == {k: v["pred_bounds"] for k, v in ref["moment_segmentation"].items()}
+    for p in ref["final"]:
+        for fn, a in ref["final"][p].items():
+            assert got["final"][p][fn]["bounds"] == a["bounds"], (p, fn)
+            assert got["final"][p][fn]["steps"] == a["steps"], (p, fn)   # step bounds (ints) and captions (strings)
+    n_steps = sum(len(a["steps"]) for p in got["final"] for a in got["final"][p].values())
+    assert n_steps >= 8 and all(s["heading"] for p in got["final"] for a in got["final"][p].values() for s in a["steps"])

@@ -140,6 +140,8 @@ int main(int argc, char** argv) {
   const bool quick = argc > 1 && std::string(argv[1]) == "quick";
   const int only_cg = argc > 2 ? atoi(argv[2]) : 0;  // 0 = both
   const std::string only_case = argc > 3 ? argv[3] : "";  // run just this big case (for ncu)
+  if (argc > 5) hb::gemm_set_l2_hints(atoi(argv[4]), atoi(argv[5]));  // L2 eviction hints of the A / W loads (0 normal, 1 first, 2 last)
+  if (argc > 6) hb::gemm_set_balanced_tiles(atoi(argv[6]));
   int dev = 0;
   CK(cudaSetDevice(dev));
   cudaDeviceProp prop;
@@ -169,7 +171,7 @@ int main(int argc, char** argv) {
     fails += (r != 0);
   }
   if (!quick) {
-    const int M = 257 * 512;  // 512 frames
+    const int M = 257 * (argc > 7 ? atoi(argv[7]) : 512);  // 512 frames by default
     Case big[] = {
         {"qkv_cg1", M, 4224, 1408, hb::EPI_BF16, 1, false, true},
         {"qkv_cg2", M, 4224, 1408, hb::EPI_BF16, 2, false, true},
