@@ -30,6 +30,7 @@ thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 int g_cg = 2;
 int g_attn_version = 2;
+int g_dyn_sched = 1; // ViT GEMMs take their tiles from an atomic counter (in sequence order) instead of a static round-robin
 int g_ln_fold = 1;   // fold the ViT block LayerNorms into the QKV / fc1 GEMM epilogues (no LayerNorm kernel)
 int g_num_sms = 148;
 bool g_inited = false;
@@ -216,8 +217,9 @@ struct LnFold {
 
 int run_gemm(const CUtensorMap& tmA, const Linear& L, long long M, void* out, int ldo, int epi, cudaStream_t s,
              const float* resid = nullptr, float qscale = 1.f, int qcols = 0, const float* rowadd = nullptr, int remap_in = 0,
-             int remap_out = 0, int remap_off = 0, const LnFold* lf = nullptr) {
+             int remap_out = 0, int remap_off = 0, const LnFold* lf = nullptr, int* sched = nullptr) {
   hb::GemmParams p;
+  p.sched = g_dyn_sched ? sched : nullptr;
   if (lf != nullptr) {
     p.stats_in = lf->stats_in; p.ln_eps = lf->eps; p.ln_dim = lf->dim; p.c1 = L.c1.as<float>();
     p.xb_out = lf->xb_out; p.ld_xb = lf->ld_xb; p.stats_out = lf->stats_out; p.ln_slots = lf->slots;
@@ -250,7 +252,7 @@ struct HbVit {
   F32Vec nw, nb;
   Linear head;
   Act col, h, hid, clsn, xb;
-  DevBuf x, qkv, cls_idx, stats1, stats2;
+  DevBuf x, qkv, cls_idx, stats1, stats2, sched;
   bool ln_fold = false;
   int tap_layer = -1;
   float* tap_dst = nullptr;
@@ -294,6 +296,11 @@ int hb_set_ln_fold(int on) {
 
 int hb_set_gemm_balanced_tiles(int on) {
   hb::gemm_set_balanced_tiles(on);
+  return HB_OK;
+}
+
+int hb_set_gemm_dynamic_schedule(int on) {
+  g_dyn_sched = on ? 1 : 0;
   return HB_OK;
 }
 
@@ -396,6 +403,8 @@ int hb_vit_create(const HbVitConfig* cfg, const HbVitWeights* w, int max_batch, 
   if ((r = m->x.alloc(static_cast<size_t>(rows) * D * 4))) return r;
   if ((r = m->qkv.alloc(static_cast<size_t>(rows) * 3 * D * 2))) return r;
   if ((r = m->cls_idx.alloc(static_cast<size_t>(max_batch) * 4))) return r;
+  if ((r = m->sched.alloc(2 * sizeof(int)))) return r;   // dynamic tile scheduler counters (re-zeroed by every GEMM that uses them)
+  HB_CUDA(cudaMemsetAsync(m->sched.p, 0, m->sched.bytes, s));
   {
     std::vector<int> idx(max_batch);
     for (int i = 0; i < max_batch; ++i) idx[i] = i * m->T;
@@ -433,6 +442,7 @@ static int vit_encode_chunk(HbVit* m, const float* frames, const uint8_t* frames
   if (m->tap_layer == 0 && m->tap_dst)
     HB_CUDA(cudaMemcpyAsync(m->tap_dst, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, s));
   const float qscale = 1.0f / sqrtf(88.0f);
+  int* sched = m->sched.as<int>();
   if (m->ln_fold) {
     // LayerNorm folded into the GEMMs: the residual stream travels as fp32 x + a bf16 copy xb + per-row (sum, sumsq)
     // partials, one slot per 128 columns, each written by exactly one warp (no atomics: bit-reproducible, batch-independent).
@@ -447,13 +457,13 @@ static int vit_encode_chunk(HbVit* m, const float* frames, const uint8_t* frames
     lp1.xb_out = m->xb.ptr(); lp1.ld_xb = D; lp1.stats_out = m->stats1.as<float>();   // fc2   -> statistics for the next LN1
     for (int i = 0; i < c.layers; ++i) {
       HbVit::Layer& L = *m->layers[i];
-      if ((r = run_gemm(m->xb.tm, L.qkv, M, qkv, 3 * D, hb::EPI_BF16_LN, s, nullptr, qscale, D, nullptr, 0, 0, 0, &lf1))) return r;
+      if ((r = run_gemm(m->xb.tm, L.qkv, M, qkv, 3 * D, hb::EPI_BF16_LN, s, nullptr, qscale, D, nullptr, 0, 0, 0, &lf1, sched))) return r;
       hb::AttnParams ap;
       ap.qkv = qkv; ap.out = m->h.ptr(); ap.B = B; ap.H = c.heads;
       HB_LAUNCH_P(CAT_VIT_ATTN, 4.0 * B * c.heads * 257.0 * 257.0 * 88.0, s, g_attn_version == 1 ? hb::vit_attn_launch(ap, s) : hb::vit_attn2_launch(ap, s));
-      if ((r = run_gemm(m->h.tm, L.proj, M, x, D, hb::EPI_F32_STATS, s, x, 1.f, 0, nullptr, 0, 0, 0, &lp2))) return r;
-      if ((r = run_gemm(m->xb.tm, L.fc1, M, m->hid.ptr(), F, hb::EPI_GELU_BF16_LN, s, nullptr, 1.f, 0, nullptr, 0, 0, 0, &lf2))) return r;
-      if ((r = run_gemm(m->hid.tm, L.fc2, M, x, D, hb::EPI_F32_STATS, s, x, 1.f, 0, nullptr, 0, 0, 0, &lp1))) return r;
+      if ((r = run_gemm(m->h.tm, L.proj, M, x, D, hb::EPI_F32_STATS, s, x, 1.f, 0, nullptr, 0, 0, 0, &lp2, sched))) return r;
+      if ((r = run_gemm(m->xb.tm, L.fc1, M, m->hid.ptr(), F, hb::EPI_GELU_BF16_LN, s, nullptr, 1.f, 0, nullptr, 0, 0, 0, &lf2, sched))) return r;
+      if ((r = run_gemm(m->hid.tm, L.fc2, M, x, D, hb::EPI_F32_STATS, s, x, 1.f, 0, nullptr, 0, 0, 0, &lp1, sched))) return r;
       if (m->tap_layer == i + 1 && m->tap_dst)
         HB_CUDA(cudaMemcpyAsync(m->tap_dst, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, s));
     }
@@ -464,15 +474,15 @@ static int vit_encode_chunk(HbVit* m, const float* frames, const uint8_t* frames
     ln.x = x; ln.ldx = D; ln.y = m->h.ptr(); ln.ldy = D; ln.w = L.n1w.ptr(); ln.b = L.n1b.ptr();
     ln.eps = c.ln_eps; ln.rows = static_cast<int>(M); ln.D = D;
     HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, true, s));
-    if ((r = run_gemm(m->h.tm, L.qkv, M, qkv, 3 * D, hb::EPI_BF16, s, nullptr, qscale, D))) return r;
+    if ((r = run_gemm(m->h.tm, L.qkv, M, qkv, 3 * D, hb::EPI_BF16, s, nullptr, qscale, D, nullptr, 0, 0, 0, nullptr, sched))) return r;
     hb::AttnParams ap;
     ap.qkv = qkv; ap.out = m->h.ptr(); ap.B = B; ap.H = c.heads;
     HB_LAUNCH_P(CAT_VIT_ATTN, 4.0 * B * c.heads * 257.0 * 257.0 * 88.0, s, g_attn_version == 1 ? hb::vit_attn_launch(ap, s) : hb::vit_attn2_launch(ap, s));
-    if ((r = run_gemm(m->h.tm, L.proj, M, x, D, hb::EPI_F32, s, x))) return r;
+    if ((r = run_gemm(m->h.tm, L.proj, M, x, D, hb::EPI_F32, s, x, 1.f, 0, nullptr, 0, 0, 0, nullptr, sched))) return r;
     ln.w = L.n2w.ptr(); ln.b = L.n2b.ptr();
     HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, true, s));
-    if ((r = run_gemm(m->h.tm, L.fc1, M, m->hid.ptr(), F, hb::EPI_GELU_BF16, s))) return r;
-    if ((r = run_gemm(m->hid.tm, L.fc2, M, x, D, hb::EPI_F32, s, x))) return r;
+    if ((r = run_gemm(m->h.tm, L.fc1, M, m->hid.ptr(), F, hb::EPI_GELU_BF16, s, nullptr, 1.f, 0, nullptr, 0, 0, 0, nullptr, sched))) return r;
+    if ((r = run_gemm(m->hid.tm, L.fc2, M, x, D, hb::EPI_F32, s, x, 1.f, 0, nullptr, 0, 0, 0, nullptr, sched))) return r;
     if (m->tap_layer == i + 1 && m->tap_dst)
       HB_CUDA(cudaMemcpyAsync(m->tap_dst, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, s));
   }

@@ -83,6 +83,43 @@ struct NTiling {
   }
 };
 
+// ---- tile hand-out ----------------------------------------------------------------------------------------------------
+// Static: worker w takes tiles w, w + W, w + 2W, ... (TileIter).  Dynamic (GemmParams::sched): tile 0..W-1 are taken the same
+// way, every later tile id comes from an atomic counter, fetched one tile ahead by the leader CTA's producer warp and sent
+// to both CTAs of the pair with st.async (value + mbarrier complete_tx in one operation) through a 4-slot ring.  Tiles are
+// then STARTED in sequence order whatever delays individual workers pick up, so the N-tile workers that share an M-block's
+// A operand through L2 always run within a few microseconds of each other (static schedules drift apart by up to a tile
+// over the ~80 rounds of a launch and fc2 read its 3.2 GB A operand through DRAM twice).
+constexpr int SCHED_RING = 4;
+
+struct TileFeed {   // consumer view of either schedule; every lane of the warp calls next()
+  bool dyn;
+  TileIter st;
+  uint64_t* full; uint64_t* empty; const int* tile;
+  int it, total, n_tiles;
+  bool arm, remote;
+  __device__ TileFeed(bool dyn_, int worker, int num_workers, int m_tiles, int n_tiles_, uint64_t* f, uint64_t* e, const int* t,
+                      bool arm_, bool remote_)
+      : dyn(dyn_), st(worker, num_workers, m_tiles, n_tiles_), full(f), empty(e), tile(t), it(0), total(m_tiles * n_tiles_),
+        n_tiles(n_tiles_), arm(arm_), remote(remote_) {}
+  __device__ bool next(int& m, int& n) {
+    if (!dyn) return st.next(m, n);
+    const int slot = it % SCHED_RING;
+    mbar_wait(&full[slot], static_cast<uint32_t>(it / SCHED_RING) & 1u);
+    const int t = __shfl_sync(0xffffffffu, *reinterpret_cast<const volatile int*>(tile + slot), 0);
+    __syncwarp();
+    if (elect_one()) {
+      if (arm) mbar_arrive_expect_tx(&full[slot], 4);          // arm the slot's next use (its current phase is complete)
+      if (remote) mbar_arrive_cluster(&empty[slot], 0); else mbar_arrive(&empty[slot]);
+    }
+    __syncwarp();
+    ++it;
+    if (t >= total) return false;
+    m = t / n_tiles; n = t - m * n_tiles;
+    return true;
+  }
+};
+
 // bf16-output epilogues (thread-per-row): r = 32 consecutive fp32 accumulator columns [col0, col0+32) of one row.
 template <int EPI>
 __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const uint32_t (&r)[32], long long row_out,
@@ -150,6 +187,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tmem_full_bar = bars + 2 * C::STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* sched_full = tmem_empty_bar + 3;       // [SCHED_RING]  dynamic tile scheduler (p.sched != nullptr)
+  uint64_t* sched_empty = sched_full + SCHED_RING; // [SCHED_RING]  (leader CTA's copy is the one that is used)
+  int* sched_tile = reinterpret_cast<int*>(sched_empty + SCHED_RING);  // [SCHED_RING]
   float* sbias = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256 + NUM_EPI_WARPS * C::EPI_STAGE_BYTES);  // [2][BN]
 
   // warp-uniform values are routed through shfl(…, 0) so the compiler KNOWS they are uniform: the producer / MMA loops then
@@ -182,7 +222,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], NUM_EPI_WARPS * CG);
     }
+    for (int i = 0; i < SCHED_RING; ++i) {
+      mbar_init(&sched_full[i], 1);
+      mbar_init(&sched_empty[i], (NUM_EPI_WARPS + 1) * CG);   // per CTA: 8 epilogue warps + (MMA warp | the peer's producer warp)
+    }
     fence_mbar_init();
+    for (int i = 0; i < SCHED_RING; ++i) mbar_arrive_expect_tx(&sched_full[i], 4);   // first use of every slot is armed here
   }
   if (warp == 2) tmem_alloc<CG>(tmem_slot, TMEM_COLS);
   tc_fence_before();
@@ -191,16 +236,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
 
+  const bool dyn = (p.sched != nullptr);
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loop, one elected lane issues) =====================
     int stage = 0;
     uint32_t phase = 0;
-    TileIter it(worker, num_workers, m_tiles, n_tiles);
-    int m_blk, n_blk;
     const uint64_t hint_a = p.a_hint == 1 ? kEvictFirst : (p.a_hint == 2 ? kEvictLast : kEvictNormal);
     const uint64_t hint_w = p.w_hint == 1 ? kEvictFirst : (p.w_hint == 2 ? kEvictLast : kEvictNormal);
     (void)hint_a; (void)hint_w;
-    while (it.next(m_blk, n_blk)) {
+    auto load_tile = [&](int m_blk, int n_blk) {
       const int n0 = nt.n0(n_blk);
       const int n_eff = nt.width(n_blk, p.N);
       const int row_a = m_blk * tile_m + static_cast<int>(cta_rank) * BM;
@@ -226,6 +270,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
+    };
+    if (dyn && leader) {
+      // ---- scheduler: this warp hands tile ids to every consumer warp of the pair, one tile ahead of its own loads ----
+      const int total = m_tiles * n_tiles;
+      auto publish = [&](int it, int t) {
+        const int slot = it % SCHED_RING;
+        if (it >= SCHED_RING) mbar_wait(&sched_empty[slot], static_cast<uint32_t>(it / SCHED_RING - 1) & 1u);
+        if (elect_one()) {
+#pragma unroll
+          for (uint32_t c = 0; c < static_cast<uint32_t>(CG); ++c)
+            st_async_u32(mapa_u32(smem_u32(sched_tile + slot), c), static_cast<uint32_t>(t), mapa_u32(smem_u32(&sched_full[slot]), c));
+        }
+        __syncwarp();
+      };
+      int it = 0;
+      int t = min(worker, total);
+      publish(0, t);
+      while (t < total) {
+        int v = 0;
+        if (lane == 0) v = num_workers + atomicAdd(p.sched, 1);
+        const int t_next = min(__shfl_sync(0xffffffffu, v, 0), total);   // `total` is the end marker
+        publish(it + 1, t_next);
+        const int m_blk = t / n_tiles;
+        load_tile(m_blk, t - m_blk * n_tiles);
+        t = t_next;
+        ++it;
+      }
+      if (lane == 0) {   // the last pair to finish re-zeroes the counters for the next launch on this stream
+        if (atomicAdd(p.sched + 1, 1) == num_workers - 1) { p.sched[0] = 0; p.sched[1] = 0; __threadfence(); }
+      }
+      __syncwarp();
+    } else {
+      TileFeed feed(dyn, worker, num_workers, m_tiles, n_tiles, sched_full, sched_empty, sched_tile, /*arm=*/true, /*remote=*/true);
+      int m_blk, n_blk;
+      while (feed.next(m_blk, n_blk)) load_tile(m_blk, n_blk);
     }
   } else if (warp == 1) {
    if (leader) {
@@ -234,7 +313,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    TileIter it(worker, num_workers, m_tiles, n_tiles);
+    TileFeed it(dyn, worker, num_workers, m_tiles, n_tiles, sched_full, sched_empty, sched_tile, /*arm=*/true, /*remote=*/false);
     int m_blk, n_blk;
     constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B (umma_desc_sw128)
     while (it.next(m_blk, n_blk)) {
@@ -272,7 +351,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = (warp - 4) >> 2;     // column half of the tile
     int acc = 0;
     uint32_t acc_phase = 0;
-    TileIter it(worker, num_workers, m_tiles, n_tiles);
+    TileFeed it(dyn, worker, num_workers, m_tiles, n_tiles, sched_full, sched_empty, sched_tile, /*arm=*/false, /*remote=*/!leader);
     int m_blk, n_blk;
     bool first_tile = true;
     while (it.next(m_blk, n_blk)) {
@@ -328,7 +407,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // Off by default (prefetch_max_k = 0): a tile lasts 15 us (proj) to 50 us (fc2), longer than a line survives in L2 under
         // this kernel's 3-5 TB/s of DRAM traffic, so the prefetched residual was evicted and read twice (DRAM reads per launch
         // fc2 12.1 -> 10.3 GB, proj 3.0 -> 2.25 GB = exactly A + residual); step time unchanged either way.
-        if (!ROWADD && p.resid != nullptr && p.K < p.prefetch_max_k) {
+        if (!ROWADD && p.resid != nullptr && p.K < p.prefetch_max_k && !dyn) {
           const int et = (warp - 4) * 32 + lane;  // 0..255: row et/2 of the tile, half et%2 of its column span
           auto prefetch_tile = [&](int pm, int pn) {
             const int pri = pm * tile_m + static_cast<int>(cta_rank) * BM + (et >> 1);
@@ -340,7 +419,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           };
           if (first_tile) prefetch_tile(m_blk, n_blk);
-          TileIter peek = it;
+          TileIter peek = it.st;
           int pm2, pn2;
           if (peek.next(pm2, pn2)) prefetch_tile(pm2, pn2);
         }
@@ -427,7 +506,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               a += __shfl_xor_sync(0xffffffffu, a, o);
               b += __shfl_xor_sync(0xffffffffu, b, o);
             }
-            if (cc == 0 && ((okmask >> i) & 1u) && c_begin < c_end) {
+            if (cc == 0 && ((okmask >> i) & 1u)) {   // an empty column half writes zeros: every slot is defined after every launch
               const long long rowi = row_base + 4 * i + rr_base;
               *reinterpret_cast<float2*>(p.stats_out + 2 * (rowi * p.ln_slots + slot)) = make_float2(a, b);
             }

@@ -47,6 +47,8 @@ struct GemmParams {
   int ln_slots = 1;               // partial-sum slots per row (producer writes slot 2 * n_tile + column half: >= 2 * ceil(N / 256))
   int prefetch_max_k = 0;         // EPI_F32*: the next tile's residual is L2-prefetched only when K < this (0 = never)
   int a_hint = 0, w_hint = 2;     // L2 eviction priority of the TMA operand loads: 0 normal, 1 evict-first, 2 evict-last
+  int* sched = nullptr;           // optional dynamic tile scheduler: 2 zero-initialised device ints owned by the caller (one
+                                  // pair per stream; the kernel re-zeroes them).  nullptr = static round-robin schedule.
   int balanced_n = 1;             // N tiling: equal-cost tiles (see NTiling in hb_gemm.cu) instead of 256-wide tiles + narrow tail
 };
 

@@ -58,6 +58,19 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `cta` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(cta));
+  return remote;
+}
+// 4-byte store into (possibly another CTA's) shared memory that completes 4 tx-bytes on an mbarrier of the destination CTA:
+// the value is visible to whoever observes that barrier phase complete (no separate fence / flag).
+__device__ __forceinline__ void st_async_u32(uint32_t cluster_addr, uint32_t value, uint32_t cluster_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr), "r"(value),
+               "r"(cluster_bar)
+               : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

@@ -55,6 +55,9 @@ HB_API int hb_set_ln_fold(int on);
 /* GEMM column tiling: 1 (default) = equal-cost N tiles (1408 = 2 x 256 + 4 x 224), 0 = 256-wide tiles + narrow tail.
  * Same results bit for bit; process-wide; exists for A/B measurements. */
 HB_API int hb_set_gemm_balanced_tiles(int on);
+/* ViT GEMM tile hand-out: 1 (default) = dynamic (atomic tile counter, tiles start in sequence order so the workers sharing an
+ * A block through L2 stay together), 0 = static round-robin.  Same results bit for bit; process-wide. */
+HB_API int hb_set_gemm_dynamic_schedule(int on);
 /* fp32-residual epilogues L2-prefetch the next tile's residual only when K < k (default 0 = never). */
 HB_API int hb_set_gemm_resid_prefetch_max_k(int k);
 

@@ -198,3 +198,31 @@ def test_layernorm_fold_matches_separate_layernorm(hb, golden_dir):
         print(f"{gname}: rel err folded {errs[1]:.3e}, separate LayerNorm {errs[0]:.3e}")
         assert errs[1] < (TOL_TINY_IMAGE if cfg is synthetic.EVA_TINY else TOL_G14_IMAGE)
         assert errs[1] <= errs[0] * 1.25 + 1e-4
+
+
+def test_schedule_and_tiling_knobs_do_not_change_results(hb):
+    """Dynamic vs static tile hand-out and balanced vs plain N tiles only change WHEN a tile runs and how N is cut, never the
+    arithmetic of an output element: encode_image must be bit-identical in all four combinations (EVA-CLIP-g/14 shapes,
+    64 frames so that every GEMM has more tiles than workers and the atomic scheduler actually hands tiles out)."""
+    cfg = dict(synthetic.EVA_G14)
+    cfg["vision_cfg"] = dict(cfg["vision_cfg"], layers=2)
+    sd = synthetic.make_eva_state_dict(cfg, seed=0)
+    model = eva_clip.EVA_CLIP(**cfg, max_image_batch=64, max_text_batch=8)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(DEV).eval()
+    frames = synthetic.make_frames(64, 224, seed=4).to(DEV)
+    outs = {}
+    try:
+        for dyn in (1, 0):
+            for bal in (1, 0):
+                _lib.check(hb.hb_set_gemm_dynamic_schedule(dyn))
+                _lib.check(hb.hb_set_gemm_balanced_tiles(bal))
+                outs[(dyn, bal)] = model.encode_image(frames).clone()
+                assert torch.equal(outs[(dyn, bal)], model.encode_image(frames)), "not reproducible run to run"
+    finally:
+        _lib.check(hb.hb_set_gemm_dynamic_schedule(1))
+        _lib.check(hb.hb_set_gemm_balanced_tiles(1))
+    ref = outs[(1, 1)]
+    assert torch.isfinite(ref).all()
+    for k, v in outs.items():
+        assert torch.equal(v, ref), k

@@ -22,6 +22,7 @@
   } while (0)
 
 static uint32_t g_seed = 12345u;
+static int* g_sched = nullptr;   // dynamic tile scheduler counters (argv[8] = 1)
 static float frand() {
   g_seed = g_seed * 1664525u + 1013904223u;
   return ((g_seed >> 8) & 0xFFFF) / 65536.0f - 0.5f;
@@ -68,6 +69,7 @@ static int run_case(const Case& c, int num_sms, bool verify, int iters) {
   hb::GemmParams p;
   p.M = M; p.N = N; p.K = K; p.bias = dbias; p.out = dout; p.ldo = N;
   p.resid = dres;
+  p.sched = g_sched;
   if (c.qscale) { p.qscale = 0.25f; p.qcols = N / 3; }
   r = hb::gemm_launch(tmA, tmW, p, c.epi, c.cg, num_sms, 0);
   if (r) { printf("%s: launch failed %d\n", c.name, r); return 1; }
@@ -142,6 +144,9 @@ int main(int argc, char** argv) {
   const std::string only_case = argc > 3 ? argv[3] : "";  // run just this big case (for ncu)
   if (argc > 5) hb::gemm_set_l2_hints(atoi(argv[4]), atoi(argv[5]));  // L2 eviction hints of the A / W loads (0 normal, 1 first, 2 last)
   if (argc > 6) hb::gemm_set_balanced_tiles(atoi(argv[6]));
+  if (argc > 8 && atoi(argv[8]) != 0) {
+    if (cudaMalloc(&g_sched, 8) != cudaSuccess || cudaMemset(g_sched, 0, 8) != cudaSuccess) { printf("sched alloc failed\n"); return 1; }
+  }
   int dev = 0;
   CK(cudaSetDevice(dev));
   cudaDeviceProp prop;
