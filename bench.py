@@ -30,10 +30,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = "frames/sec encoded+scored (EVA-CLIP-g/14 224px)"
 # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, mean over the four GEMMs of one ViT layer at 1024 frames
-# (QKV 2.95, proj 4.43, fc1 3.98, fc2 10.53 GB) from the `ncu --set full` capture in profiles/r01_one_layer_ncu_full.txt;
+# (QKV 2.95, proj 4.42, fc1 3.97, fc2 6.96 GB) from the `ncu --set full` capture in profiles/r01_one_layer_ncu_full.txt;
 # algorithmic bytes of the same four launches: 2.96 + 4.44 + 3.97 + 6.93 GB (fp32 residual in/out + bf16 copy counted for
-# proj / fc2; fc2 still re-reads part of its A operand through DRAM).
-GEMM_TRAFFIC_BYTES_PER_LAUNCH = 5.47e9
+# proj / fc2): every GEMM now moves its algorithmic bytes and nothing else.
+GEMM_TRAFFIC_BYTES_PER_LAUNCH = 4.57e9
 UNIT = "frames/s"
 
 
@@ -270,24 +270,34 @@ def main():
             copied = [torch.cuda.Event(), torch.cuda.Event()]
             consumed = [None, None]
 
+            copy_marks = []   # (start, end) events of every H2D copy, host enqueue / sync times: diagnostics only
+
             def issue_copy(i):
                 with torch.cuda.stream(copy_stream):
                     if consumed[i % 2] is not None:
                         copy_stream.wait_event(consumed[i % 2])
+                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    c0.record(copy_stream)
                     dev_bufs[i % 2].copy_(frames_host, non_blocking=True)
+                    c1.record(copy_stream)
+                    copy_marks.append((c0, c1))
                     copied[i % 2].record(copy_stream)
 
             step_events = []
+            host_ms = []
 
             def run_e2e(n):
                 for k in range(2):
                     consumed[k] = None
                 step_events.clear()
+                copy_marks.clear()
+                host_ms.clear()
                 issue_copy(0)
                 for i in range(n):
                     ev0 = torch.cuda.Event(enable_timing=True)
                     ev0.record()
                     step_events.append(ev0)
+                    th0 = time.perf_counter()
                     if i + 1 < n:
                         issue_copy(i + 1)
                     cur = torch.cuda.current_stream()
@@ -300,7 +310,9 @@ def main():
                     ev.record(cur)
                     consumed[i % 2] = ev
                     scores_host.copy_(sc, non_blocking=True)
+                    th1 = time.perf_counter()
                     cur.synchronize()  # the caller holds this step's scores on the host before the next step starts
+                    host_ms.append((round((th1 - th0) * 1e3, 1), round((time.perf_counter() - th0) * 1e3, 1)))
 
             # the clock sampler (an nvidia-smi child process) starts BEFORE the warm-up so that its start-up cost and the idle gap
             # it would open (the GPU drops out of its boost state and the first timed step pays for the ramp) stay outside the
@@ -328,7 +340,8 @@ def main():
             e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                    "h2d_bytes_per_step": frames_host.numel() * frames_host.element_size() + tokens_host.numel() * 8,
                    "h2d_ms_alone": h2d_ms, "clocks": clocks_e2e,
-                   "ms_steps": ms_steps_e2e,
+                   "ms_steps": ms_steps_e2e, "h2d_ms_steps": [round(a.elapsed_time(b), 1) for a, b in copy_marks],
+                   "host_enqueue_and_total_ms": list(host_ms),
                    "input": "uint8 frames [B,3,224,224] in pinned host memory, normalised on the GPU; H2D double-buffered on a side stream",
                    "d2h_bytes_per_step": scores_host.numel() * 4, "ms_per_step": ms_e2e / args.steps}
 

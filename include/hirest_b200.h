@@ -53,7 +53,8 @@ HB_API int hb_set_attention_version(int v);
  * separate LayerNorm kernels (0). */
 HB_API int hb_set_ln_fold(int on);
 /* GEMM column tiling: 1 (default) = equal-cost N tiles (1408 = 2 x 256 + 4 x 224), 0 = 256-wide tiles + narrow tail.
- * Same results bit for bit; process-wide; exists for A/B measurements. */
+ * Same arithmetic per output element; with the LayerNorm fold the per-row statistics are summed in a different grouping, so
+ * results differ by fp32 summation order (then bf16 rounding).  Process-wide; exists for A/B measurements. */
 HB_API int hb_set_gemm_balanced_tiles(int on);
 /* ViT GEMM tile hand-out: 1 (default) = dynamic (atomic tile counter, tiles start in sequence order so the workers sharing an
  * A block through L2 stay together), 0 = static round-robin.  Same results bit for bit; process-wide. */

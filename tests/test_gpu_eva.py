@@ -200,10 +200,11 @@ def test_layernorm_fold_matches_separate_layernorm(hb, golden_dir):
         assert errs[1] <= errs[0] * 1.25 + 1e-4
 
 
-def test_schedule_and_tiling_knobs_do_not_change_results(hb):
-    """Dynamic vs static tile hand-out and balanced vs plain N tiles only change WHEN a tile runs and how N is cut, never the
-    arithmetic of an output element: encode_image must be bit-identical in all four combinations (EVA-CLIP-g/14 shapes,
-    64 frames so that every GEMM has more tiles than workers and the atomic scheduler actually hands tiles out)."""
+def test_schedule_and_tiling_knobs(hb):
+    """Dynamic vs static tile hand-out only changes WHEN a tile runs: encode_image must be bit-identical.  Balanced vs plain
+    N tiles also regroups the per-row LayerNorm partial sums (one slot per tile half), i.e. the fp32 summation order of the
+    row statistics: results agree to bf16-rounding noise, each setting is reproducible run to run.  (EVA-CLIP-g/14 shapes,
+    2 layers, 64 frames so that every GEMM has more tiles than workers and the atomic scheduler really hands tiles out.)"""
     cfg = dict(synthetic.EVA_G14)
     cfg["vision_cfg"] = dict(cfg["vision_cfg"], layers=2)
     sd = synthetic.make_eva_state_dict(cfg, seed=0)
@@ -222,7 +223,6 @@ def test_schedule_and_tiling_knobs_do_not_change_results(hb):
     finally:
         _lib.check(hb.hb_set_gemm_dynamic_schedule(1))
         _lib.check(hb.hb_set_gemm_balanced_tiles(1))
-    ref = outs[(1, 1)]
-    assert torch.isfinite(ref).all()
-    for k, v in outs.items():
-        assert torch.equal(v, ref), k
+    assert torch.isfinite(outs[(1, 1)]).all()
+    assert torch.equal(outs[(1, 1)], outs[(0, 1)]) and torch.equal(outs[(1, 0)], outs[(0, 0)])
+    assert rel(outs[(1, 0)], outs[(1, 1)]) < 3e-3
