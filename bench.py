@@ -181,7 +181,19 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the first communicator is created; stdout carries exactly one JSON
+        # line (bench contract), so the banner is sent to stderr
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     lib = _lib.init(local_rank)
     if os.environ.get("HB_PLAIN_TILES") == "1":  # A/B switch for the GEMM column tiling (same results, see hb_set_gemm_balanced_tiles)
         _lib.check(lib.hb_set_gemm_balanced_tiles(0))

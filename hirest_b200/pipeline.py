@@ -151,15 +151,22 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
             s, e = step["absolute_bounds"]
             sf = timestamp_to_frame_index(s, video_duration=d, n_frames=n)
             ef = timestamp_to_frame_index(e, video_duration=d, n_frames=n)
-            it = _base_item(v, "step_captioning", n)
             mm = torch.zeros(n, dtype=torch.long)
             mm[sf:ef] = 1
             mm[ef] = 1
-            it["moment_mask"] = mm
+            # Step captioning only ever reads the frames inside the step (trim_feats, modeling.py:529-554, keeps the rows with
+            # moment_mask == 1, in order), so the item carries just those rows with an all-ones mask instead of the whole video
+            # padded to the longest one in the batch: same trimmed tensor, ~30x fewer bytes collated and copied to the GPU.
+            rows = mm.nonzero(as_tuple=True)[0]
+            it = _base_item(v, "step_captioning", n)
+            it["vis_feats"] = v["vis_feats"][rows]
+            it["asr_feats"] = v["asr_feats"][rows]
+            it["video_mask"] = torch.ones(rows.numel(), dtype=torch.long)
+            it["moment_mask"] = torch.ones(rows.numel(), dtype=torch.long)
             items.append(it)
     sc: Dict[str, dict] = {}
     for chunk in _batches(items, batch_size):
-        pred = model.test_step(collate(chunk, nmf), num_beams=num_beams)["prediction"]
+        pred = model.test_step(collate(chunk, -1), num_beams=num_beams)["prediction"]   # ragged (sliced) items: pad path
         for it, sent in zip(chunk, pred):
             e = sc.setdefault(it["fname"], {"captions": []})
             e["captions"].append({"sentence": sent})
