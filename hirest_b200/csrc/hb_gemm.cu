@@ -120,12 +120,12 @@ struct TileFeed {   // consumer view of either schedule; every lane of the warp 
   }
 };
 
-// bf16-output epilogues (thread-per-row): r = 32 consecutive fp32 accumulator columns [col0, col0+32) of one row.
+// bf16-output epilogues: r = 32 consecutive fp32 accumulator columns [col0, col0+32) of this thread's row -> four 16-byte
+// granules of packed bf16 (bias / LayerNorm fold / GELU / q-scale applied).
 template <int EPI>
-__device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const uint32_t (&r)[32], long long row_out,
-                                                     int row_in, int col0, int n_valid, const float* sb /*smem bias of this chunk*/,
-                                                     const float* sc1, float ln_a, float ln_b) {
-  (void)row_in;
+__device__ __forceinline__ void epilogue_pack_chunk(const GemmParams& p, const uint32_t (&r)[32], int col0,
+                                                    const float* sb /*smem bias of this chunk*/, const float* sc1, float ln_a,
+                                                    float ln_b, uint4 (&q)[4]) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -159,17 +159,12 @@ __device__ __forceinline__ void epilogue_store_chunk(const GemmParams& p, const 
       for (int j = 0; j < 32; ++j) v[j] = (col0 + j < p.qcols) ? v[j] * p.qscale : v[j];
     }
   }
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row_out * p.ldo + col0;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    if (g * 8 < n_valid) {
-      uint4 q;
-      q.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
-      q.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-      q.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
-      q.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
-      __stcs(reinterpret_cast<uint4*>(o + 8 * g), q);  // written once, far larger than L2: do not displace the weights
-    }
+    q[g].x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
+    q[g].y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+    q[g].z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+    q[g].w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
   }
 }
 
@@ -529,12 +524,50 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
+        // 64 columns (= 128 bytes of bf16 per row) at a time go through this warp's 4 KiB staging buffer (32 rows x 128 B,
+        // 16-byte granules XOR-swizzled by row) so that every global store instruction writes four full 128-byte lines.
+        // Thread-per-row 16-byte stores touched 32 lines per instruction and left every L2 sector half filled (ncu: 16 of
+        // 32 bytes per written sector, 139 M write requests per QKV launch).
+        (void)row_ok;
+        const uint32_t stage = smem_u32(smem + C::STAGES * C::STAGE_BYTES + 256) + static_cast<uint32_t>(warp - 4) * C::EPI_STAGE_BYTES;
+        const int row_base = m_blk * tile_m + static_cast<int>(cta_rank) * BM + q * 32;
+        const int rr_base = lane >> 3, gg = lane & 7;
 #pragma unroll 1
-        for (int c = c_begin; c < c_end; c += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + c), r);
-          tmem_ld_wait();
-          if (row_ok) epilogue_store_chunk<EPI>(p, r, row_out, row_in, n0 + c, n_eff - c, sb_tile + c, sc1_tile + c, ln_a, ln_b);
+        for (int c = c_begin; c < c_end; c += 64) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int cc0 = c + 32 * h;
+            if (cc0 < c_end) {
+              uint32_t r[32];
+              tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + cc0), r);
+              tmem_ld_wait();
+              uint4 pk[4];
+              epilogue_pack_chunk<EPI>(p, r, n0 + cc0, sb_tile + cc0, sc1_tile + cc0, ln_a, ln_b, pk);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + static_cast<uint32_t>(lane) * 128u +
+                                                                             (static_cast<uint32_t>((4 * h + g) ^ (lane & 7)) << 4)),
+                             "r"(pk[g].x), "r"(pk[g].y), "r"(pk[g].z), "r"(pk[g].w) : "memory");
+              }
+            }
+          }
+          __syncwarp();
+          const int col = c + gg * 8;                 // tile-relative first column of this lane's granule
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + rr_base;
+            const int ri = row_base + rr;
+            if (ri < p.M && col < c_end) {
+              uint4 v;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                           : "r"(stage + static_cast<uint32_t>(rr) * 128u + (static_cast<uint32_t>(gg ^ (rr & 7)) << 4)));
+              long long ro = ri;
+              if (p.remap_in > 0) ro = static_cast<long long>(ri / p.remap_in) * p.remap_out + (ri % p.remap_in) + p.remap_off;
+              // written once, far larger than L2: streaming store, do not displace the weights
+              __stcs(reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + ro * p.ldo + n0 + col), v);
+            }
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();
