@@ -200,8 +200,8 @@ def main():
 
     if os.environ.get("HB_STATIC_SCHED") == "1":
         _lib.check(lib.hb_set_gemm_dynamic_schedule(0))
-    if os.environ.get("HB_PREFETCH_MAX_K"):
-        _lib.check(lib.hb_set_gemm_resid_prefetch_max_k(int(os.environ["HB_PREFETCH_MAX_K"])))
+    if os.environ.get("HB_PREFETCH_CHUNKS"):
+        _lib.check(lib.hb_set_gemm_resid_prefetch_chunks(int(os.environ["HB_PREFETCH_CHUNKS"])))
 
     sd = synthetic.make_eva_state_dict(cfg, seed=0, device=dev)
     model = eva_clip.EVA_CLIP(**cfg, max_image_batch=args.frames, max_text_batch=max(args.queries, 8))

@@ -90,7 +90,7 @@ SIGNATURES = {
     "hb_set_attention_version": (C.c_int, [C.c_int]),
     "hb_set_ln_fold": (C.c_int, [C.c_int]),
     "hb_set_gemm_balanced_tiles": (C.c_int, [C.c_int]),
-    "hb_set_gemm_resid_prefetch_max_k": (C.c_int, [C.c_int]),
+    "hb_set_gemm_resid_prefetch_chunks": (C.c_int, [C.c_int]),
     "hb_set_gemm_dynamic_schedule": (C.c_int, [C.c_int]),
     "hb_profile_start": (C.c_int, []),
     "hb_profile_stop": (C.c_int, [C.POINTER(HbProfileSummary)]),

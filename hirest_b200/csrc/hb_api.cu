@@ -304,8 +304,8 @@ int hb_set_gemm_dynamic_schedule(int on) {
   return HB_OK;
 }
 
-int hb_set_gemm_resid_prefetch_max_k(int k) {
-  hb::gemm_set_resid_prefetch_max_k(k);
+int hb_set_gemm_resid_prefetch_chunks(int k) {
+  hb::gemm_set_resid_prefetch_chunks(k);
   return HB_OK;
 }
 

@@ -348,7 +348,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t acc_phase = 0;
     TileFeed it(dyn, worker, num_workers, m_tiles, n_tiles, sched_full, sched_empty, sched_tile, /*arm=*/false, /*remote=*/!leader);
     int m_blk, n_blk;
-    bool first_tile = true;
     while (it.next(m_blk, n_blk)) {
       const int n0 = nt.n0(n_blk);
       const int n_eff = nt.width(n_blk, p.N);
@@ -397,27 +396,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         };
         constexpr bool ROWADD = (EPI == EPI_F32_ROWADD);
         const bool has_add = ROWADD ? (p.rowadd != nullptr) : (p.resid != nullptr);
-        // DRAM latency under load (~2-3k cycles) is far longer than one chunk of epilogue work, so the residual of the
-        // NEXT tile is pulled into L2 a whole tile ahead; the register prefetch below then only has to cover L2 latency.
-        // Off by default (prefetch_max_k = 0): a tile lasts 15 us (proj) to 50 us (fc2), longer than a line survives in L2 under
-        // this kernel's 3-5 TB/s of DRAM traffic, so the prefetched residual was evicted and read twice (DRAM reads per launch
-        // fc2 12.1 -> 10.3 GB, proj 3.0 -> 2.25 GB = exactly A + residual); step time unchanged either way.
-        if (!ROWADD && p.resid != nullptr && p.K < p.prefetch_max_k && !dyn) {
-          const int et = (warp - 4) * 32 + lane;  // 0..255: row et/2 of the tile, half et%2 of its column span
-          auto prefetch_tile = [&](int pm, int pn) {
-            const int pri = pm * tile_m + static_cast<int>(cta_rank) * BM + (et >> 1);
-            const int pn0 = nt.n0(pn), pne = nt.width(pn, p.N);
-            if (pri < p.M) {
-              const float* base = p.resid + static_cast<long long>(pri) * p.ldo + pn0;
-              for (int cidx = (et & 1) * 128; cidx < min(pne, (et & 1) * 128 + 128); cidx += 32)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + cidx));
-            }
-          };
-          if (first_tile) prefetch_tile(m_blk, n_blk);
-          TileIter peek = it.st;
-          int pm2, pn2;
-          if (peek.next(pm2, pn2)) prefetch_tile(pm2, pn2);
-        }
+        // Optional (prefetch_chunks > 0, default off): each lane pulls its row's 128-byte residual line of the chunk
+        // `prefetch_chunks` ahead into L2, so the one-chunk-ahead register prefetch only has to cover L2 latency.  Measured:
+        // proj 1.062 -> 1.034 ms alone, nothing inside the power-capped step, fc2 +0.4 GB of DRAM reads (some lines are
+        // evicted before use).  The earlier variant prefetched the NEXT TILE's residual, 15-50 us ahead — longer than a line
+        // survives in L2 under this kernel's 3-5 TB/s of DRAM traffic: evicted and read twice (proj 3.0 vs 2.25 GB).
+        const int pf_row = row_base + lane;
+        auto l2_prefetch = [&](int c) {   // tile-relative first column of the chunk
+          if (!ROWADD && p.resid != nullptr && p.prefetch_chunks > 0 && c < c_end && pf_row < p.M)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.resid + static_cast<long long>(pf_row) * p.ldo + n0 + c));
+        };
         auto load_add = [&](int col0, int n_valid, float4 (&res)[8]) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -476,15 +464,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
         for (int i = 0; i < 8; ++i) res_a[i] = res_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (has_add && c_begin < c_end) load_add(n0 + c_begin, n_eff - c_begin, res_a);
+        for (int k = 1; k <= p.prefetch_chunks; ++k) l2_prefetch(c_begin + 32 * k);
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
 #pragma unroll 1
         for (int c = c_begin; c < c_end; c += 64) {
           const bool second = (c + 32 < c_end);
           if (has_add && second) load_add(n0 + c + 32, n_eff - c - 32, res_b);
+          l2_prefetch(c + 32 * (p.prefetch_chunks + 1));
           do_chunk(c, res_a);
           if (second) {
             if (has_add && c + 64 < c_end) load_add(n0 + c + 64, n_eff - c - 64, res_a);
+            l2_prefetch(c + 32 * (p.prefetch_chunks + 2));
             do_chunk(c + 32, res_b);
           }
         }
@@ -578,7 +569,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
-      first_tile = false;
     }
   }
 
@@ -676,16 +666,16 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, const uint64_t dims[3],
   return r == CUDA_SUCCESS ? 0 : -(1000 + static_cast<int>(r));
 }
 
-namespace { int g_balanced_n = 1; int g_prefetch_max_k = 0; int g_a_hint = -1; int g_w_hint = -1; }
+namespace { int g_balanced_n = 1; int g_prefetch_chunks = 0; int g_a_hint = -1; int g_w_hint = -1; }
 void gemm_set_l2_hints(int a_hint, int w_hint) { g_a_hint = a_hint; g_w_hint = w_hint; }
 void gemm_set_balanced_tiles(int on) { g_balanced_n = on ? 1 : 0; }
-void gemm_set_resid_prefetch_max_k(int k) { g_prefetch_max_k = k; }
+void gemm_set_resid_prefetch_chunks(int k) { g_prefetch_chunks = k < 0 ? 0 : (k > 3 ? 3 : k); }
 
 int gemm_launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams& p_in, int epi, int cg, int num_sms,
                 cudaStream_t stream) {
   GemmParams p = p_in;
   p.balanced_n = g_balanced_n;
-  p.prefetch_max_k = g_prefetch_max_k;
+  p.prefetch_chunks = g_prefetch_chunks;
   if (g_a_hint >= 0) p.a_hint = g_a_hint;
   if (g_w_hint >= 0) p.w_hint = g_w_hint;
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return -3;

@@ -45,7 +45,7 @@ struct GemmParams {
   float ln_eps = 1e-6f;
   int ln_dim = 0;                 // number of features the statistics were taken over
   int ln_slots = 1;               // partial-sum slots per row (producer writes slot 2 * n_tile + column half: >= 2 * ceil(N / 256))
-  int prefetch_max_k = 0;         // EPI_F32*: the next tile's residual is L2-prefetched only when K < this (0 = never)
+  int prefetch_chunks = 0;        // EPI_F32*: residual lines are L2-prefetched this many 32-column chunks ahead (0 = off)
   int a_hint = 0, w_hint = 2;     // L2 eviction priority of the TMA operand loads: 0 normal, 1 evict-first, 2 evict-last
   int* sched = nullptr;           // optional dynamic tile scheduler: 2 zero-initialised device ints owned by the caller (one
                                   // pair per stream; the kernel re-zeroes them).  nullptr = static round-robin schedule.
@@ -70,7 +70,7 @@ constexpr uint32_t gemm_a_box_rows() { return 128u; }
 
 // Process-wide switch between balanced N tiles (default) and 256-wide tiles + narrow tail (A/B measurements).
 void gemm_set_balanced_tiles(int on);
-void gemm_set_resid_prefetch_max_k(int k);
+void gemm_set_resid_prefetch_chunks(int k);
 void gemm_set_l2_hints(int a_hint, int w_hint);   // -1 keeps the default (A normal, W evict-last)
 
 // Launch. tmA must have box_rows = 128, tmW box_rows = gemm_w_box_rows(cg). cg in {1,2}.

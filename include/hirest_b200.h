@@ -59,8 +59,9 @@ HB_API int hb_set_gemm_balanced_tiles(int on);
 /* ViT GEMM tile hand-out: 1 (default) = dynamic (atomic tile counter, tiles start in sequence order so the workers sharing an
  * A block through L2 stay together), 0 = static round-robin.  Same results bit for bit; process-wide. */
 HB_API int hb_set_gemm_dynamic_schedule(int on);
-/* fp32-residual epilogues L2-prefetch the next tile's residual only when K < k (default 0 = never). */
-HB_API int hb_set_gemm_resid_prefetch_max_k(int k);
+/* fp32-residual epilogues (proj, fc2) pull their residual lines into L2 k chunks of 32 columns ahead of use
+ * (default 0 = off, max 3; measured: no gain inside the power-capped step). */
+HB_API int hb_set_gemm_resid_prefetch_chunks(int k);
 
 /* Per-launch timing for bench.py's roofline: while enabled every kernel launch of this library is bracketed
  * by CUDA events on its own stream.  hb_profile_stop synchronises the device and sums per category:
