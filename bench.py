@@ -198,6 +198,8 @@ def main():
     if os.environ.get("HB_PLAIN_TILES") == "1":  # A/B switch for the GEMM column tiling (same results, see hb_set_gemm_balanced_tiles)
         _lib.check(lib.hb_set_gemm_balanced_tiles(0))
 
+    if os.environ.get("HB_ATTN_PREFETCH") == "0":
+        _lib.check(lib.hb_set_attention_prefetch(0))
     if os.environ.get("HB_STATIC_SCHED") == "1":
         _lib.check(lib.hb_set_gemm_dynamic_schedule(0))
     if os.environ.get("HB_PREFETCH_CHUNKS"):

@@ -88,6 +88,7 @@ SIGNATURES = {
     "hb_launch_count": (C.c_int64, []),
     "hb_set_gemm_cta_group": (C.c_int, [C.c_int]),
     "hb_set_attention_version": (C.c_int, [C.c_int]),
+    "hb_set_attention_prefetch": (C.c_int, [C.c_int]),
     "hb_set_ln_fold": (C.c_int, [C.c_int]),
     "hb_set_gemm_balanced_tiles": (C.c_int, [C.c_int]),
     "hb_set_gemm_resid_prefetch_chunks": (C.c_int, [C.c_int]),

@@ -30,6 +30,7 @@ thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 int g_cg = 2;
 int g_attn_version = 2;
+int g_attn_prefetch = 0;   // attention v2: L2-prefetch the operands of the CTA one wave ahead (measured: 1.05 -> 1.14 ms, off)
 int g_dyn_sched = 1; // ViT GEMMs take their tiles from an atomic counter (in sequence order) instead of a static round-robin
 int g_ln_fold = 1;   // fold the ViT block LayerNorms into the QKV / fc1 GEMM epilogues (no LayerNorm kernel)
 int g_num_sms = 148;
@@ -315,6 +316,11 @@ int hb_set_attention_version(int v) {
   return HB_OK;
 }
 
+int hb_set_attention_prefetch(int on) {
+  g_attn_prefetch = on ? 1 : 0;
+  return HB_OK;
+}
+
 int hb_set_gemm_cta_group(int cg) {
   if (cg != 1 && cg != 2) return fail(HB_ERR_INVALID, "cta group must be 1 or 2");
   g_cg = cg;
@@ -459,7 +465,7 @@ static int vit_encode_chunk(HbVit* m, const float* frames, const uint8_t* frames
       HbVit::Layer& L = *m->layers[i];
       if ((r = run_gemm(m->xb.tm, L.qkv, M, qkv, 3 * D, hb::EPI_BF16_LN, s, nullptr, qscale, D, nullptr, 0, 0, 0, &lf1, sched))) return r;
       hb::AttnParams ap;
-      ap.qkv = qkv; ap.out = m->h.ptr(); ap.B = B; ap.H = c.heads;
+      ap.qkv = qkv; ap.out = m->h.ptr(); ap.B = B; ap.H = c.heads; ap.prefetch_ahead = g_attn_prefetch ? 2 * g_num_sms : 0;
       HB_LAUNCH_P(CAT_VIT_ATTN, 4.0 * B * c.heads * 257.0 * 257.0 * 88.0, s, g_attn_version == 1 ? hb::vit_attn_launch(ap, s) : hb::vit_attn2_launch(ap, s));
       if ((r = run_gemm(m->h.tm, L.proj, M, x, D, hb::EPI_F32_STATS, s, x, 1.f, 0, nullptr, 0, 0, 0, &lp2, sched))) return r;
       if ((r = run_gemm(m->xb.tm, L.fc1, M, m->hid.ptr(), F, hb::EPI_GELU_BF16_LN, s, nullptr, 1.f, 0, nullptr, 0, 0, 0, &lf2, sched))) return r;
@@ -476,7 +482,7 @@ static int vit_encode_chunk(HbVit* m, const float* frames, const uint8_t* frames
     HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, true, s));
     if ((r = run_gemm(m->h.tm, L.qkv, M, qkv, 3 * D, hb::EPI_BF16, s, nullptr, qscale, D, nullptr, 0, 0, 0, nullptr, sched))) return r;
     hb::AttnParams ap;
-    ap.qkv = qkv; ap.out = m->h.ptr(); ap.B = B; ap.H = c.heads;
+    ap.qkv = qkv; ap.out = m->h.ptr(); ap.B = B; ap.H = c.heads; ap.prefetch_ahead = g_attn_prefetch ? 2 * g_num_sms : 0;
     HB_LAUNCH_P(CAT_VIT_ATTN, 4.0 * B * c.heads * 257.0 * 257.0 * 88.0, s, g_attn_version == 1 ? hb::vit_attn_launch(ap, s) : hb::vit_attn2_launch(ap, s));
     if ((r = run_gemm(m->h.tm, L.proj, M, x, D, hb::EPI_F32, s, x, 1.f, 0, nullptr, 0, 0, 0, nullptr, sched))) return r;
     ln.w = L.n2w.ptr(); ln.b = L.n2b.ptr();

@@ -144,6 +144,12 @@ __device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
                : "memory");
 }
+// Prefetch one 3D box of a tensor map into L2.
+__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1),
+               "r"(c2)
+               : "memory");
+}
 // 3D tiled load, CTA-local destination + barrier.
 __device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
