@@ -86,16 +86,27 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self) -> int:
+        """Index of the next sample: brackets a timed region without restarting nvidia-smi (its start-up takes NVML / driver
+        locks for up to a second, which stalls a host-synchronised loop that happens to run at the same time)."""
+        return len(self.lines)
+
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        self.proc = None
+        self.stopped = True
+
+    def summary(self, i0: int = 0, i1: int = None):
+        if self.proc is None and not getattr(self, "stopped", False):
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm, mx, pw, reasons = [], [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[i0:i1]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -240,12 +251,15 @@ def main():
         return float(t.item())
 
     with torch.no_grad():
-        for _ in range(args.warmup):
-            step_device()
-        barrier()
+        # ONE nvidia-smi sampler for the whole run, started before the warm-up: its start-up (NVML / driver locks, up to ~1 s)
+        # must not coincide with a timed region — it stalled the first step of the host-synchronised e2e loop by ~0.5 s.
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
+        for _ in range(args.warmup):
+            step_device()
+        barrier()
+        mark0 = sampler.mark()
         launches0 = lib.hb_launch_count()
         lib.hb_profile_start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -264,21 +278,27 @@ def main():
         prof = _lib.HbProfileSummary()
         _lib.check(lib.hb_profile_stop(prof), "hb_profile_stop")
         launches = lib.hb_launch_count() - launches0
-        clocks = sampler.stop() if rank == 0 else None
+        clocks = sampler.summary(mark0, sampler.mark()) if rank == 0 else None
         value = world * B * args.steps / (ms_total * 1e-3)
 
         # ---------------- e2e through the public API with host buffers
         e2e = None
+        if args.no_e2e:
+            sampler.stop()
         if not args.no_e2e:
             # raw uint8 frames in pinned host memory: ToTensor + Normalize run on the GPU inside the patch gather
             # (encode_image accepts uint8), so a step moves 154 MB over PCIe instead of 617 MB of fp32 frames
             gen = torch.Generator().manual_seed(200 + rank)
             frames_host = torch.randint(0, 256, (B, 3, S, S), generator=gen, dtype=torch.uint8).pin_memory()
             tokens_host = tokens_step.cpu().pin_memory()
-            scores_host = torch.empty((Q, world * (B // Fv)), dtype=torch.float32).pin_memory()
+            scores_host = [torch.empty((Q, world * (B // Fv)), dtype=torch.float32).pin_memory() for _ in range(2)]
 
             # Streaming pipeline a user would write: the H2D copy of step i+1 (pinned host -> device, side stream) overlaps
-            # the compute of step i; every step's copy and its D2H result read are inside the timed region.
+            # the compute of step i, and the host picks up the scores of step i-1 (pinned, double-buffered) after it has
+            # enqueued step i, so the GPU always has the next step queued.  Every step's H2D copy and D2H result read are
+            # inside the timed region.  (Synchronising the stream after EVERY step leaves the GPU idle for the few ms the host
+            # needs to enqueue the next one; on some boxes it then takes ~0.4 s to get back to speed — isolated 900-1100 ms
+            # steps at < 800 W with unchanged SM clocks, which is what `e2e.ms_steps` is recorded for.)
             copy_stream = torch.cuda.Stream(device=dev)
             dev_bufs = [torch.empty((B, 3, S, S), dtype=torch.uint8, device=dev) for _ in range(2)]
             copied = [torch.cuda.Event(), torch.cuda.Event()]
@@ -299,6 +319,7 @@ def main():
 
             step_events = []
             host_ms = []
+            done = [None, None]
 
             def run_e2e(n):
                 for k in range(2):
@@ -323,26 +344,30 @@ def main():
                     ev = torch.cuda.Event()
                     ev.record(cur)
                     consumed[i % 2] = ev
-                    scores_host.copy_(sc, non_blocking=True)
+                    scores_host[i % 2].copy_(sc, non_blocking=True)
+                    done[i % 2] = torch.cuda.Event()
+                    done[i % 2].record(cur)
                     th1 = time.perf_counter()
-                    cur.synchronize()  # the caller holds this step's scores on the host before the next step starts
+                    if i > 0:
+                        done[(i - 1) % 2].synchronize()   # the caller now holds the scores of step i-1 on the host
                     host_ms.append((round((th1 - th0) * 1e3, 1), round((time.perf_counter() - th0) * 1e3, 1)))
+                evl = torch.cuda.Event(enable_timing=True)
+                evl.record()
+                step_events.append(evl)
+                done[(n - 1) % 2].synchronize()
 
-            # the clock sampler (an nvidia-smi child process) starts BEFORE the warm-up so that its start-up cost and the idle gap
-            # it would open (the GPU drops out of its boost state and the first timed step pays for the ramp) stay outside the
-            # timed region; the warm-up runs straight into the timed steps
-            sampler2 = ClockSampler(local_rank)
-            if rank == 0:
-                sampler2.start()
             run_e2e(max(2, min(args.warmup, 3)))
             barrier()
-            sampler2.lines.clear()
+            mark2 = sampler.mark()
             e0.record()
             run_e2e(args.steps)
-            e1.record()
             barrier()
-            clocks_e2e = sampler2.stop() if rank == 0 else None
-            ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+            clocks_e2e = sampler.summary(mark2, sampler.mark()) if rank == 0 else None
+            sampler.stop()
+            # e0 -> the event recorded on the stream right after the last step's D2H copy (stream order: the last scores are
+            # on the host when it fires).  Taking the end stamp on the device keeps a descheduled host thread (observed: 0.3-1 s
+            # inside cudaEventSynchronize on busy boxes, GPU already idle) out of a device-side throughput number.
+            ms_e2e = max_over_ranks(e0.elapsed_time(step_events[-1]))
             ms_steps_e2e = [round(step_events[i].elapsed_time(step_events[i + 1]), 1) for i in range(len(step_events) - 1)]
             # diagnostic: the bare pinned-host -> device copy of one step's frames, nothing else running
             h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -357,7 +382,7 @@ def main():
                    "ms_steps": ms_steps_e2e, "h2d_ms_steps": [round(a.elapsed_time(b), 1) for a, b in copy_marks],
                    "host_enqueue_and_total_ms": list(host_ms),
                    "input": "uint8 frames [B,3,224,224] in pinned host memory, normalised on the GPU; H2D double-buffered on a side stream",
-                   "d2h_bytes_per_step": scores_host.numel() * 4, "ms_per_step": ms_e2e / args.steps}
+                   "d2h_bytes_per_step": scores_host[0].numel() * 4, "ms_per_step": ms_e2e / args.steps}
 
     if rank != 0:
         if world > 1:
