@@ -93,6 +93,7 @@ SIGNATURES = {
     "hb_set_gemm_balanced_tiles": (C.c_int, [C.c_int]),
     "hb_set_gemm_resid_prefetch_chunks": (C.c_int, [C.c_int]),
     "hb_set_gemm_dynamic_schedule": (C.c_int, [C.c_int]),
+    "hb_gemm_n_tiling": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "hb_profile_start": (C.c_int, []),
     "hb_profile_stop": (C.c_int, [C.POINTER(HbProfileSummary)]),
     "hb_vit_create": (C.c_int, [C.POINTER(HbVitConfig), C.POINTER(HbVitWeights), C.c_int, C.c_void_p,

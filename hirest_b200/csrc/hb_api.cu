@@ -300,6 +300,12 @@ int hb_set_gemm_balanced_tiles(int on) {
   return HB_OK;
 }
 
+int hb_gemm_n_tiling(int N, int cta_group, int balanced, int* n0, int* width, int cap) {
+  const int r = hb::gemm_n_tiling(N, cta_group, balanced, n0, width, cap);
+  if (r < 0) return fail(HB_ERR_INVALID, "need N > 0 and cta_group 1 or 2");
+  return r;
+}
+
 int hb_set_gemm_dynamic_schedule(int on) {
   g_dyn_sched = on ? 1 : 0;
   return HB_OK;

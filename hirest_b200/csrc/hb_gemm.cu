@@ -3,8 +3,10 @@
 //   out[M,N] = epilogue( A[M,K] x W[N,K]^T ),  A and W bf16 with K contiguous, fp32 accumulate in TMEM.
 //
 // Structure (one CTA per SM, or one CTA pair per TPC when CG == 2):
-//   warp 0      : TMA producer   (cp.async.bulk.tensor -> SWIZZLE_128B smem ring, mbarrier complete_tx)
-//   warp 1      : MMA issuer     (one thread, tcgen05.mma kind::f16, 128xN (CG=1) or 256xN (CG=2) tiles)
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> SWIZZLE_128B smem ring, mbarrier complete_tx); in the leader CTA
+//                 also the dynamic tile scheduler (atomic tile counter -> st.async ring to both CTAs of the pair)
+//   warp 1      : MMA issuer     (whole warp walks the loop, one elected lane issues tcgen05.mma kind::f16,
+//                 128xN (CG=1) or 256xN (CG=2) tiles)
 //   warp 2      : TMEM allocator (512 columns = two 256-column accumulator buffers)
 //   warps 4..11 : epilogue       (tcgen05.ld -> bias / GELU / residual -> vectorised st.global)
 // The accumulator is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
@@ -664,6 +666,15 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, const uint64_t dims[3],
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -(1000 + static_cast<int>(r));
+}
+
+int gemm_n_tiling(int N, int cg, int balanced, int* n0_out, int* width_out, int cap) {
+  if (N <= 0 || (cg != 1 && cg != 2)) return -1;
+  const NTiling nt(N, cg, balanced);
+  if (n0_out && width_out) {
+    for (int n = 0; n < nt.n_tiles && n < cap; ++n) { n0_out[n] = nt.n0(n); width_out[n] = nt.width(n, N); }
+  }
+  return nt.n_tiles;
 }
 
 namespace { int g_balanced_n = 1; int g_prefetch_chunks = 0; int g_a_hint = -1; int g_w_hint = -1; }

@@ -68,6 +68,9 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, const uint64_t dims[3],
 constexpr uint32_t gemm_w_box_rows(int cg) { return 256u / static_cast<uint32_t>(cg); }
 constexpr uint32_t gemm_a_box_rows() { return 128u; }
 
+// Host-side view of the column tiling the kernel uses (for tests): fills n0 / width of up to `cap` tiles, returns the tile count.
+int gemm_n_tiling(int N, int cg, int balanced, int* n0_out, int* width_out, int cap);
+
 // Process-wide switch between balanced N tiles (default) and 256-wide tiles + narrow tail (A/B measurements).
 void gemm_set_balanced_tiles(int on);
 void gemm_set_resid_prefetch_chunks(int k);

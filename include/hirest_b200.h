@@ -59,6 +59,9 @@ HB_API int hb_set_ln_fold(int on);
  * Same arithmetic per output element; with the LayerNorm fold the per-row statistics are summed in a different grouping, so
  * results differ by fp32 summation order (then bf16 rounding).  Process-wide; exists for A/B measurements. */
 HB_API int hb_set_gemm_balanced_tiles(int on);
+/* Host-only: the column tiling the GEMM kernel uses for an N-wide output (first column and width of up to `cap` tiles);
+ * returns the number of tiles or < 0.  For verification. */
+HB_API int hb_gemm_n_tiling(int N, int cta_group, int balanced, int* n0, int* width, int cap);
 /* ViT GEMM tile hand-out: 1 (default) = dynamic (atomic tile counter, tiles start in sequence order so the workers sharing an
  * A block through L2 stay together), 0 = static round-robin.  Same results bit for bit; process-wide. */
 HB_API int hb_set_gemm_dynamic_schedule(int on);

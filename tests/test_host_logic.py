@@ -103,3 +103,36 @@ def test_bench_reference_arm_json_contract():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--tiny"], capture_output=True, text=True,
                          timeout=120, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_gemm_column_tiling_partitions_n():
+    """Host view of the kernel's N tiling (hb_gemm_n_tiling): tiles partition [0, N), are <= 256 wide, multiples of 16 * cta_group,
+    balanced tiles differ by at most one unit, and the ViT shapes come out as documented in DESIGN.md §3.1."""
+    import numpy as np
+
+    from hirest_b200 import _lib
+
+    lib = _lib.load()
+
+    def tiles(N, cg, bal):
+        n0 = np.zeros(256, np.int32)
+        w = np.zeros(256, np.int32)
+        n = lib.hb_gemm_n_tiling(N, cg, bal, n0.ctypes.data, w.ctypes.data, 256)
+        assert n > 0
+        return n0[:n].tolist(), w[:n].tolist()
+
+    for cg in (1, 2):
+        unit = 16 * cg
+        for N in [unit * k for k in (1, 2, 3, 7, 8, 9, 15, 16, 17, 44, 88, 132, 192, 954)]:
+            for bal in (0, 1):
+                n0, w = tiles(N, cg, bal)
+                assert n0[0] == 0 and sum(w) == N and all(a + b == c for a, b, c in zip(n0, w, n0[1:] + [N]))
+                assert max(w) <= 256 and all(x % unit == 0 and x > 0 for x in w)
+                assert len(w) == (N + 255) // 256
+                if bal:
+                    assert max(w) - min(w) <= unit
+    assert tiles(1408, 2, 1)[1] == [256, 256, 224, 224, 224, 224]
+    assert tiles(1408, 2, 0)[1] == [256] * 5 + [128]
+    assert sorted(tiles(4224, 2, 1)[1], reverse=True) == [256] * 13 + [224] * 4
+    assert tiles(6144, 2, 1)[1] == [256] * 24
+    assert lib.hb_gemm_n_tiling(0, 2, 1, None, None, 0) < 0
