@@ -87,13 +87,28 @@ def _batches(items: List[dict], batch_size: int):
 
 
 @torch.no_grad()
-def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beams: int = 5, n_model_frames: int = -1) -> Dict:
+def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beams: int = 5, n_model_frames: int = -1,
+                   tokenize=None) -> Dict:
     """Chain the three tasks over ``videos`` (dicts with ``prompt``, ``fname``, ``video_duration``, ``vis_feats [T,1024]``,
-    ``asr_feats [T,384]``, ``clip_text_ids [77]``; order = dataset order).  Returns
+    ``asr_feats [T,384]``, ``clip_text_ids [77]``; order = dataset order).  Videos without ``clip_text_ids`` get them from
+    ``tokenize(prompt) -> LongTensor[1, 77]`` (e.g. ``hirest_b200.tokenizer.tokenize``), as ``collate_fn`` does with
+    ``clip.tokenize`` (hirest_dataset.py:528).  Returns
     ``{"final": {prompt: {fname: {"bounds", "steps": [{"index", "heading", "absolute_bounds"}]}}},
     "moment_retrieval": ..., "moment_segmentation": ..., "step_captioning": ...}`` with the per-task dictionaries the
     reference dumps next to the final file."""
     nmf = n_model_frames
+    if any("clip_text_ids" not in v for v in videos):
+        if tokenize is None:
+            raise ValueError("videos without 'clip_text_ids' need a tokenize callable (hirest_b200.tokenizer.tokenize)")
+        cache: Dict[str, torch.Tensor] = {}
+        filled = []
+        for v in videos:
+            if "clip_text_ids" not in v:
+                if v["prompt"] not in cache:
+                    cache[v["prompt"]] = tokenize(v["prompt"])[0]
+                v = dict(v, clip_text_ids=cache[v["prompt"]])
+            filled.append(v)
+        videos = filled
     # ---- 1. moment retrieval (dataset :153-183, evaluate :704-744) -------------------------------------------------
     items = []
     for v in videos:

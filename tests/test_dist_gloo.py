@@ -38,3 +38,28 @@ def test_sharded_scores_equal_single_process(tmp_path):
     for r in range(world):
         got = torch.load(os.path.join(str(tmp_path), f"scores_{r}.pt"))
         assert torch.equal(got, ref)
+
+
+def test_feature_store_shards_reassemble(tmp_path):
+    """Every rank reads only its own contiguous block of videos from the packed store (retrieval.shard_range); the blocks tile
+    the store exactly, in order — host logic, no GPU."""
+    import numpy as np
+    import torch
+
+    from hirest_b200 import feature_store, retrieval
+
+    g = torch.Generator().manual_seed(0)
+    vids = [(f"v{i}", torch.randn(int(torch.randint(1, 9, (1,), generator=g)), 16, generator=g)) for i in range(11)]
+    path = str(tmp_path / "s.hbf")
+    feature_store.pack_features(vids, path)
+    st = feature_store.FeatureStore(path)
+    for world in (1, 2, 3, 4, 8, 16):
+        rows, names = [], []
+        for rank in range(world):
+            lo, hi = retrieval.shard_range(len(st), rank, world)
+            feats, offs = st.to_device("cpu", video_range=(lo, hi))
+            assert offs[0] == 0 and offs.numel() == hi - lo + 1
+            rows.append(feats)
+            names += st.video_ids[lo:hi]
+        assert names == st.video_ids
+        assert torch.equal(torch.cat(rows), torch.from_numpy(np.array(st.data)))

@@ -118,3 +118,30 @@ def test_end_to_end_chain_matches_reference_flow(hb, tmp_path):
             assert got["final"][p][fn]["steps"] == a["steps"], (p, fn)   # step bounds (ints) and captions (strings)
     n_steps = sum(len(a["steps"]) for p in got["final"] for a in got["final"][p].values())
     assert n_steps >= 8 and all(s["heading"] for p in got["final"] for a in got["final"][p].values() for s in a["steps"])
+
+
+def test_prompts_are_tokenized_when_ids_are_missing():
+    """run_end_to_end fills clip_text_ids through the tokenize callable (once per distinct prompt) before the first model call."""
+    calls = []
+
+    def fake_tokenize(prompt):
+        calls.append(prompt)
+        ids = torch.zeros(1, 77, dtype=torch.long)
+        ids[0, 0], ids[0, 1], ids[0, 2] = 49406, len(prompt), 49407
+        return ids
+
+    class Stop(Exception):
+        pass
+
+    class Probe:
+        def test_step(self, batch, **kw):
+            assert batch["clip_text_ids"].shape == (3, 77) and batch["clip_text_ids"][:, 1].tolist() == [5, 5, 8]
+            raise Stop
+
+    vids = [{"prompt": p, "fname": f"v{i}", "video_duration": 6, "vis_feats": torch.zeros(6, 4), "asr_feats": torch.zeros(6, 3)}
+            for i, p in enumerate(["aaaaa", "aaaaa", "bbbbbbbb"])]
+    with pytest.raises(Stop):
+        pipeline.run_end_to_end(Probe(), vids, tokenize=fake_tokenize)
+    assert calls == ["aaaaa", "bbbbbbbb"]
+    with pytest.raises(ValueError):
+        pipeline.run_end_to_end(Probe(), vids)
