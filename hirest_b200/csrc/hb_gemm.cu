@@ -8,7 +8,8 @@
 //   warp 1      : MMA issuer     (whole warp walks the loop, one elected lane issues tcgen05.mma kind::f16,
 //                 128xN (CG=1) or 256xN (CG=2) tiles)
 //   warp 2      : TMEM allocator (512 columns = two 256-column accumulator buffers)
-//   warps 4..11 : epilogue       (tcgen05.ld -> bias / GELU / residual -> vectorised st.global)
+//   warps 4..11 : epilogue       (tcgen05.ld -> bias / LayerNorm fold / GELU / residual -> per-warp smem staging ->
+//                 line-coalesced st.global: four full 128-byte lines per store instruction)
 // The accumulator is double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // Reference call sites replaced: every F.linear on the hot path, e.g. EVA_clip/vit_model.py:57-61
