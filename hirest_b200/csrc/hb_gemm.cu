@@ -466,6 +466,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         float4 res_a[8], res_b[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) res_a[i] = res_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifdef HB_EXP_INTERLEAVE_HALVES
+        // EXPERIMENT (compile-time -DHB_EXP_INTERLEAVE_HALVES, not built by default; measured: results identical, proj 1079 ->
+        // 1114 TFLOP/s alone, nothing inside the power-capped step): chunk k of this warp sits at
+        // tile column 64 k + 32 half instead of 128 half + 32 k, so the two warps of a lane quarter touch ADJACENT 128-byte
+        // lines of a row at about the same time (better DRAM page locality for the HBM-bound proj epilogue).  Statistics slots
+        // stay one per (tile, half): any fixed partition of the columns works.
+        auto colk = [&](int k) { return 64 * k + 32 * half; };
+        if (has_add && colk(0) < n_eff) load_add(n0 + colk(0), n_eff - colk(0), res_a);
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int k = 0; colk(k) < n_eff; k += 2) {
+          const int ca = colk(k), cb = colk(k + 1), cn = colk(k + 2);
+          const bool second = cb < n_eff;
+          if (has_add && second) load_add(n0 + cb, n_eff - cb, res_b);
+          do_chunk(ca, res_a);
+          if (second) {
+            if (has_add && cn < n_eff) load_add(n0 + cn, n_eff - cn, res_a);
+            do_chunk(cb, res_b);
+          }
+        }
+#else
         if (has_add && c_begin < c_end) load_add(n0 + c_begin, n_eff - c_begin, res_a);
         for (int k = 1; k <= p.prefetch_chunks; ++k) l2_prefetch(c_begin + 32 * k);
         mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -482,6 +504,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             do_chunk(c + 32, res_b);
           }
         }
+#endif
         if constexpr (EPI == EPI_F32_STATS) {
           // the 8 lanes that share a row (same lane >> 3) combine their partials in a fixed order and one lane writes them to
           // this warp's slot (one per 128-column span): no atomics, so the statistics — and everything downstream — are
