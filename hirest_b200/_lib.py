@@ -35,7 +35,7 @@ class HbVitWeights(C.Structure):
 
 class HbTextConfig(C.Structure):
     _fields_ = [("context_length", C.c_int), ("vocab_size", C.c_int), ("width", C.c_int), ("heads", C.c_int),
-                ("layers", C.c_int), ("embed_dim", C.c_int), ("ln_eps", C.c_float)]
+                ("layers", C.c_int), ("embed_dim", C.c_int), ("ln_eps", C.c_float), ("precise", C.c_int)]
 
 
 class HbTextWeights(C.Structure):

@@ -235,6 +235,66 @@ int run_gemm(const CUtensorMap& tmA, const Linear& L, long long M, void* out, in
   return 0;
 }
 
+// src fp32 [K,N] -> dst fp32 [N,K]
+__global__ void transpose_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int K) {
+  const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t >= static_cast<long long>(N) * K) return;
+  const int n = static_cast<int>(t / K), k = static_cast<int>(t % K);
+  dst[t] = src[static_cast<long long>(k) * N + n];
+}
+
+// nn.Linear as a 3-term split-bf16 GEMM: weight [N, 3K] = [hi | lo | hi], activations [R, 3K] = [lo | hi | hi].
+struct SplitLinear {
+  DevBuf w, b;
+  CUtensorMap tm;
+  int N = 0, K = 0, cg = 2;
+  bool has_bias = false;
+  // w_f32: device [N,K], or [K,N] when transposed (x @ P == x (P^T)^T, eva_model.py:249)
+  int init_from(const float* w_f32, const float* bias, int N_, int K_, cudaStream_t s, bool transposed = false) {
+    N = N_; K = K_; cg = (N_ % 32 == 0) ? g_cg : 1;
+    if (int r = w.alloc(static_cast<size_t>(N) * 3 * K * 2)) return r;
+    DevBuf wt;
+    if (transposed) {
+      if (int r = wt.alloc(static_cast<size_t>(N) * K * 4)) return r;
+      const long long total = static_cast<long long>(N) * K;
+      transpose_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(w_f32, wt.as<float>(), N, K);
+      HB_CUDA(cudaGetLastError());
+      w_f32 = wt.as<float>();
+    }
+    if (int r = hb::split3_weight_launch(w_f32, w.as<__nv_bfloat16>(), N, K, s)) return fail(HB_ERR_CUDA, "split3_weight launch failed: %d", r);
+    if (transposed) HB_CUDA(cudaStreamSynchronize(s));  // wt is a temporary
+    if (bias) {
+      has_bias = true;
+      if (int r = b.alloc(static_cast<size_t>(N) * 4)) return r;
+      HB_CUDA(cudaMemcpyAsync(b.p, bias, static_cast<size_t>(N) * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    if (hb::make_tmap_bf16(&tm, w.p, N, 3 * K, 3 * K, hb::gemm_w_box_rows(cg))) return fail(HB_ERR_CUDA, "tensor map (split weight) failed");
+    return 0;
+  }
+};
+
+
+// fp32 activations [rows, K] -> split operand in `op` -> 3-term split-bf16 GEMM with L -> out fp32 [rows, N]
+int split_gemm_op(__nv_bfloat16* op, const float* act, long long rows, int K, int gelu, const CUtensorMap& tmA, const SplitLinear& L,
+                  float* out, int epi, cudaStream_t s, const float* resid = nullptr, const float* rowadd = nullptr, int remap = 0) {
+  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(act, op, rows, K, gelu, s));
+  hb::GemmParams p;
+  p.M = static_cast<int>(rows); p.N = L.N; p.K = 3 * K;
+  p.bias = L.has_bias ? L.b.as<float>() : nullptr; p.out = out; p.ldo = L.N; p.resid = resid;
+  p.rowadd = rowadd; p.remap_in = remap; p.remap_out = remap; p.remap_off = 0;
+  HB_LAUNCH_P(CAT_GEMM_F32, 2.0 * rows * L.N * 3.0 * K, s, hb::gemm_launch(tmA, L.tm, p, epi, L.cg, g_num_sms, s));
+  return 0;
+}
+
+int ln_f32(const float* x, float* y, const F32Vec& w, const F32Vec& b, float eps, long long rows, int D, cudaStream_t s,
+           const int* row_idx = nullptr) {
+  hb::LayerNormParams ln;
+  ln.x = x; ln.ldx = D; ln.y = y; ln.ldy = D; ln.w = w.ptr(); ln.b = b.ptr(); ln.eps = eps; ln.rows = static_cast<int>(rows); ln.D = D;
+  ln.row_idx = row_idx;
+  HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, false, s));
+  return 0;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -555,6 +615,16 @@ struct HbText {
   Linear proj;
   Act h, hid, eot;
   DevBuf x, qkv, eot_row;
+  // precise mode (cfg.precise != 0, the default of the Python surface): every Linear as a 3-term split-bf16 GEMM, LayerNorm /
+  // attention / residual stream in fp32 -- encode_text within ~1e-5 of the fp32 reference, so that the integer decisions the
+  // MomentModel derives from the text feature (argmax, region growing, beam top-k) match the reference's.
+  bool precise = false;
+  int chunk = 0;   // queries per pass
+  struct PLayer { SplitLinear qkv, out, fc, cproj; };
+  std::vector<std::unique_ptr<PLayer>> players;
+  SplitLinear proj_s;
+  DevBuf op, opE, lnb, qkvf, att, mid, eotf;
+  CUtensorMap tm_w, tm_4w, tm_eot;
 };
 
 extern "C" {
@@ -570,6 +640,8 @@ int hb_text_create(const HbTextConfig* cfg, const HbTextWeights* w, int max_batc
   if (!m) return fail(HB_ERR_NOMEM, "host allocation failed");
   m->cfg = *cfg;
   m->max_batch = max_batch;
+  m->precise = (cfg->precise != 0);
+  m->chunk = m->precise ? std::min(max_batch, 128) : max_batch;
   int r;
   if ((r = m->tok.init(w->token_embedding, static_cast<size_t>(cfg->vocab_size) * W, s))) return r;
   if ((r = m->pos.init(w->positional_embedding, static_cast<size_t>(C) * W, s))) return r;
@@ -579,22 +651,46 @@ int hb_text_create(const HbTextConfig* cfg, const HbTextWeights* w, int max_batc
     if ((r = L->l1b.init(w->ln1_b[i], W, s))) return r;
     if ((r = L->l2w.init(w->ln2_w[i], W, s))) return r;
     if ((r = L->l2b.init(w->ln2_b[i], W, s))) return r;
-    if ((r = L->qkv.init(w->in_proj_w[i], 3 * W, W, w->in_proj_b[i], false, s))) return r;
-    if ((r = L->out.init(w->out_proj_w[i], W, W, w->out_proj_b[i], false, s))) return r;
-    if ((r = L->fc.init(w->fc_w[i], 4 * W, W, w->fc_b[i], false, s))) return r;
-    if ((r = L->cproj.init(w->cproj_w[i], W, 4 * W, w->cproj_b[i], false, s))) return r;
+    if (m->precise) {
+      std::unique_ptr<HbText::PLayer> P(new HbText::PLayer);
+      if ((r = P->qkv.init_from(w->in_proj_w[i], w->in_proj_b[i], 3 * W, W, s))) return r;
+      if ((r = P->out.init_from(w->out_proj_w[i], w->out_proj_b[i], W, W, s))) return r;
+      if ((r = P->fc.init_from(w->fc_w[i], w->fc_b[i], 4 * W, W, s))) return r;
+      if ((r = P->cproj.init_from(w->cproj_w[i], w->cproj_b[i], W, 4 * W, s))) return r;
+      m->players.push_back(std::move(P));
+    } else {
+      if ((r = L->qkv.init(w->in_proj_w[i], 3 * W, W, w->in_proj_b[i], false, s))) return r;
+      if ((r = L->out.init(w->out_proj_w[i], W, W, w->out_proj_b[i], false, s))) return r;
+      if ((r = L->fc.init(w->fc_w[i], 4 * W, W, w->fc_b[i], false, s))) return r;
+      if ((r = L->cproj.init(w->cproj_w[i], W, 4 * W, w->cproj_b[i], false, s))) return r;
+    }
     m->layers.push_back(std::move(L));
   }
   if ((r = m->lfw.init(w->ln_final_w, W, s))) return r;
   if ((r = m->lfb.init(w->ln_final_b, W, s))) return r;
-  if ((r = m->proj.init(w->text_projection, E, W, nullptr, /*transposed=*/true, s))) return r;  // x @ P == x P'^T, P' = P^T
-  const long long rows = static_cast<long long>(max_batch) * C;
-  if ((r = m->h.init(rows, W))) return r;
-  if ((r = m->hid.init(rows, 4 * W))) return r;
-  if ((r = m->eot.init(max_batch, W))) return r;
+  const long long rows = static_cast<long long>(m->chunk) * C;
   if ((r = m->x.alloc(static_cast<size_t>(rows) * W * 4))) return r;
-  if ((r = m->qkv.alloc(static_cast<size_t>(rows) * 3 * W * 2))) return r;
-  if ((r = m->eot_row.alloc(static_cast<size_t>(max_batch) * 4))) return r;
+  if ((r = m->eot_row.alloc(static_cast<size_t>(m->chunk) * 4))) return r;
+  if (m->precise) {
+    if ((r = m->proj_s.init_from(w->text_projection, nullptr, E, W, s, /*transposed=*/true))) return r;  // x @ P == x (P^T)^T
+    if ((r = m->op.alloc(static_cast<size_t>(rows) * 3 * 4 * W * 2))) return r;
+    if ((r = m->opE.alloc(static_cast<size_t>(m->chunk) * 3 * W * 2))) return r;
+    if ((r = m->lnb.alloc(static_cast<size_t>(rows) * W * 4))) return r;
+    if ((r = m->qkvf.alloc(static_cast<size_t>(rows) * 3 * W * 4))) return r;
+    if ((r = m->att.alloc(static_cast<size_t>(rows) * W * 4))) return r;
+    if ((r = m->mid.alloc(static_cast<size_t>(rows) * 4 * W * 4))) return r;
+    if ((r = m->eotf.alloc(static_cast<size_t>(m->chunk) * W * 4))) return r;
+    if (hb::make_tmap_bf16(&m->tm_w, m->op.p, rows, 3 * W, 3 * W, hb::gemm_a_box_rows()) ||
+        hb::make_tmap_bf16(&m->tm_4w, m->op.p, rows, 12 * W, 12 * W, hb::gemm_a_box_rows()) ||
+        hb::make_tmap_bf16(&m->tm_eot, m->opE.p, m->chunk, 3 * W, 3 * W, hb::gemm_a_box_rows()))
+      return fail(HB_ERR_CUDA, "tensor map (text operands) failed");
+  } else {
+    if ((r = m->proj.init(w->text_projection, E, W, nullptr, /*transposed=*/true, s))) return r;  // x @ P == x P'^T, P' = P^T
+    if ((r = m->h.init(rows, W))) return r;
+    if ((r = m->hid.init(rows, 4 * W))) return r;
+    if ((r = m->eot.init(m->chunk, W))) return r;
+    if ((r = m->qkv.alloc(static_cast<size_t>(rows) * 3 * W * 2))) return r;
+  }
   HB_CUDA(cudaStreamSynchronize(s));
   *out = m.release();
   return HB_OK;
@@ -609,6 +705,30 @@ static int text_encode_chunk(HbText* m, const int64_t* ids, int Q, float* out, c
   int r;
   HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::text_embed_launch(reinterpret_cast<const long long*>(ids), m->tok.ptr(), m->pos.ptr(), x,
                                   m->eot_row.as<int>(), Q, C, W, c.vocab_size, s));
+  if (m->precise) {
+    __nv_bfloat16* op = m->op.as<__nv_bfloat16>();
+    float *lnb = m->lnb.as<float>(), *qf = m->qkvf.as<float>(), *att = m->att.as<float>(), *mid = m->mid.as<float>();
+    for (int i = 0; i < c.layers; ++i) {
+      HbText::Layer& L = *m->layers[i];
+      HbText::PLayer& P = *m->players[i];
+      if ((r = ln_f32(x, lnb, L.l1w, L.l1b, c.ln_eps, M, W, s))) return r;
+      if ((r = split_gemm_op(op, lnb, M, W, 0, m->tm_w, P.qkv, qf, hb::EPI_F32, s))) return r;
+      hb::SmallAttnF32Params ap;
+      ap.q = qf; ap.k = qf + W; ap.v = qf + 2 * W; ap.out = att;
+      ap.B = Q; ap.H = c.heads; ap.Tq = C; ap.Tk = C;
+      ap.ldq = ap.ldk = ap.ldv = 3 * W; ap.ldo = W;
+      ap.bsq = ap.bsk = ap.bsv = static_cast<long long>(C) * 3 * W; ap.bso = static_cast<long long>(C) * W;
+      ap.scale = 0.125f; ap.mask_mode = 1;   // causal, eva_model.py:224-230
+      HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::small_attn_f32_launch(ap, s));
+      if ((r = split_gemm_op(op, att, M, W, 0, m->tm_w, P.out, x, hb::EPI_F32, s, x))) return r;
+      if ((r = ln_f32(x, lnb, L.l2w, L.l2b, c.ln_eps, M, W, s))) return r;
+      if ((r = split_gemm_op(op, lnb, M, W, 0, m->tm_w, P.fc, mid, hb::EPI_F32, s))) return r;
+      if ((r = split_gemm_op(op, mid, M, 4 * W, /*gelu=*/1, m->tm_4w, P.cproj, x, hb::EPI_F32, s, x))) return r;
+    }
+    if ((r = ln_f32(x, m->eotf.as<float>(), m->lfw, m->lfb, c.ln_eps, Q, W, s, m->eot_row.as<int>()))) return r;
+    if ((r = split_gemm_op(m->opE.as<__nv_bfloat16>(), m->eotf.as<float>(), Q, W, 0, m->tm_eot, m->proj_s, out, hb::EPI_F32, s))) return r;
+    return HB_OK;
+  }
   for (int i = 0; i < c.layers; ++i) {
     HbText::Layer& L = *m->layers[i];
     hb::LayerNormParams ln;
@@ -644,8 +764,8 @@ int hb_text_encode(HbText* m, const int64_t* ids, int64_t Q, float* out, void* s
   if (!m || !ids || !out) return fail(HB_ERR_INVALID, "null argument");
   if (Q < 0) return fail(HB_ERR_INVALID, "negative batch");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  for (int64_t q0 = 0; q0 < Q; q0 += m->max_batch) {
-    const int nq = static_cast<int>(std::min<int64_t>(m->max_batch, Q - q0));
+  for (int64_t q0 = 0; q0 < Q; q0 += m->chunk) {
+    const int nq = static_cast<int>(std::min<int64_t>(m->chunk, Q - q0));
     int r = text_encode_chunk(m, ids + q0 * m->cfg.context_length, nq, out + q0 * m->cfg.embed_dim, s);
     if (r) return r;
   }
@@ -829,30 +949,6 @@ int hb_small_attention(const void* q, const void* k, const void* v, void* out, i
 // =================================================================================================
 // MomentModel shared encoder + heads
 // =================================================================================================
-namespace {
-
-// nn.Linear as a 3-term split-bf16 GEMM: weight [N, 3K] = [hi | lo | hi], activations [R, 3K] = [lo | hi | hi].
-struct SplitLinear {
-  DevBuf w, b;
-  CUtensorMap tm;
-  int N = 0, K = 0, cg = 2;
-  bool has_bias = false;
-  int init_from(const float* w_f32 /*device [N,K]*/, const float* bias, int N_, int K_, cudaStream_t s) {
-    N = N_; K = K_; cg = (N_ % 32 == 0) ? g_cg : 1;
-    if (int r = w.alloc(static_cast<size_t>(N) * 3 * K * 2)) return r;
-    if (int r = hb::split3_weight_launch(w_f32, w.as<__nv_bfloat16>(), N, K, s)) return fail(HB_ERR_CUDA, "split3_weight launch failed: %d", r);
-    if (bias) {
-      has_bias = true;
-      if (int r = b.alloc(static_cast<size_t>(N) * 4)) return r;
-      HB_CUDA(cudaMemcpyAsync(b.p, bias, static_cast<size_t>(N) * 4, cudaMemcpyDeviceToDevice, s));
-    }
-    if (hb::make_tmap_bf16(&tm, w.p, N, 3 * K, 3 * K, hb::gemm_w_box_rows(cg))) return fail(HB_ERR_CUDA, "tensor map (split weight) failed");
-    return 0;
-  }
-};
-
-}  // namespace
-
 struct HbMoment {
   HbMomentConfig cfg;
   long long max_rows = 0;
@@ -875,21 +971,7 @@ namespace {
 int split_gemm(HbMoment* m, const float* act, long long rows, int K, int gelu, const CUtensorMap& tmA, const SplitLinear& L,
                float* out, int epi, cudaStream_t s, const float* resid = nullptr, const float* rowadd = nullptr, int remap = 0,
                __nv_bfloat16* opbuf = nullptr) {
-  __nv_bfloat16* dst = opbuf ? opbuf : m->op.as<__nv_bfloat16>();
-  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(act, dst, rows, K, gelu, s));
-  hb::GemmParams p;
-  p.M = static_cast<int>(rows); p.N = L.N; p.K = 3 * K;
-  p.bias = L.has_bias ? L.b.as<float>() : nullptr; p.out = out; p.ldo = L.N; p.resid = resid;
-  p.rowadd = rowadd; p.remap_in = remap; p.remap_out = remap; p.remap_off = 0;
-  HB_LAUNCH_P(CAT_GEMM_F32, 2.0 * rows * L.N * 3.0 * K, s, hb::gemm_launch(tmA, L.tm, p, epi, L.cg, g_num_sms, s));
-  return 0;
-}
-
-int ln_f32(const float* x, float* y, const F32Vec& w, const F32Vec& b, float eps, long long rows, int D, cudaStream_t s) {
-  hb::LayerNormParams ln;
-  ln.x = x; ln.ldx = D; ln.y = y; ln.ldy = D; ln.w = w.ptr(); ln.b = b.ptr(); ln.eps = eps; ln.rows = static_cast<int>(rows); ln.D = D;
-  HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, false, s));
-  return 0;
+  return split_gemm_op(opbuf ? opbuf : m->op.as<__nv_bfloat16>(), act, rows, K, gelu, tmA, L, out, epi, s, resid, rowadd, remap);
 }
 
 }  // namespace
@@ -902,19 +984,21 @@ int hb_moment_create(const HbMomentConfig* cfg, const HbMomentWeights* w, int64_
   if (!cfg || !w || !out || max_rows <= 0 || max_batch <= 0) return fail(HB_ERR_INVALID, "null argument");
   const int E = cfg->embed_dim, Hd = cfg->hidden, Ff = cfg->ffn, A = cfg->asr_dim, Cd = cfg->clip_dim;
   if (Hd != cfg->heads * 64) return fail(HB_ERR_INVALID, "head_dim must be 64");
-  if (E % 32 || Hd % 32 || Ff % 32 || A % 8 || Cd % 8 || E > 1024) return fail(HB_ERR_INVALID, "unsupported MomentModel dims");
+  if (E % 32 || Hd % 32 || Ff % 32 || A < 0 || A % 8 || Cd % 8 || E > 1024) return fail(HB_ERR_INVALID, "unsupported MomentModel dims");
+  const bool use_asr = A > 0;   // modeling.py:28-35: asr_dim <= 0 builds no asr_enc_layer
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   std::unique_ptr<HbMoment> m(new (std::nothrow) HbMoment);
   if (!m) return fail(HB_ERR_NOMEM, "host allocation failed");
   m->cfg = *cfg; m->max_rows = max_rows; m->max_batch = max_batch;
   int r;
 #define INITV(dst, src, n) if ((r = m->dst.init(w->src, static_cast<size_t>(n), s))) return r
-  INITV(asr_ln_w, asr_ln_w, A); INITV(asr_ln_b, asr_ln_b, A); INITV(temp_w1, temp_w1, E); INITV(temp_b1, temp_b1, E);
+  if (use_asr) { INITV(asr_ln_w, asr_ln_w, A); INITV(asr_ln_b, asr_ln_b, A); }
+  INITV(temp_w1, temp_w1, E); INITV(temp_b1, temp_b1, E);
   INITV(memb, mask_embed, 2 * E); INITV(bemb, boundary_embed, 2 * E); INITV(head_w, head_w, 3 * Hd); INITV(head_b, head_b, 3);
   INITV(vn_w, vis_norm_w, E); INITV(vn_b, vis_norm_b, E); INITV(pos, pos_emb, static_cast<size_t>(cfg->max_pos) * Hd);
   INITV(emb_ln_w, emb_ln_w, Hd); INITV(emb_ln_b, emb_ln_b, Hd);
 #undef INITV
-  if ((r = m->asr.init_from(w->asr_w, w->asr_b, E, A, s))) return r;
+  if (use_asr && (r = m->asr.init_from(w->asr_w, w->asr_b, E, A, s))) return r;
   if ((r = m->temp2.init_from(w->temp_w2, w->temp_b2, E, E, s))) return r;
   if ((r = m->gmap.init_from(w->clip_g_map_w, w->clip_g_map_b, E, Cd, s))) return r;
   if ((r = m->gmap_text.init_from(w->clip_g_map_text_w, w->clip_g_map_text_b, E, Cd, s))) return r;
@@ -945,7 +1029,7 @@ int hb_moment_create(const HbMomentConfig* cfg, const HbMomentWeights* w, int64_
   if ((r = m->op.alloc(R * 3 * Kmax * 2))) return r;
   if ((r = m->opT.alloc(static_cast<size_t>(max_batch) * 3 * Cd * 2))) return r;
 #define ALLOCF(buf, cols) if ((r = m->buf.alloc(R * static_cast<size_t>(cols) * 4))) return r
-  ALLOCF(vlin, E); ALLOCF(asr_ln, A); ALLOCF(asr_lin, E); ALLOCF(tanh_in, E); ALLOCF(temporal, E); ALLOCF(base, E); ALLOCF(f, E);
+  ALLOCF(vlin, E); if (use_asr) { ALLOCF(asr_ln, A); ALLOCF(asr_lin, E); } ALLOCF(tanh_in, E); ALLOCF(temporal, E); ALLOCF(base, E); ALLOCF(f, E);
   ALLOCF(e_lin, Hd); ALLOCF(x, Hd); ALLOCF(qkv, 3 * Hd); ALLOCF(att, Hd); ALLOCF(t1, Hd); ALLOCF(h, Hd); ALLOCF(mid, Ff);
 #undef ALLOCF
   if ((r = m->tlin.alloc(static_cast<size_t>(max_batch) * E * 4))) return r;
@@ -953,7 +1037,7 @@ int hb_moment_create(const HbMomentConfig* cfg, const HbMomentWeights* w, int64_
   auto amap = [&](CUtensorMap* tm, void* ptr, long long rows, int K) {
     return hb::make_tmap_bf16(tm, ptr, rows, 3 * K, 3 * K, hb::gemm_a_box_rows());
   };
-  if (amap(&m->tm_clip, m->op.p, max_rows, Cd) || amap(&m->tm_asr, m->op.p, max_rows, A) || amap(&m->tm_e, m->op.p, max_rows, E) ||
+  if (amap(&m->tm_clip, m->op.p, max_rows, Cd) || (use_asr && amap(&m->tm_asr, m->op.p, max_rows, A)) || amap(&m->tm_e, m->op.p, max_rows, E) ||
       amap(&m->tm_hd, m->op.p, max_rows, Hd) || amap(&m->tm_ffn, m->op.p, max_rows, Ff) || amap(&m->tm_text, m->opT.p, max_batch, Cd))
     return fail(HB_ERR_CUDA, "tensor map (moment operands) failed");
   HB_CUDA(cudaStreamSynchronize(s));  // tmpw/tmpb are released on return
@@ -976,7 +1060,7 @@ int hb_moment_forward(HbMoment* m, const float* video, const float* text_feat, c
   const int E = c.embed_dim, Hd = c.hidden, Ff = c.ffn, A = c.asr_dim, Cd = c.clip_dim;
   int r;
   if (!(flags & HB_MOMENT_REUSE_BASE)) {
-    if (!video || !text_feat || !asr || !video_mask) return fail(HB_ERR_INVALID, "null argument");
+    if (!video || !text_feat || (A > 0 && !asr) || !video_mask) return fail(HB_ERR_INVALID, "null argument");
     // clip_g_map (modeling.py:158), clip_g_map_text + L2 norm (:159,163)
     if ((r = split_gemm(m, video, R, Cd, 0, m->tm_clip, m->gmap, m->vlin.as<float>(), hb::EPI_F32, s))) return r;
     if ((r = split_gemm(m, text_feat, B, Cd, 0, m->tm_text, m->gmap_text, m->tlin.as<float>(), hb::EPI_F32, s, nullptr, nullptr, 0,
@@ -984,14 +1068,16 @@ int hb_moment_forward(HbMoment* m, const float* video, const float* text_feat, c
       return r;
     HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::pool_normalize_launch(m->tlin.as<float>(), m->that.p, B, 1, E, true, false, s));
     // asr_enc_layer = LayerNorm(1e-5) -> Linear (:167-169)
-    if ((r = ln_f32(asr, m->asr_ln.as<float>(), m->asr_ln_w, m->asr_ln_b, 1e-5f, R, A, s))) return r;
-    if ((r = split_gemm(m, m->asr_ln.as<float>(), R, A, 0, m->tm_asr, m->asr, m->asr_lin.as<float>(), hb::EPI_F32, s))) return r;
+    if (A > 0) {
+      if ((r = ln_f32(asr, m->asr_ln.as<float>(), m->asr_ln_w, m->asr_ln_b, 1e-5f, R, A, s))) return r;
+      if ((r = split_gemm(m, m->asr_ln.as<float>(), R, A, 0, m->tm_asr, m->asr, m->asr_lin.as<float>(), hb::EPI_F32, s))) return r;
+    }
     // temporal_embed = Linear(1,E) -> tanh -> Linear(E,E) on the per-sample time grid (:178-196)
     HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::time_tanh_launch(reinterpret_cast<const long long*>(video_mask), m->temp_w1.ptr(),
                                                         m->temp_b1.ptr(), m->tanh_in.as<float>(), B, T, E, s));
     if ((r = split_gemm(m, m->tanh_in.as<float>(), R, E, 0, m->tm_e, m->temp2, m->temporal.as<float>(), hb::EPI_F32, s))) return r;
     HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::moment_base_launch(m->vlin.as<float>(), m->vn_w.ptr(), m->vn_b.ptr(), m->that.as<float>(),
-                                                          m->asr_lin.as<float>(), m->temporal.as<float>(), m->base.as<float>(), B, T, E, s));
+                                                          A > 0 ? m->asr_lin.as<float>() : nullptr, m->temporal.as<float>(), m->base.as<float>(), B, T, E, s));
   }
   HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::moment_embed_launch(m->base.as<float>(), m->bemb.ptr(), m->memb.ptr(),
                                                          reinterpret_cast<const long long*>(boundary_mask),

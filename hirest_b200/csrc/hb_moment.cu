@@ -105,7 +105,8 @@ __global__ void __launch_bounds__(256) moment_base_kernel(const float* __restric
   for (int i = 0; i < 8; ++i) {
     const int idx = lane + i * 32;
     if (idx < nv) {
-      const float4 w = w4[idx], bb = b4[idx], th = t4[idx], a = a4[idx], p = p4[idx];
+      const float4 w = w4[idx], bb = b4[idx], th = t4[idx], p = p4[idx];
+      const float4 a = (asr_lin != nullptr) ? a4[idx] : make_float4(0.f, 0.f, 0.f, 0.f);   // ASR-free model: modeling.py:167 skipped
       float4 o;
       o.x = (w.x * ((v[i].x - mean) * rstd) + bb.x) * th.x + a.x + p.x;
       o.y = (w.y * ((v[i].y - mean) * rstd) + bb.y) * th.y + a.y + p.y;

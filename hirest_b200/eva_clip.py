@@ -103,6 +103,14 @@ def _text_shapes(embed_dim: int, t: dict) -> dict:
     return s
 
 
+def _param_key(params):
+    """Cache key of an engine's repacked weights: device, storage address and version counter of EVERY parameter.  In-place
+    updates bump ``_version``; ``p.data = other`` / ``.to()`` change ``data_ptr()``.  Writes through ``p.data.copy_()`` are invisible
+    to both: call ``invalidate()`` on the module after such a write."""
+    params = list(params)
+    return (params[0].device,) + tuple((q.data_ptr(), q._version) for q in params)
+
+
 class _Engine:
     """Owns one native handle; destroys it when collected."""
 
@@ -135,8 +143,12 @@ class VisionTransformer(_ParamTree):
         self._engine_key = None
 
     def _key(self):
-        p = self.cls_token
-        return (p.device, p.data_ptr(), tuple(q._version for q in self.parameters()))
+        return _param_key(self.parameters())
+
+    def invalidate(self):
+        """Drop the native handle (repacked bf16 weights); the next forward rebuilds it from the current parameters."""
+        self._engine = None
+        self._engine_key = None
 
     def _get_engine(self):
         key = self._key()
@@ -215,19 +227,27 @@ class VisionTransformer(_ParamTree):
 class TextTransformer(_ParamTree):
     """EVA-CLIP text tower (EVA_clip/eva_model.py:177-250)."""
 
-    def __init__(self, embed_dim: int, cfg: dict, max_batch: int = 512):
+    def __init__(self, embed_dim: int, cfg: dict, max_batch: int = 512, precise: bool = True):
         super().__init__(_text_shapes(embed_dim, cfg))
         self.cfg = dict(cfg)
         self.embed_dim = embed_dim
         self.context_length = cfg["context_length"]
         self.vocab_size = cfg["vocab_size"]
         self.max_batch = max_batch
+        # precise=True (default): 3-term split-bf16 GEMMs + fp32 LayerNorm / attention, ~1e-5 of the fp32 reference.  The text
+        # feature multiplies every frame feature inside MomentModel (modeling.py:159-165) and decides argmax / 0.5-ratio /
+        # beam top-k outcomes there, and the tower is tiny (13.3 GFLOP per query), so accuracy is worth 3x its GEMM work.
+        # precise=False: plain bf16 GEMMs + bf16 attention (rel. error ~8e-3), the north_star's bf16 wording.
+        self.precise = bool(precise)
         self._engine = None
         self._engine_key = None
 
     def _key(self):
-        p = self.positional_embedding
-        return (p.device, p.data_ptr(), tuple(q._version for q in self.parameters()))
+        return _param_key(self.parameters()) + (self.precise,)
+
+    def invalidate(self):
+        self._engine = None
+        self._engine_key = None
 
     def _get_engine(self):
         key = self._key()
@@ -236,10 +256,13 @@ class TextTransformer(_ParamTree):
         dev = self.positional_embedding.device
         if dev.type != "cuda":
             raise RuntimeError("hirest_b200: the text tower runs on a B200 only (no CPU fallback)")
+        for q in self.parameters():
+            if q.dtype != torch.float32:
+                raise RuntimeError("hirest_b200: parameters must be fp32 (the engine keeps its own bf16 copies)")
         lib = _lib.init(dev.index or 0)
         t = self.cfg
         W, L = t["width"], t["layers"]
-        cfg = _lib.HbTextConfig(t["context_length"], t["vocab_size"], W, t["heads"], L, self.embed_dim, 1e-5)
+        cfg = _lib.HbTextConfig(t["context_length"], t["vocab_size"], W, t["heads"], L, self.embed_dim, 1e-5, 1 if self.precise else 0)
         sd = {k: v.detach().contiguous() for k, v in self.state_dict().items()}
         keep = []
 
@@ -273,6 +296,9 @@ class TextTransformer(_ParamTree):
         if text.device != dev:
             raise RuntimeError(f"input is on {text.device}, model on {dev}")
         ids = text.to(torch.int64).contiguous()
+        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self.vocab_size):
+            # nn.Embedding raises on out-of-range ids (eva_model.py:233); the device kernel would clamp them silently
+            raise IndexError(f"token id out of range [0, {self.vocab_size})")
         out = torch.empty((ids.shape[0], self.embed_dim), dtype=torch.float32, device=dev)
         lib = _lib.load()
         with torch.cuda.device(dev):
@@ -285,13 +311,13 @@ class EVA_CLIP(nn.Module):
     """Drop-in for EVA_clip/eva_model.py:273-334 (inference surface)."""
 
     def __init__(self, embed_dim: int, vision_cfg: dict, text_cfg: dict, quick_gelu: bool = False,
-                 max_image_batch: int = 1024, max_text_batch: int = 512):
+                 max_image_batch: int = 1024, max_text_batch: int = 512, precise_text: bool = True):
         super().__init__()
         if quick_gelu:
             raise NotImplementedError("quick_gelu is not used by EVA_CLIP_g_14 (eva_model.py:289)")
         vision_cfg = {k: v for k, v in dict(vision_cfg).items()}
         self.visual = VisionTransformer(embed_dim, vision_cfg, max_batch=max_image_batch)
-        self.text = TextTransformer(embed_dim, dict(text_cfg), max_batch=max_text_batch)
+        self.text = TextTransformer(embed_dim, dict(text_cfg), max_batch=max_text_batch, precise=precise_text)
 
     def encode_image(self, image):
         return self.visual(image)

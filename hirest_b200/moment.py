@@ -19,7 +19,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from .eva_clip import _Engine, _ParamTree
+from .eva_clip import _Engine, _ParamTree, _param_key
 
 _DEFAULTS = dict(embed_dim=512, hidden=768, heads=12, ffn=3072, max_pos_visual=2048, max_pos_decoder=512, vocab=30522, clip_dim=1024)
 
@@ -101,9 +101,7 @@ class MomentModel(nn.Module):
         self.args = args if args is not None else default_args()
         self.n_frames = n_frames
         self.asr_dim = asr_dim
-        self.use_asr = asr_dim > 0
-        if not self.use_asr:
-            raise NotImplementedError("hirest_b200.MomentModel: the ASR-free variant (asr_dim <= 0) is not implemented")
+        self.use_asr = asr_dim > 0   # modeling.py:28-35: asr_dim <= 0 builds no asr_enc_layer and ignores batch['asr_feats']
         vl = getattr(self.args, "visual_num_hidden_layers", 2)
         dl = getattr(self.args, "decoder_num_hidden_layers", 2)
         self.visual_layers = vl
@@ -155,7 +153,7 @@ class MomentModel(nn.Module):
 
     def _get_engine(self, rows: int, batch: int):
         ps = self._own_params()
-        key = (self._device(), ps[0].data_ptr(), tuple(q._version for q in ps), self.max_rows, self.max_batch)
+        key = _param_key(ps) + (self.max_rows, self.max_batch)
         if self._engine is not None and key == self._engine_key and rows <= self.max_rows and batch <= self.max_batch:
             return self._engine
         self.max_rows, self.max_batch = max(self.max_rows, rows), max(self.max_batch, batch)
@@ -177,9 +175,10 @@ class MomentModel(nn.Module):
 
         v = "clip4cap_model.visual."
         e = v + "encoder.layer.{}."
+        asr_ptrs = [sd[k].data_ptr() if self.use_asr else None
+                    for k in ("asr_enc_layer.0.weight", "asr_enc_layer.0.bias", "asr_enc_layer.1.weight", "asr_enc_layer.1.bias")]
         w = _lib.HbMomentWeights(
-            sd["asr_enc_layer.0.weight"].data_ptr(), sd["asr_enc_layer.0.bias"].data_ptr(), sd["asr_enc_layer.1.weight"].data_ptr(),
-            sd["asr_enc_layer.1.bias"].data_ptr(), sd["temporal_embed.0.weight"].data_ptr(), sd["temporal_embed.0.bias"].data_ptr(),
+            *asr_ptrs, sd["temporal_embed.0.weight"].data_ptr(), sd["temporal_embed.0.bias"].data_ptr(),
             sd["temporal_embed.2.weight"].data_ptr(), sd["temporal_embed.2.bias"].data_ptr(), sd["mask_embed.weight"].data_ptr(),
             sd["boundary_embed.weight"].data_ptr(), head_w.data_ptr(), head_b.data_ptr(),
             sd["clip4cap_model.normalize_video.visual_norm2d.weight"].data_ptr(),
@@ -197,13 +196,13 @@ class MomentModel(nn.Module):
             per_layer(e + "output.dense.weight"), per_layer(e + "output.dense.bias"),
             per_layer(e + "output.LayerNorm.weight"), per_layer(e + "output.LayerNorm.bias"))
         d = _DEFAULTS
-        cfg = _lib.HbMomentConfig(d["embed_dim"], d["hidden"], d["heads"], d["ffn"], L, self.asr_dim, d["clip_dim"], d["max_pos_visual"])
+        cfg = _lib.HbMomentConfig(d["embed_dim"], d["hidden"], d["heads"], d["ffn"], L, max(0, self.asr_dim), d["clip_dim"], d["max_pos_visual"])
         handle = C.c_void_p()
         with torch.cuda.device(dev):
             _lib.check(lib.hb_moment_create(C.byref(cfg), C.byref(w), int(self.max_rows), int(self.max_batch), _lib.stream_ptr(dev),
                                             C.byref(handle)), "hb_moment_create")
         self._engine = _Engine(handle, lib.hb_moment_destroy)
-        self._engine_key = (self._device(), ps[0].data_ptr(), tuple(q._version for q in ps), self.max_rows, self.max_batch)
+        self._engine_key = _param_key(ps) + (self.max_rows, self.max_batch)
         return self._engine
 
     @torch.no_grad()
@@ -216,7 +215,8 @@ class MomentModel(nn.Module):
         feats = torch.empty((B, T, _DEFAULTS["hidden"]), dtype=torch.float32, device=dev) if want_feats else None
         lib = _lib.load()
         with torch.cuda.device(dev):
-            _lib.check(lib.hb_moment_forward(eng.handle, video.data_ptr(), text_feat.data_ptr(), asr.data_ptr(), vmask.data_ptr(),
+            _lib.check(lib.hb_moment_forward(eng.handle, video.data_ptr(), text_feat.data_ptr(),
+                                             asr.data_ptr() if asr is not None else None, vmask.data_ptr(),
                                              mmask.data_ptr(), bmask.data_ptr() if bmask is not None else None, B, T,
                                              1 if reuse_base else 0, feats.data_ptr() if want_feats else None, logits.data_ptr(),
                                              _lib.stream_ptr(dev)), "hb_moment_forward")
@@ -226,7 +226,7 @@ class MomentModel(nn.Module):
         dev = self._device()
         video = batch["vis_feats"].to(dev).float().contiguous()
         vmask = batch["vis_mask"].to(dev).long().contiguous()
-        asr = batch["asr_feats"].to(dev).float().contiguous()
+        asr = batch["asr_feats"].to(dev).float().contiguous() if self.use_asr else None
         text_feat = self.clip_model.encode_text(batch["clip_text_ids"].to(dev)).float().contiguous()
         return video, vmask, asr, text_feat
 
@@ -237,7 +237,7 @@ class MomentModel(nn.Module):
         if video_mask is None:
             video_mask = torch.ones((B, T), dtype=torch.long, device=dev)
         _, feats = self._forward(video_feats.to(dev).float().contiguous(), text_feat.to(dev).float().contiguous(),
-                                 asr_feats.to(dev).float().contiguous(), video_mask.to(dev).long().contiguous(),
+                                 asr_feats.to(dev).float().contiguous() if self.use_asr else None, video_mask.to(dev).long().contiguous(),
                                  moment_mask.to(dev).long().contiguous(),
                                  boundary_mask.to(dev).long().contiguous() if boundary_mask is not None else None, want_feats=True)
         return feats
@@ -290,7 +290,7 @@ class MomentModel(nn.Module):
     # ------------------------------------------------------------------ step captioning
     def _get_decoder(self, n_inst: int, beam: int):
         ps = self._own_params()
-        key = (self._device(), ps[0].data_ptr(), tuple(q._version for q in ps))
+        key = _param_key(ps)
         cap = getattr(self, "_dec_cap", (0, 0))
         if getattr(self, "_dec_engine", None) is not None and key == self._dec_key and n_inst <= cap[0] and beam <= cap[1]:
             return self._dec_engine
@@ -399,18 +399,22 @@ class MomentModel(nn.Module):
         return str(" ".join(toks).replace(" ##", "").strip("##").strip())
 
     @torch.no_grad()
-    def test_step_captioning(self, batch, **kwargs):
-        """modeling.py:556-632."""
+    def caption_token_ids(self, batch, num_beams: int = 5):
+        """The device part of modeling.py:556-613: trim to the moment, shared encoder, beam search -> best-hypothesis token ids."""
         dev = self._device()
         video, vmask, asr, text_feat = self._inputs(batch)
         mmask = batch["moment_mask"].to(dev).long().contiguous()
         B = video.shape[0]
         video = self.trim_feats(video, mmask)
-        asr = self.trim_feats(asr, mmask)
+        asr = self.trim_feats(asr, mmask) if self.use_asr else None
         ones = torch.ones((B, self.args.max_frames), dtype=torch.long, device=dev)
         _, feats = self._forward(video, text_feat, asr, ones, ones, want_feats=True)
-        beam_size = kwargs.get("num_beams", 5)
-        ids = self.generate_caption_ids(feats, beam_size)
+        return self.generate_caption_ids(feats, num_beams)
+
+    @torch.no_grad()
+    def test_step_captioning(self, batch, **kwargs):
+        """modeling.py:556-632."""
+        ids = self.caption_token_ids(batch, kwargs.get("num_beams", 5))
         return {"prediction": [self.ids_to_text(x) for x in ids], "token_ids": ids}
 
     @torch.no_grad()

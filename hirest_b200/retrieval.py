@@ -67,16 +67,64 @@ def shard_range(n_items: int, rank: int, world: int):
     return lo, min(n_items, lo + per)
 
 
-def all_gather_embeddings(local_hat: torch.Tensor, group=None) -> torch.Tensor:
-    """The one collective of the path: all-gather of L2-normalised video embeddings (equal shard sizes)."""
+class PendingGather:
+    """Handle of an all-gather in flight (see all_gather_embeddings(..., async_op=True)); ``wait()`` makes the current stream wait
+    for it and returns the gathered [n_total, E] embeddings in global video order."""
+
+    def __init__(self, work, out, sizes, per):
+        self._work, self._out, self._sizes, self._per = work, out, sizes, per
+
+    def wait(self) -> torch.Tensor:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        out, sizes, per = self._out, self._sizes, self._per
+        total = sum(sizes)
+        if all(n == per for n in sizes[:-1]) or total == 0:
+            # full blocks followed by at most one short block, then empty ones: the valid rows are a prefix
+            full = 0
+            for n in sizes:
+                if n != per:
+                    break
+                full += 1
+            if sum(sizes[full + 1:]) == 0:
+                return out[:total]
+        return torch.cat([out[r * per:r * per + n] for r, n in enumerate(sizes) if n > 0], dim=0)
+
+
+def all_gather_embeddings(local_hat: torch.Tensor, group=None, n_total: Optional[int] = None, async_op: bool = False):
+    """The one collective of the path: all-gather of the L2-normalised video embeddings over NCCL (gloo in the CPU tests).
+
+    Shards may be UNEQUAL (4282 validation videos over 8 ranks = 7 x 536 + 530, or trailing empty shards): every rank pads its
+    block to the common size, one ``all_gather_into_tensor`` moves the padded blocks, and the padding is dropped afterwards.
+    ``n_total`` = the global number of videos when the shards are the contiguous blocks of ``shard_range`` (no extra
+    communication); without it the per-rank sizes are exchanged first (one tiny all-gather + a host sync).
+    ``async_op=True`` returns a PendingGather: the collective runs on the communicator's stream while the caller keeps
+    enqueueing compute (bench.py overlaps the gather of step i with the encoder of step i+1)."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return local_hat
-    world = dist.get_world_size(group)
-    out = torch.empty((world * local_hat.shape[0], local_hat.shape[1]), dtype=local_hat.dtype, device=local_hat.device)
-    dist.all_gather_into_tensor(out, local_hat.contiguous(), group=group)
-    return out
+        return PendingGather(None, local_hat, [local_hat.shape[0]], local_hat.shape[0]) if async_op else local_hat
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n_local, E = local_hat.shape
+    if n_total is not None:
+        sizes = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
+        if sizes[rank] != n_local:
+            raise ValueError(f"rank {rank} holds {n_local} embeddings, shard_range({n_total}, {rank}, {world}) says {sizes[rank]}")
+    else:
+        cnt = torch.tensor([n_local], dtype=torch.int64, device=local_hat.device)
+        all_cnt = torch.empty((world,), dtype=torch.int64, device=local_hat.device)
+        dist.all_gather_into_tensor(all_cnt, cnt, group=group)
+        sizes = [int(x) for x in all_cnt.tolist()]
+    per = max(sizes)
+    block = local_hat.contiguous()
+    if n_local != per:
+        block = torch.zeros((per, E), dtype=local_hat.dtype, device=local_hat.device)
+        block[:n_local].copy_(local_hat)
+    out = torch.empty((world * per, E), dtype=local_hat.dtype, device=local_hat.device)
+    work = dist.all_gather_into_tensor(out, block, group=group, async_op=async_op)
+    pend = PendingGather(work if async_op else None, out, sizes, per)
+    return pend if async_op else pend.wait()
 
 
 def rank_videos(scores_row: Sequence[float], video_names: Sequence[str]) -> List[int]:
@@ -96,10 +144,40 @@ def topk(scores: torch.Tensor, video_names: Optional[Sequence[str]], k: int) -> 
 
 
 @torch.no_grad()
-def encode_and_score(model, frames: torch.Tensor, n_frames: int, text_hat: torch.Tensor, exact: bool = True, group=None):
+def encode_and_score(model, frames: torch.Tensor, n_frames: int, text_hat: torch.Tensor, exact: bool = True, group=None,
+                     n_total: Optional[int] = None):
     """One retrieval step: encode this rank's frames, mean-pool per video, L2-normalise, all-gather, score.
     frames: [V_local * n_frames, 3, S, S]; text_hat: [Q, E] normalised queries. Returns (scores [Q, V_total], v_hat)."""
-    emb = model.encode_image(frames)
-    v_hat = pool_normalize(emb, n_frames)
-    v_all = all_gather_embeddings(v_hat, group)
+    v_all = all_gather_embeddings(encode_videos(model, frames, n_frames), group, n_total=n_total)
     return similarity(text_hat, v_all, exact=exact), v_all
+
+
+@torch.no_grad()
+def encode_videos(model, frames: torch.Tensor, n_frames: int) -> torch.Tensor:
+    """This rank's frames [V_local * n_frames, 3, S, S] -> L2-normalised video embeddings [V_local, E]
+    (inference_video_retrieval.py:270-285: encode_image, view(B, F, E), mean over F, / norm)."""
+    return pool_normalize(model.encode_image(frames), n_frames)
+
+
+@torch.no_grad()
+def retrieve(model, frames: torch.Tensor, n_frames: int, text_hat: torch.Tensor, n_total: Optional[int] = None, group=None,
+             chunk_videos: int = 32, exact: bool = True, ks: Sequence[int] = (1, 5, 10, 50)):
+    """BASELINE configs[2] as ONE job (inference_video_retrieval.py:257-334 without the file I/O): this rank encodes its contiguous
+    block of whole videos chunk by chunk, ONE all-gather of the [V/R, E] embeddings at the end, then the similarity GEMM and the
+    top-k lists.  frames: uint8 or fp32 [V_local * n_frames, 3, S, S] (host pinned or device; host chunks are copied on the
+    current stream).  Returns (scores [Q, V_total], topk {k: int64 [Q, k]}, v_all)."""
+    dev = text_hat.device
+    V_local = frames.shape[0] // n_frames
+    E = text_hat.shape[1]
+    v_hat = torch.empty((V_local, E), dtype=torch.float32, device=dev)
+    for v0 in range(0, V_local, chunk_videos):
+        v1 = min(V_local, v0 + chunk_videos)
+        chunk = frames[v0 * n_frames:v1 * n_frames]
+        if chunk.device != dev:
+            chunk = chunk.to(dev, non_blocking=True)
+        v_hat[v0:v1] = encode_videos(model, chunk, n_frames)
+    v_all = all_gather_embeddings(v_hat, group, n_total=n_total)
+    scores = similarity(text_hat, v_all, exact=exact)
+    kmax = min(max(ks), scores.shape[1])
+    order = torch.topk(scores, kmax, dim=1, largest=True, sorted=True).indices   # ranking only; ties: see rank_videos / topk()
+    return scores, {k: order[:, :min(k, kmax)] for k in ks}, v_all

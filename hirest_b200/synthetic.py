@@ -249,3 +249,28 @@ def make_moment_batch(B: int, T: int, seed: int = 5, ragged: bool = True, cfg: d
     return {"vis_feats": vis, "vis_mask": vis_mask, "asr_feats": asr, "moment_mask": moment_mask,
             "moment_bound_frames": bounds, "text_feat": text_feat, "n_frames": n,
             "clip_text_ids": torch.zeros((B, 77), dtype=torch.int64)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# encode_text -> MomentModel chain (tests/golden/chain.pt, oracle/make_golden_chain.py)
+# ---------------------------------------------------------------------------------------------------
+CHAIN_CLIP = {"embed_dim": 1024, "vision_cfg": dict(EVA_TINY["vision_cfg"]), "text_cfg": dict(EVA_G14["text_cfg"])}
+
+
+def make_chain_clip_state_dict(device="cpu"):
+    """EVA_CLIP state dict for the chain tests: tiny visual tower (MomentModel never calls encode_image), EVA-CLIP-g/14 text
+    tower with the same seeded weights as make_eva_state_dict(EVA_G14)['text.*']."""
+    sd = OrderedDict()
+    for k, v in make_visual_state_dict(CHAIN_CLIP, 0, device).items():
+        sd["visual." + k] = v
+    for k, v in make_text_state_dict(EVA_G14, 1, device).items():
+        sd["text." + k] = v
+    return sd
+
+
+def make_chain_batch(B: int, T: int, seed: int):
+    """make_moment_batch with real CLIP token rows (the prompt of each clip) instead of the zero placeholder."""
+    batch = make_moment_batch(B, T, seed=seed)
+    batch["clip_text_ids"] = make_tokens(B, EVA_G14, seed=seed + 100)
+    del batch["text_feat"]
+    return batch

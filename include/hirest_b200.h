@@ -134,6 +134,8 @@ typedef struct {
   int layers;         /* 12 */
   int embed_dim;      /* 1024 */
   float ln_eps;       /* 1e-5 */
+  int precise;        /* != 0: fp32-accurate path (3-term split-bf16 GEMMs, fp32 LayerNorm / attention / residual): encode_text
+                         within ~1e-5 of the fp32 reference, ~3x the (tiny) GEMM work.  0: plain bf16 GEMMs + bf16 attention. */
 } HbTextConfig;
 
 typedef struct {
@@ -163,7 +165,7 @@ typedef struct {
   int heads;      /* 12, head_dim must be 64 */
   int ffn;        /* 3072 */
   int layers;     /* 2    (args.py:53) */
-  int asr_dim;    /* 384 */
+  int asr_dim;    /* 384; 0 = ASR-free model (modeling.py:28-35): asr_* weights and the asr argument may be NULL */
   int clip_dim;   /* 1024 */
   int max_pos;    /* rows of visual.embeddings.position_embeddings (2048) */
 } HbMomentConfig;

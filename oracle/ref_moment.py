@@ -66,19 +66,29 @@ class _StubClip(torch.nn.Module):
         raise RuntimeError("replace encode_text before use")
 
 
-def build_reference_moment_model(num_beams=3):
+def build_reference_moment_model(num_beams=3, clip_cfg=None, asr_dim=384):
+    """clip_cfg=None: clip_model is a stub whose encode_text the caller replaces by fixed features.  clip_cfg=dict: clip_model
+    is the reference's own EVA_CLIP(**clip_cfg) (EVA_clip/eva_model.py:273, unmodified code, random init -- the caller loads
+    seeded weights), so test_step runs the reference text tower on real clip_text_ids (modeling.py:286,364,568)."""
     dst = prepare_copy()
     install_stubs()
     os.chdir(dst)
     for p in (dst, os.path.join(dst, "clip4caption"), os.path.join(dst, "EVA_clip")):
         if p not in sys.path:
             sys.path.insert(0, p)
-    # stand-in for the EVA build (eva_clip.build_eva_model_and_transforms, modeling.py:117)
-    _mod("eva_clip", build_eva_model_and_transforms=lambda *a, **k: (_StubClip(), None))
+    # stand-in for the EVA build (eva_clip.build_eva_model_and_transforms, modeling.py:117): the checkpoint file it would read
+    # (pretrained_weights/eva_clip_psz14.pt, 4.5 GB) does not exist offline
+    if clip_cfg is None:
+        build = lambda *a, **k: (_StubClip(), None)  # noqa: E731
+    else:
+        import eva_model  # /root/reference/EVA_clip/eva_model.py
+
+        build = lambda *a, **k: (eva_model.EVA_CLIP(**clip_cfg), None)  # noqa: E731
+    _mod("eva_clip", build_eva_model_and_transforms=build)
     import args as ref_args
     import modeling as ref_modeling
 
     a = ref_args.get_parser().parse_args(["--data_dir", "x", "--video_feature_dir", "x", "--num_beams", str(num_beams)])
     torch.manual_seed(0)
-    model = ref_modeling.MomentModel(n_frames=-1, asr_dim=384, args=a).eval()
+    model = ref_modeling.MomentModel(n_frames=-1, asr_dim=asr_dim, args=a).eval()
     return model, a

@@ -37,9 +37,9 @@ def test_error_strings_without_device():
 
 
 def test_struct_layouts_match_header():
-    # 7 ints + 1 float / 6 ints + 1 float, natural alignment; pointer-only weight structs
+    # 7 ints + 1 float / 6 ints + 1 float + 1 int, natural alignment; pointer-only weight structs
     assert ctypes.sizeof(_lib.HbVitConfig) == 32
-    assert ctypes.sizeof(_lib.HbTextConfig) == 28
+    assert ctypes.sizeof(_lib.HbTextConfig) == 32
     assert ctypes.sizeof(_lib.HbVitWeights) == 21 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_lib.HbTextWeights) == 17 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_lib.HbProfileSummary) == 6 * 8 * 3

@@ -40,6 +40,43 @@ def test_sharded_scores_equal_single_process(tmp_path):
         assert torch.equal(got, ref)
 
 
+UNEQUAL_CASES = [(V, wt, ua) for V in (7, 1, 4) for wt in (True, False) for ua in (False, True)]
+
+
+def _worker_unequal(rank, world, port, out_dir, Vs):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    for n, (V, with_total, use_async) in enumerate(Vs):
+        full = torch.randn(V, 16, generator=torch.Generator().manual_seed(1))
+        lo, hi = retrieval.shard_range(V, rank, world)
+        got = retrieval.all_gather_embeddings(full[lo:hi].clone(), n_total=V if with_total else None, async_op=use_async)
+        if use_async:
+            got = got.wait()
+        torch.save(got.clone(), os.path.join(out_dir, f"g_{n}_{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _check_unequal(tmp_path, world, cases):
+    for n, (V, with_total, use_async) in enumerate(cases):
+        full = torch.randn(V, 16, generator=torch.Generator().manual_seed(1))
+        for r in range(world):
+            assert torch.equal(torch.load(os.path.join(str(tmp_path), f"g_{n}_{r}.pt")), full), (V, with_total, use_async, r)
+
+
+def test_all_gather_with_unequal_and_empty_shards(tmp_path):
+    """V % world != 0 (4282 videos on 8 ranks = 7 x 536 + 530) and trailing empty shards (V = 1 on 2 ranks)."""
+    mp.spawn(_worker_unequal, args=(2, 30500 + os.getpid() % 1000, str(tmp_path), UNEQUAL_CASES), nprocs=2, join=True)
+    _check_unequal(tmp_path, 2, UNEQUAL_CASES)
+
+
+def test_all_gather_three_ranks_short_last_block(tmp_path):
+    cases = [(5, True, False), (5, False, True), (2, True, False)]   # per = 2: shards 2, 2, 1; per = 1: shards 1, 1, 0
+    mp.spawn(_worker_unequal, args=(3, 31500 + os.getpid() % 1000, str(tmp_path), cases), nprocs=3, join=True)
+    _check_unequal(tmp_path, 3, cases)
+
+
 def test_feature_store_shards_reassemble(tmp_path):
     """Every rank reads only its own contiguous block of videos from the packed store (retrieval.shard_range); the blocks tile
     the store exactly, in order — host logic, no GPU."""

@@ -13,10 +13,11 @@ from oracle import eva_oracle
 
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
-TOL_TINY_IMAGE = 1e-2    # relative L2, 3 layers
-TOL_TINY_TEXT = 2e-2
-TOL_G14_IMAGE = 2e-2     # relative L2, 40 layers (stock bf16 torch: ~1.6e-2)
-TOL_G14_TEXT = 2e-2
+# Caps = ~1.3x the measured values (fixed 2e-2 caps would have let a 2x regression through).
+TOL_TINY_IMAGE = 5.7e-3  # relative L2, 3 layers; measured 4.3e-3 (bf16 GEMM operands, fp32 residual stream)
+TOL_TINY_TEXT = 1e-4     # precise text tower (split-bf16 GEMMs, fp32 attention): measured ~1e-5; the bf16 tower measured 8.1e-3
+TOL_G14_IMAGE = 9e-3     # relative L2, 40 layers; measured 6.6e-3 (stock bf16 torch on the same box: ~1.8e-2)
+TOL_G14_TEXT = 1e-4      # measured ~1e-5
 
 
 def rel(a, b):
