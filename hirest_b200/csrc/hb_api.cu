@@ -36,6 +36,12 @@ int g_ln_fold = 1;   // fold the ViT block LayerNorms into the QKV / fc1 GEMM ep
 int g_num_sms = 148;
 bool g_inited = false;
 
+int vit_attn_dispatch(const hb::AttnParams& ap, cudaStream_t s) {
+  if (g_attn_version == 1) return hb::vit_attn_launch(ap, s);
+  if (g_attn_version == 2) return hb::vit_attn2_launch(ap, s);
+  return hb::vit_attn3_launch(ap, g_num_sms, s);
+}
+
 int fail(int code, const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -377,7 +383,7 @@ int hb_set_gemm_resid_prefetch_chunks(int k) {
 }
 
 int hb_set_attention_version(int v) {
-  if (v != 1 && v != 2) return fail(HB_ERR_INVALID, "attention version must be 1 or 2");
+  if (v < 1 || v > 3) return fail(HB_ERR_INVALID, "attention version must be 1, 2 or 3");
   g_attn_version = v;
   return HB_OK;
 }
@@ -532,7 +538,7 @@ static int vit_encode_chunk(HbVit* m, const float* frames, const uint8_t* frames
       if ((r = run_gemm(m->xb.tm, L.qkv, M, qkv, 3 * D, hb::EPI_BF16_LN, s, nullptr, qscale, D, nullptr, 0, 0, 0, &lf1, sched))) return r;
       hb::AttnParams ap;
       ap.qkv = qkv; ap.out = m->h.ptr(); ap.B = B; ap.H = c.heads; ap.prefetch_ahead = g_attn_prefetch ? 2 * g_num_sms : 0;
-      HB_LAUNCH_P(CAT_VIT_ATTN, 4.0 * B * c.heads * 257.0 * 257.0 * 88.0, s, g_attn_version == 1 ? hb::vit_attn_launch(ap, s) : hb::vit_attn2_launch(ap, s));
+      HB_LAUNCH_P(CAT_VIT_ATTN, 4.0 * B * c.heads * 257.0 * 257.0 * 88.0, s, vit_attn_dispatch(ap, s));
       if ((r = run_gemm(m->h.tm, L.proj, M, x, D, hb::EPI_F32_STATS, s, x, 1.f, 0, nullptr, 0, 0, 0, &lp2, sched))) return r;
       if ((r = run_gemm(m->xb.tm, L.fc1, M, m->hid.ptr(), F, hb::EPI_GELU_BF16_LN, s, nullptr, 1.f, 0, nullptr, 0, 0, 0, &lf2, sched))) return r;
       if ((r = run_gemm(m->hid.tm, L.fc2, M, x, D, hb::EPI_F32_STATS, s, x, 1.f, 0, nullptr, 0, 0, 0, &lp1, sched))) return r;
@@ -549,7 +555,7 @@ static int vit_encode_chunk(HbVit* m, const float* frames, const uint8_t* frames
     if ((r = run_gemm(m->h.tm, L.qkv, M, qkv, 3 * D, hb::EPI_BF16, s, nullptr, qscale, D, nullptr, 0, 0, 0, nullptr, sched))) return r;
     hb::AttnParams ap;
     ap.qkv = qkv; ap.out = m->h.ptr(); ap.B = B; ap.H = c.heads; ap.prefetch_ahead = g_attn_prefetch ? 2 * g_num_sms : 0;
-    HB_LAUNCH_P(CAT_VIT_ATTN, 4.0 * B * c.heads * 257.0 * 257.0 * 88.0, s, g_attn_version == 1 ? hb::vit_attn_launch(ap, s) : hb::vit_attn2_launch(ap, s));
+    HB_LAUNCH_P(CAT_VIT_ATTN, 4.0 * B * c.heads * 257.0 * 257.0 * 88.0, s, vit_attn_dispatch(ap, s));
     if ((r = run_gemm(m->h.tm, L.proj, M, x, D, hb::EPI_F32, s, x, 1.f, 0, nullptr, 0, 0, 0, nullptr, sched))) return r;
     ln.w = L.n2w.ptr(); ln.b = L.n2b.ptr();
     HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, true, s));
@@ -926,7 +932,7 @@ int hb_vit_attention(const void* qkv, void* out, int64_t B, int H, void* stream)
   hb::AttnParams ap;
   ap.qkv = static_cast<const __nv_bfloat16*>(qkv); ap.out = static_cast<__nv_bfloat16*>(out);
   ap.B = static_cast<int>(B); ap.H = H;
-  HB_LAUNCH(g_attn_version == 1 ? hb::vit_attn_launch(ap, static_cast<cudaStream_t>(stream)) : hb::vit_attn2_launch(ap, static_cast<cudaStream_t>(stream)));
+  HB_LAUNCH(vit_attn_dispatch(ap, static_cast<cudaStream_t>(stream)));
   return HB_OK;
 }
 

@@ -19,6 +19,7 @@ struct AttnParams {
 };
 int vit_attn_launch(const AttnParams& p, cudaStream_t stream);   // v1: one CTA per (frame, head), P through smem
 int vit_attn2_launch(const AttnParams& p, cudaStream_t stream);  // v2: one CTA per 128-query tile, 2 CTAs/SM, P in TMEM
+int vit_attn3_launch(const AttnParams& p, int num_sms, cudaStream_t stream);  // v3: persistent CTA per SM, pipelined over (frame, head)
 
 // Generic small-sequence attention on CUDA cores (text tower, MomentModel encoder, caption decoder):
 //   q: bf16 [B, Tq, ldq] (+ head*64), k/v: bf16 [B, Tk, ldk], head_dim 64, scores = q.k * scale

@@ -679,15 +679,18 @@ int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t co
 }
 
 int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, const uint64_t dims[3], const uint64_t strides_bytes[2],
-                      const uint32_t box[3]) {
+                      const uint32_t box[3], int swizzle_bytes) {
   if (tmap_init() != 0) return -1;
   if ((reinterpret_cast<uintptr_t>(ptr) % 16) != 0 || strides_bytes[0] % 16 != 0 || strides_bytes[1] % 16 != 0) return -2;
   cuuint64_t d[3] = {dims[0], dims[1], dims[2]};
   cuuint64_t st[2] = {strides_bytes[0], strides_bytes[1]};
   cuuint32_t bx[3] = {box[0], box[1], box[2]};
   cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  if (swizzle_bytes != 128 && swizzle_bytes != 64 && swizzle_bytes != 0) return -3;
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), d, st, bx, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -(1000 + static_cast<int>(r));
 }

@@ -60,9 +60,10 @@ int tmap_init();
 // box = [box_rows, 64 cols], SWIZZLE_128B, zero fill out of bounds.
 int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
-// 3D bf16 tensor map (dims/strides innermost first; strides in bytes for dims 1,2), SWIZZLE_128B, zero OOB fill.
+// 3D bf16 tensor map (dims/strides innermost first; strides in bytes for dims 1,2), zero OOB fill;
+// swizzle_bytes 128 (default) / 64 / 0 = SWIZZLE_128B / SWIZZLE_64B / SWIZZLE_NONE.
 int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, const uint64_t dims[3], const uint64_t strides_bytes[2],
-                      const uint32_t box[3]);
+                      const uint32_t box[3], int swizzle_bytes = 128);
 
 // Rows of W one CTA loads per stage for cta-group size cg (box_rows for the W map).
 constexpr uint32_t gemm_w_box_rows(int cg) { return 256u / static_cast<uint32_t>(cg); }

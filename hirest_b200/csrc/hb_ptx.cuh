@@ -84,6 +84,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a system-dependent time; a warp that polls SEVERAL barriers uses this).
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug traps (launch error) after HB_WAIT_TIMEOUT_NS instead of hanging the GPU box.
 #ifndef HB_WAIT_TIMEOUT_NS
 #define HB_WAIT_TIMEOUT_NS 4000000000ull
@@ -158,6 +172,16 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const void* tmap, uint64_
       : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// 3D tiled STORE shared::cta -> global (bulk async group; out-of-bounds elements of the box are not written).
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // 2D tiled load issued by either CTA of a pair; complete_tx lands on the LEADER CTA's barrier
 // (peer bit 24 of the shared::cluster address cleared), data lands in the issuing CTA's smem.
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const void* tmap, uint64_t* bar, int c0, int c1) {
@@ -208,6 +232,17 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 //   bits [32,46) stride byte offset >> 4 (1024 B between 8-row groups)
 //   bits [46,48) version = 1 (Blackwell)
 //   bits [61,64) layout type: 2 = SWIZZLE_128B
+// Same for SWIZZLE_64B slabs: [rows][32 bf16] = rows x 64 B, 8-row groups 512 B apart, 16-byte chunk c of row r stored at chunk
+// (c ^ ((r >> 1) & 3))  (Swizzle<2,4,3>; what a TMA load with CU_TENSOR_MAP_SWIZZLE_64B and a 32-element inner box writes).
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);

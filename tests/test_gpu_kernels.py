@@ -81,14 +81,17 @@ def test_layernorm(hb, D, eps):
     assert rel(y16, ref) < 3e-3
 
 
-@pytest.fixture(params=[2, 1], ids=["attn_v2", "attn_v1"])
+ATTN_DEFAULT = 2
+
+
+@pytest.fixture(params=[3, 2, 1], ids=["attn_v3", "attn_v2", "attn_v1"])
 def attn_version(request, hb):
     _lib.check(hb.hb_set_attention_version(request.param))
     yield request.param
-    _lib.check(hb.hb_set_attention_version(2))
+    _lib.check(hb.hb_set_attention_version(ATTN_DEFAULT))
 
 
-@pytest.mark.parametrize("B,H", [(1, 1), (3, 4), (2, 16)])
+@pytest.mark.parametrize("B,H", [(1, 1), (3, 4), (2, 16), (40, 16)])
 def test_vit_attention(hb, attn_version, B, H):
     """vit_model.py:127-147 on [B,257,3*H*88] (q pre-scaled): all three code paths — tensor-core rows, extra key, extra query."""
     torch.manual_seed(B * 100 + H)
