@@ -6,17 +6,26 @@
 // init / dealloc, read K and V twice per (frame, head), had 10 warps per SM to hide latency with, and the CTA that also owned the
 // extra query row (token 256) did ~2x the CUDA-core work of its sibling.  Here:
 //   * a CTA loops over items (frame, head); a producer warp TMA-loads Q/K of item i+1 as soon as the S = Q.K^T MMAs of item i
-//     have retired and V of item i+1 as soon as the P.V MMAs have, so loads never sit on the critical path and K / V are read once;
+//     have retired and V of item i+1 as soon as the P.V MMAs have; K / V are read once per item, not once per query tile;
 //   * 16 softmax warps: both 128-query tiles of an item are in flight (TMEM 2 x 256 columns), TWO threads per query row
-//     (keys 0..127 / 128..255), so one tile's TMEM / MUFU latency hides behind 3 other warps of the same scheduler;
+//     (keys 0..127 / 128..255); the MMA warp polls one S -> P.V sequence per tile, and the tiles take turns in the MUFU-bound
+//     exp pass, so they settle half a period apart: one tile's exps overlap the other's P.V / output / dot products;
+//   * each thread computes its NEXT item's CUDA-core dot product while the tensor core runs its tile's P.V;
 //   * the row sum comes from the tensor core: column 88 of V (zero padding of the 96-wide operand) is set to 1.0, so
 //     O[:, 88] = sum_j bf16(P[:, j]) — exactly the normalisation of the bf16 P the tensor core multiplies, and no FADD chain;
 //   * the extra query row's P.V runs on the tensor core as O_x^T = V^T p_x (A = V as an MN-major operand, M = d, N = 16, into 16
-//     TMEM columns that are free once the tile's softmax has consumed them); its 256 scores and the extra KEY's score of every
-//     row are CUDA-core dot products split over all 512 softmax threads while the S MMAs run;
-//   * P is packed bf16 in TMEM (TS-form UMMA), V is an MN-major B operand (no transposes), as in v2.
+//     TMEM columns that are free once the tile's softmax has consumed them), per tile over that tile's 128 keys relative to
+//     the tile's own maximum, merged flash-attention style at the end; its 256 scores (half-1 threads: k_row . q_x) and the
+//     extra KEY's score of every row (half-0 threads: q_row . k_x) are CUDA-core dot products;
+//   * P is packed bf16 in TMEM (TS-form UMMA), V is an MN-major B operand (no transposes), as in v2;
 //   * the output leaves through a dense bf16 staging tile per 128-query tile and ONE TMA store (cp.async.bulk.tensor, box 88 x 128):
 //     thread-per-row 16-byte global stores touched 32 lines per instruction and backed the LSU pipe up for ~5k cycles per item.
+// Measured (1024 frames x 16 heads, profiles/r02_attention_v3.txt): 1.02 ms (v2) -> 0.73 ms per layer = 4.0 TB/s of algorithmic
+// traffic (61 % of the measured HBM peak).  What bounds it now: K / V are single-buffered (shared memory is full) and have two
+// consumers half a period apart, so a load window is ~half an item period while one SM's share of HBM bandwidth needs ~2/3 of
+// it; MUFU (4096 cycles per item) and the tensor pipe (~4300) are the next floors.  L2-prefetching the next item's boxes
+// (-DHB_A3_L2_PREFETCH) slows the TMEM loads of the max pass 4x and costs 20 %; lock-step tiles (-DHB_A3_NO_TURNS) and dot
+// products at the end of the item (-DHB_A3_DOTS_LATE) are within 2 % of the default.
 // TMEM per tile (256 columns): S fp32 [0,256); P (bf16x2) keys 0..127 -> [0,64) (ascending, behind the reader), keys 128..255 ->
 // [192,256) (that thread walks its S columns in DESCENDING order, so it too only overwrites columns it has consumed);
 // O d 0..95 -> [64,160) (column 152 = row sum); extra-query partial output [160,176).
@@ -110,20 +119,21 @@ __device__ __forceinline__ float ex2(float x) {
 }
 __device__ __forceinline__ void named_bar(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// Partial dot of one smem row of Q / K (88 bf16: columns 0..63 in a SWIZZLE_128B slab at `row0_addr`, columns 64..87 in a
-// SWIZZLE_64B slab at `row1_addr`; both addresses already point at the row) with an fp32 vector in smem: 16-byte chunks
-// [CH0, CH1) of the row's 11.
+// Partial dot of one smem row of Q / K (88 bf16: columns 0..63 in a SWIZZLE_128B slab, row at shared address `row0`; columns
+// 64..87 in a SWIZZLE_64B slab, row at `row1`) with an fp32 vector in smem: 16-byte chunks [CH0, CH1) of the row's 11.
+// (ld.shared through 32-bit shared addresses: C++ loads through the re-aligned dynamic-smem pointer compile to generic LD.E.128
+// with 64-bit address arithmetic and spilled pointers.)
 template <int CH0, int CH1>
-__device__ __forceinline__ float dot_row_part(uint32_t row0_addr, uint32_t row1_addr, int row, const float* vec) {
+__device__ __forceinline__ float dot_row_part(uint32_t row0, uint32_t row1, int row, const float* vec) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
   for (int ch = CH0; ch < CH1; ++ch) {
-    const uint32_t addr = (ch < 8) ? row0_addr + (static_cast<uint32_t>(ch ^ (row & 7)) << 4)
-                                   : row1_addr + (static_cast<uint32_t>((ch - 8) ^ ((row >> 1) & 3)) << 4);
-    const uint4 v = lds16(addr);
+    const uint32_t addr = (ch < 8) ? row0 + (static_cast<uint32_t>(ch ^ (row & 7)) << 4)
+                                   : row1 + (static_cast<uint32_t>((ch - 8) ^ ((row >> 1) & 3)) << 4);
+    const uint4 x = lds16(addr);
     const float4 k0 = *reinterpret_cast<const float4*>(vec + ch * 8), k1 = *reinterpret_cast<const float4*>(vec + ch * 8 + 4);
-    a0 = fmaf(bf_lo(v.x), k0.x, a0); a1 = fmaf(bf_hi(v.x), k0.y, a1); a2 = fmaf(bf_lo(v.y), k0.z, a2); a3 = fmaf(bf_hi(v.y), k0.w, a3);
-    a0 = fmaf(bf_lo(v.z), k1.x, a0); a1 = fmaf(bf_hi(v.z), k1.y, a1); a2 = fmaf(bf_lo(v.w), k1.z, a2); a3 = fmaf(bf_hi(v.w), k1.w, a3);
+    a0 = fmaf(bf_lo(x.x), k0.x, a0); a1 = fmaf(bf_hi(x.x), k0.y, a1); a2 = fmaf(bf_lo(x.y), k0.z, a2); a3 = fmaf(bf_hi(x.y), k0.w, a3);
+    a0 = fmaf(bf_lo(x.z), k1.x, a0); a1 = fmaf(bf_hi(x.z), k1.y, a1); a2 = fmaf(bf_lo(x.w), k1.z, a2); a3 = fmaf(bf_hi(x.w), k1.w, a3);
   }
   return (a0 + a1) + (a2 + a3);
 }
@@ -155,9 +165,9 @@ __global__ void __launch_bounds__(A3_THREADS, 1) vit_attn3_kernel(const __grid_c
       mbar_init(bars + B_V_FREE, 2);         // one tcgen05.commit per tile's P.V group
       mbar_init(bars + B_OX, 3);             // tile 0's warps 0..2 parked their share of the extra query row
       for (int t = 0; t < 2; ++t) {
-        mbar_init(bars + B_PX0 + t, 4);      // the tile's half-0 warps wrote p_x of their 128 keys
+        mbar_init(bars + B_PX0 + t, 4);      // the tile's half-1 warps wrote p_x of their 128 keys
         mbar_init(bars + B_S0 + t, 1);
-        mbar_init(bars + B_P0 + t, 8);
+        mbar_init(bars + B_P0 + t, 8);       // the tile's P is in TMEM (all 8 warps)
         mbar_init(bars + B_O0 + t, 1);
         mbar_init(bars + B_TF0 + t, 8);
       }
@@ -220,6 +230,26 @@ __global__ void __launch_bounds__(A3_THREADS, 1) vit_attn3_kernel(const __grid_c
             tma_load_3d(smem + V_OFF + slab * 32768 + half * 16384, &tmQKV, bars + B_V_FULL, slab * 64, 2 * p.H + h, row0 + half * 128);
       }
       __syncwarp();
+#ifdef HB_A3_L2_PREFETCH   // measured: harmful (0.73 -> 0.88 ms per layer; the TMEM loads of the max pass slow down 4x)
+      // Pull the NEXT item's boxes into L2 now.  At the HBM roofline one SM's share of the bandwidth (6.5 TB/s / 148 = 44 GB/s)
+      // needs the whole item period to deliver an item's 160 KiB, but the shared-memory buffers are only free for part of it
+      // (Q / K from "S retired" to the next item's dot products, V from "P.V retired" to the next P.V): with the lines already
+      // in L2 the TMA loads complete in L2 time and DRAM streams all the time.
+      const int nitem = item + static_cast<int>(gridDim.x);
+      if (nitem < n_items && elect_one()) {
+        const int nb = nitem / p.H, nh = nitem - nb * p.H, nrow0 = nb * T_TOK;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          tma_prefetch_3d(&tmQKV, 0, nh, nrow0 + half * 128);
+          tma_prefetch_3d(&tmQK1, 64, nh, nrow0 + half * 128);
+          tma_prefetch_3d(&tmQKV, 0, p.H + nh, nrow0 + half * 128);
+          tma_prefetch_3d(&tmQK1, 64, p.H + nh, nrow0 + half * 128);
+          tma_prefetch_3d(&tmQKV, 0, 2 * p.H + nh, nrow0 + half * 128);
+          tma_prefetch_3d(&tmQKV, 64, 2 * p.H + nh, nrow0 + half * 128);
+        }
+      }
+      __syncwarp();
+#endif
     }
   } else if (warp == 17) {
     // ================================================================== MMA issue
@@ -266,9 +296,11 @@ __global__ void __launch_bounds__(A3_THREADS, 1) vit_attn3_kernel(const __grid_c
           stage[t] = 1;
           progressed = true;
         } else {
+          // (P.V cannot start before the whole exp pass has finished: its accumulator lives in S columns [64,160), which the two
+          // halves consume last.)
           if (!mbar_test_wait(bar0 + 8 * B_V_FULL, ph)) continue;
-          if (!mbar_test_wait(bar0 + 8 * (B_PX0 + t), ph)) continue;
           if (!mbar_test_wait(bar0 + 8 * (B_P0 + t), ph)) continue;
+          if (!mbar_test_wait(bar0 + 8 * (B_PX0 + t), ph)) continue;
           A3_STAMP(2, 7 + 2 * t);
           if (ones_it != it) {
             // ones column: V[key, 88] = 1.0 (bf16 0x3F80) in the zero padding of slab 1 -> O[:, 88] = row sum of P
@@ -303,9 +335,9 @@ __global__ void __launch_bounds__(A3_THREADS, 1) vit_attn3_kernel(const __grid_c
           }
           __syncwarp();
           A3_STAMP(2, 8 + 2 * t);
+          progressed = true;
           stage[t] = 0;
           it_t[t] = it + 1;
-          progressed = true;
         }
       }
       if (!progressed) {
@@ -320,69 +352,63 @@ __global__ void __launch_bounds__(A3_THREADS, 1) vit_attn3_kernel(const __grid_c
     const int hf = (warp >> 2) & 1;        // 0: keys 0..127, 1: keys 128..255
     const int wq = warp & 3;               // TMEM lane quarter
     const int r = wq * 32 + lane;          // row inside the tile
-    const int row = tile * 128 + r;        // query row of this thread; also the KEY this thread scores for the extra query
+    const int row = tile * 128 + r;        // query row of this thread; also the KEY a half-1 thread scores for the extra query
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + static_cast<uint32_t>(tile * 256);
-    const uint32_t qrow0 = sbase + Q_OFF + static_cast<uint32_t>(tile) * Q_TILE + static_cast<uint32_t>(r >> 3) * 1024u +
-                           static_cast<uint32_t>(r & 7) * 128u;
-    const uint32_t qrow1 = sbase + Q_OFF + static_cast<uint32_t>(tile) * Q_TILE + Q_S1 + static_cast<uint32_t>(r >> 3) * 512u +
-                           static_cast<uint32_t>(r & 7) * 64u;
-    const uint32_t krow0 = sbase + K_OFF + static_cast<uint32_t>(row >> 3) * 1024u + static_cast<uint32_t>(row & 7) * 128u;
-    const uint32_t krow1 = sbase + K_OFF + K_S1 + static_cast<uint32_t>(row >> 3) * 512u + static_cast<uint32_t>(row & 7) * 64u;
+    const uint32_t t_s = t_row + static_cast<uint32_t>(hf * 128);
+    // CUDA-core dot product of this thread: half 0 -> extra KEY's score of its query row (q_row . k_x, needed by both halves
+    // after the first pass); half 1 -> extra QUERY's score of key `row` (k_row . q_x)
+    const uint32_t drow0 = hf == 0 ? sbase + Q_OFF + static_cast<uint32_t>(tile * Q_TILE + (r >> 3) * 1024 + (r & 7) * 128)
+                                   : sbase + K_OFF + static_cast<uint32_t>((row >> 3) * 1024 + (row & 7) * 128);
+    const uint32_t drow1 = hf == 0 ? sbase + Q_OFF + static_cast<uint32_t>(tile * Q_TILE + Q_S1 + (r >> 3) * 512 + (r & 7) * 64)
+                                   : sbase + K_OFF + K_S1 + static_cast<uint32_t>((row >> 3) * 512 + (row & 7) * 64);
+    const int drow = hf == 0 ? r : row;
     const uint32_t stage_row = sbase + ST_OFF + static_cast<uint32_t>(tile) * ST_TILE + static_cast<uint32_t>(r) * (DH * 2);
+    float* redt = red + tile * 16;
     bool store_pending = false;   // this thread issued a TMA store whose smem source has not been waited for yet
-    int it = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const uint32_t ph = it & 1;
-      const int b = item / p.H, h = item - b * p.H;
-      __nv_bfloat16* og = p.out + static_cast<size_t>(b) * T_TOK * ldo + h * DH;
-      const float* kx = xt + (it & 1) * 288;
-      const float* vx = kx + 96;
-      const float* qx = kx + 192;
-
-      // ---- extra key (every row) and extra query (every key): CUDA-core dots, 88 dims split between the two halves
+    const int my_items = (n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 #ifdef HB_ATTN_TIMING
-      const int trole = (warp == 0) ? 0 : (warp == 8 ? 1 : -1);
+    const int trole = (warp == 0) ? 0 : (warp == 8 ? 1 : -1);
 #define A3_SSTAMP(k) do { if (trole >= 0) A3_STAMP(trole, k); } while (0)
 #else
 #define A3_SSTAMP(k) do { } while (0)
 #endif
-      A3_SSTAMP(0);
-      mbar_wait(bars + B_QK_FULL, ph);
-      A3_SSTAMP(1);
-      float sxp, ep;
-      if (hf == 0) {
-        sxp = dot_row_part<0, 6>(qrow0, qrow1, r, kx);
-        ep = dot_row_part<0, 6>(krow0, krow1, row, qx);
-      } else {
-        sxp = dot_row_part<6, 11>(qrow0, qrow1, r, kx);
-        ep = dot_row_part<6, 11>(krow0, krow1, row, qx);
-      }
-      xs[hf * 256 + row] = sxp;
-      xe[hf * 256 + row] = ep;
-      float e_self = qx[lane] * kx[lane] + qx[lane + 32] * kx[lane + 32] + (lane < DH - 64 ? qx[lane + 64] * kx[lane + 64] : 0.f);
+
+    // dot(it): this thread's CUDA-core dot product for item `it` (+ the extra token's own score q_x . k_x, per warp)
+    float dotv = 0.f, e_self_next = 0.f;
+    auto dots = [&](int it) {
+      mbar_wait(bars + B_QK_FULL, it & 1);
+      const float* kx = xt + (it & 1) * 288;
+      const float* qx = kx + 192;
+      dotv = dot_row_part<0, 11>(drow0, drow1, drow, hf == 0 ? kx : qx);
+      float es = qx[lane] * kx[lane] + qx[lane + 32] * kx[lane + 32] + (lane < DH - 64 ? qx[lane + 64] * kx[lane + 64] : 0.f);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) e_self += __shfl_xor_sync(0xffffffffu, e_self, o);
+      for (int o = 16; o > 0; o >>= 1) es += __shfl_xor_sync(0xffffffffu, es, o);
+      e_self_next = es;
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars + B_QK_FREE);
-      A3_SSTAMP(2);
-      named_bar(1 + tile, 256);
-      A3_SSTAMP(3);
-      const float s_x = xs[row] + xs[256 + row];
-      const float e = xe[row] + xe[256 + row];
-      float* redt = red + tile * 16;
-      {
+      if (lane == 0) mbar_arrive(bars + B_QK_FREE);   // this warp is done with the Q / K rows in shared memory
+    };
+    if (my_items > 0) dots(0);
+
+    for (int it = 0; it < my_items; ++it) {
+      const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+      const uint32_t ph = it & 1;
+      const int b = item / p.H, h = item - b * p.H;
+      __nv_bfloat16* og = p.out + static_cast<size_t>(b) * T_TOK * ldo + h * DH;
+      const float* vx = xt + (it & 1) * 288 + 96;
+      const float e_self = e_self_next;
+      A3_SSTAMP(0);
+
+      // ---- extra query, half-1 threads: softmax numerators over THIS tile's 128 keys relative to the tile's own maximum m_t
+      // (the two tiles' partial results are merged at the end, flash-attention style, so the tiles never wait for each other)
+      float m_t = 0.f;
+      if (hf == 1) {
+        const float e = dotv;
         float wm = e;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
-        if (lane == 0) redt[warp & 7] = wm;
-      }
-      named_bar(1 + tile, 256);
-      // softmax numerators of the extra query over THIS tile's 128 keys, relative to the tile's own maximum m_t; the two tiles'
-      // partial results are merged at the end (flash-attention style), so the tiles never wait for each other here
-      float m_t = redt[0];
-#pragma unroll
-      for (int i = 1; i < 8; ++i) m_t = fmaxf(m_t, redt[i]);
-      if (hf == 0) {
+        if (lane == 0) redt[wq] = wm;
+        named_bar(3 + tile, 128);
+        m_t = fmaxf(fmaxf(redt[0], redt[1]), fmaxf(redt[2], redt[3]));
         // p_x rounded to bf16: the tensor core multiplies exactly these values, so the normaliser sums the same ones.
         // B operand of the O_x MMA: row 0 of a [16 x 256] K-major SWIZZLE_128B tile (row 0 is not permuted by the swizzle)
         const __nv_bfloat16 pkb = __float2bfloat16(ex2((e - m_t) * LOG2E));
@@ -394,14 +420,15 @@ __global__ void __launch_bounds__(A3_THREADS, 1) vit_attn3_kernel(const __grid_c
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + B_PX0 + tile);
+      } else {
+        xs[row] = dotv;   // extra key's score of this row, for both halves (read after the pair barrier below)
       }
+      A3_SSTAMP(1);
 
       // ---- pass 1: row maximum over this thread's 128 keys
-      A3_SSTAMP(4);
       mbar_wait(bars + B_S0 + tile, ph);
-      A3_SSTAMP(5);
+      A3_SSTAMP(2);
       tc_fence_after();
-      const uint32_t t_s = t_row + static_cast<uint32_t>(hf * 128);
       float m = -INFINITY;
       {
         uint32_t v[32];
@@ -421,39 +448,53 @@ __global__ void __launch_bounds__(A3_THREADS, 1) vit_attn3_kernel(const __grid_c
       xm[(tile * 2 + hf) * 128 + r] = m;
       // the previous item's TMA store has finished reading the staging tile before anyone of the pair writes it again
       if (store_pending) { tma_store_wait_read(); store_pending = false; }
-      A3_SSTAMP(6);
+      A3_SSTAMP(3);
       named_bar(1 + tile, 256);
-      A3_SSTAMP(7);
+      A3_SSTAMP(4);
+      const float s_x = xs[row];
       m = fmaxf(fmaxf(m, xm[(tile * 2 + (hf ^ 1)) * 128 + r]), s_x);
       const float m2 = m * LOG2E;
 
       // ---- pass 2: P = exp(S - m) as packed bf16 back into TMEM, over S columns this thread has already consumed:
       // half 0 walks S[0,128) upwards and writes P chunk c at [16c, 16c+16); half 1 walks S[128,256) DOWNWARDS and writes P chunk
       // c at [192+16c, 192+16c+16) -- so [64,192) is free for O and the extra-query partial when the P.V MMAs start.
+      // The pass is MUFU-bound (65536 ex2 per item at 16 per clock per SM = 4096 cycles), so the two tiles take turns: tile 1
+      // starts its pass when tile 0 has finished, tile 0's next pass follows tile 1's; the tiles settle half a period apart.
+#ifndef HB_A3_NO_TURNS
+      if (tile == 1) mbar_wait(bars + B_P0, ph);
+      else if (it > 0) mbar_wait(bars + B_P1, (it - 1) & 1);
+#endif
       {
         uint32_t v[32];
+        tmem_ld_32x32(t_s + (hf ? 3 : 0) * 32, v);
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           const int c = hf ? 3 - cc : cc;
-          tmem_ld_32x32(t_s + c * 32, v);
           tmem_ld_wait();
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             pk[j] = pack_bf16x2(ex2(fmaf(__uint_as_float(v[2 * j]), LOG2E, -m2)), ex2(fmaf(__uint_as_float(v[2 * j + 1]), LOG2E, -m2)));
           tmem_st_32x16(t_row + static_cast<uint32_t>(hf * 192 + c * 16), pk);
+          if (cc < 3) tmem_ld_32x32(t_s + (hf ? 2 - cc : cc + 1) * 32, v);   // next chunk's S while this chunk's P store drains
         }
       }
-      const float p_x = ex2(fmaf(s_x, LOG2E, -m2));
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + B_P0 + tile);
-      A3_SSTAMP(8);
+      const float p_x = ex2(fmaf(s_x, LOG2E, -m2));
+      A3_SSTAMP(5);
+
+      // ---- while the tensor core runs this tile's P.V: the NEXT item's dot products (its Q / K landed long ago)
+#ifndef HB_A3_DOTS_LATE
+      if (it + 1 < my_items) dots(it + 1);
+#endif
+      A3_SSTAMP(6);
 
       // ---- output: (O + the extra key's rank-1 term) / row sum -> dense bf16 staging tile -> one TMA store per tile
       mbar_wait(bars + B_O0 + tile, ph);
-      A3_SSTAMP(9);
+      A3_SSTAMP(7);
       tc_fence_after();
       uint32_t ox_raw = 0;
       {
@@ -473,7 +514,6 @@ __global__ void __launch_bounds__(A3_THREADS, 1) vit_attn3_kernel(const __grid_c
           tmem_ld_32x32(t_row + 64, v);
           tmem_ld_32x16(t_row + 96, w);
           const uint32_t su = tmem_ld_32x1(t_row + 152);
-          if (wq < 3) ox_raw = tmem_ld_32x1(t_row + 160);   // extra-query partial, lanes = d
           tmem_ld_wait();
           inv = 1.0f / (__uint_as_float(su) + p_x);
           pxi = p_x * inv;
@@ -484,6 +524,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) vit_attn3_kernel(const __grid_c
         } else {         // d 48..63: columns [112,128); d 64..87: columns [128,152); row sum: column 152 = v[24]
           tmem_ld_32x16(t_row + 112, w);
           tmem_ld_32x32(t_row + 128, v);
+          if (wq < 3) ox_raw = tmem_ld_32x1(t_row + 160);   // extra-query partial, lanes = d
           tmem_ld_wait();
           inv = 1.0f / (__uint_as_float(v[24]) + p_x);
           pxi = p_x * inv;
@@ -493,6 +534,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) vit_attn3_kernel(const __grid_c
           for (int jj = 0; jj < 3; ++jj) pack8(v + jj * 8, 64 + jj * 8);
         }
       }
+      // (read before the TF arrive below: once both tiles have drained TMEM the producer may refill this xt buffer two items on)
+      const float vx_r = (hf == 1 && r < DH) ? vx[r] : 0.f;
       // the tile's TMEM columns are drained: S of the next item may start while the store is being staged
       tc_fence_before();
       __syncwarp();
@@ -504,16 +547,15 @@ __global__ void __launch_bounds__(A3_THREADS, 1) vit_attn3_kernel(const __grid_c
         tma_store_commit();
         store_pending = true;
       }
-      A3_SSTAMP(10);
-      // ---- extra query row (token 256): O_x^T partials in TMEM (lanes = d, column 224 of each tile), over each tile's 128 keys
+      A3_SSTAMP(8);
+      // ---- extra query row (token 256): O_x^T partials in TMEM (lanes = d, column 160 of each tile), over each tile's 128 keys
       // relative to that tile's maximum.  Tile 0 parks (partial, m_0, sum_0) in smem; tile 1 merges both with the extra key's own
-      // term and stores the row.  Warps with hf == 0 and wq < 3: lanes cover d = 0..95.
-      if (hf == 0 && wq < 3) {
-        const uint32_t ox = ox_raw;
+      // term and stores the row.  Half-1 warps with wq < 3: lanes cover d = 0..95.
+      if (hf == 1 && wq < 3) {
         const float sum_t = (redt[8] + redt[9]) + (redt[10] + redt[11]);
         float* park = oxs + (it & 1) * 128;
         if (tile == 0) {
-          park[r] = __uint_as_float(ox);
+          park[r] = __uint_as_float(ox_raw);
           if (r == 0) { park[96] = m_t; park[97] = sum_t; }
           __syncwarp();
           if (lane == 0) mbar_arrive(bars + B_OX);
@@ -524,12 +566,14 @@ __global__ void __launch_bounds__(A3_THREADS, 1) vit_attn3_kernel(const __grid_c
           const float f0 = ex2((m_0 - M) * LOG2E), f1 = ex2((m_t - M) * LOG2E), fs = ex2((e_self - M) * LOG2E);
           const float tot = fmaf(sum_0, f0, fmaf(sum_t, f1, fs));
           if (r < DH) {
-            const float o = fmaf(park[r], f0, fmaf(__uint_as_float(ox), f1, fs * vx[r]));
+            const float o = fmaf(park[r], f0, fmaf(__uint_as_float(ox_raw), f1, fs * vx_r));
             og[static_cast<size_t>(TQ) * ldo + r] = __float2bfloat16(o / tot);
           }
         }
       }
-      A3_SSTAMP(11);
+#ifdef HB_A3_DOTS_LATE
+      if (it + 1 < my_items) dots(it + 1);
+#endif
     }
     if (store_pending) tma_store_wait_all();
   }

@@ -46,8 +46,9 @@ HB_API const char* hb_strerror(int code);
 HB_API int64_t hb_launch_count(void);
 /* cta_group used by the GEMMs: 2 (CTA pairs, default) or 1. */
 HB_API int hb_set_gemm_cta_group(int cg);
-/* ViT attention kernel: 2 (default: one CTA per 128-query tile, two CTAs per SM, P kept in TMEM) or 1 (one CTA per
- * (frame, head), P staged through shared memory). Same results up to bf16 rounding of the output. */
+/* ViT attention kernel: 3 (default: one persistent CTA per SM pipelined over (frame, head) items, TMA-store output), 2 (one CTA
+ * per 128-query tile, two CTAs per SM, P kept in TMEM) or 1 (one CTA per (frame, head), P staged through shared memory).
+ * Same results up to bf16 rounding of the output. */
 HB_API int hb_set_attention_version(int v);
 /* Attention v2: every CTA L2-prefetches the Q / K / V boxes of the CTA one wave (2 x #SMs blocks) ahead (1) or not (0, default:
  * measured slower, 1.05 -> 1.14 ms per layer; kept as an A/B knob). */

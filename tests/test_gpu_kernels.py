@@ -81,7 +81,7 @@ def test_layernorm(hb, D, eps):
     assert rel(y16, ref) < 3e-3
 
 
-ATTN_DEFAULT = 2
+ATTN_DEFAULT = 3
 
 
 @pytest.fixture(params=[3, 2, 1], ids=["attn_v3", "attn_v2", "attn_v1"])

@@ -27,12 +27,12 @@ int main(int argc, char** argv) {
   std::vector<long long> t(tn);
   cudaMemcpy(t.data(), tim, tn * 8, cudaMemcpyDeviceToHost);
   const int items_per_cta = (B * H) / sms;
-  const char* sn[12] = {"start", "wait QK_FULL", "dots + arrive QK_FREE", "barrier #1 (512)", "e softmax + barrier #2 + p_x", "wait S", "pass 1 (max)",
-                        "pair barrier", "pass 2 (exp, P) + arrive", "wait O", "output stores", "extra row + TF arrive"};
+  const char* sn[12] = {"start (prev: extra row)", "e softmax (half 1) / s_x", "wait S", "pass 1 (max)", "pair barrier (+store wait)",
+                        "turn wait + pass 2 (exp, P)", "next item's dots (wait QK_FULL)", "wait O", "output + stage + TMA store", "", "", ""};
   const char* mn[11] = {"start", "wait QK_FULL", "wait TF0", "issue S0", "wait TF1", "issue S1", "wait V_FULL + ones", "wait P0/PX", "issue PV0+x", "wait P1", "issue PV1"};
   const char* pn[4] = {"start", "x loads + wait QK_FREE", "issue QK", "wait V_FREE"};
   for (int role = 0; role < 4; ++role) {
-    const int ns = role < 2 ? 12 : (role == 2 ? 11 : 4);
+    const int ns = role < 2 ? 9 : (role == 2 ? 11 : 4);
     std::vector<double> acc(16, 0.0);
     double period = 0; int cnt = 0, pc = 0;
     for (int c = 0; c < sms; ++c)
