@@ -50,6 +50,15 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tiny", action="store_true", help="debug: tiny config instead of EVA-CLIP-g/14")
+    ap.add_argument("--config", default="step", choices=["step", "retrieval", "moment", "e2e"],
+                    help="step (default, the driver's line): BASELINE configs[1]-shaped step per GPU; retrieval / moment / e2e: "
+                         "BASELINE configs[2] / [3] / [4] as whole jobs (tools/bench_extra.py)")
+    ap.add_argument("--no-check", action="store_true", help="N > 1: skip the sharded-vs-single-GPU equality check after the timed region")
+    ap.add_argument("--videos-per-gpu", type=int, default=512, help="--config retrieval: videos per rank (x 32 frames)")
+    ap.add_argument("--clips-per-gpu", type=int, default=64, help="--config moment: clips per rank per step")
+    ap.add_argument("--clip-frames", type=int, default=300, help="--config moment: frames per clip")
+    ap.add_argument("--videos", type=int, default=256, help="--config e2e: videos in the whole job")
+    ap.add_argument("--beam", type=int, default=3)
     return ap.parse_args()
 
 
@@ -162,6 +171,11 @@ def main():
 
     cfg = synthetic.EVA_TINY if args.tiny else synthetic.EVA_G14
     model_name = "EVA-TINY(debug)" if args.tiny else "EVA-CLIP-g/14"
+    if args.config != "step":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_extra
+
+        return bench_extra.main(args, cfg, model_name, ClockSampler, load_peaks)
 
     # ------------------------------------------------------------------ reference arm: CPU oracle port
     if args.impl == "reference":
@@ -232,11 +246,33 @@ def main():
         text_hat = retrieval.normalize(model.encode_text(tokens_all))
     tokens_step = tokens_all[:new_q].contiguous()
 
-    def step_device():
+    V_total = world * (B // Fv)
+    pending = [None]   # all-gather of the previous step's video embeddings, still in flight
+
+    def score_pending():
+        """Scores of the step whose all-gather is in flight (None if there is none)."""
+        if pending[0] is None:
+            return None
+        v_all = pending[0].wait()
+        pending[0] = None
+        return retrieval.similarity(text_hat, v_all, exact=True)
+
+    def step_device(frames=None):
+        """One step: re-encode `new_q` queries, encode + pool this rank's frames, START the all-gather of the normalised video
+        embeddings, and score the PREVIOUS step's gathered embeddings.  Deferring the scoring by one step takes the collective
+        off the critical path: with an in-line gather every step ended in a rank barrier, so the step time was the max over
+        (power-capped, jittering) ranks (r01: 0.983 efficiency at 8 GPUs); now a rank only ever waits for a gather its peers
+        started a whole step earlier.  `drain()` scores the last step; both are inside every timed region."""
         t_new = retrieval.normalize(model.encode_text(tokens_step))
         text_hat[:new_q].copy_(t_new)
-        scores, _ = retrieval.encode_and_score(model, frames_dev, Fv, text_hat, exact=True)
+        v_hat = retrieval.encode_videos(model, frames_dev if frames is None else frames, Fv)
+        nxt = retrieval.all_gather_embeddings(v_hat, n_total=V_total, async_op=True)
+        scores = score_pending()
+        pending[0] = nxt
         return scores
+
+    def drain():
+        return score_pending()
 
     def barrier():
         if world > 1:
@@ -258,6 +294,7 @@ def main():
             sampler.start()
         for _ in range(args.warmup):
             step_device()
+        drain()
         barrier()
         mark0 = sampler.mark()
         launches0 = lib.hb_launch_count()
@@ -267,10 +304,11 @@ def main():
         e0.record()
         marks = []
         for _ in range(args.steps):
-            scores = step_device()
+            step_device()
             mk = torch.cuda.Event(enable_timing=True)
             mk.record()
             marks.append(mk)
+        scores = drain()
         e1.record()
         barrier()
         ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -340,20 +378,30 @@ def main():
                     tk = tokens_host.to(dev, non_blocking=True)
                     t_new = retrieval.normalize(model.encode_text(tk))
                     text_hat[:new_q].copy_(t_new)
-                    sc, _ = retrieval.encode_and_score(model, dev_bufs[i % 2], Fv, text_hat, exact=True)
+                    v_hat = retrieval.encode_videos(model, dev_bufs[i % 2], Fv)
                     ev = torch.cuda.Event()
                     ev.record(cur)
                     consumed[i % 2] = ev
-                    scores_host[i % 2].copy_(sc, non_blocking=True)
-                    done[i % 2] = torch.cuda.Event()
-                    done[i % 2].record(cur)
+                    nxt = retrieval.all_gather_embeddings(v_hat, n_total=V_total, async_op=True)
+                    sc = score_pending()          # scores of step i-1 (its gather has had a whole step to complete)
+                    pending[0] = nxt
+                    if sc is not None:
+                        scores_host[(i - 1) % 2].copy_(sc, non_blocking=True)
+                        done[(i - 1) % 2] = torch.cuda.Event()
+                        done[(i - 1) % 2].record(cur)
                     th1 = time.perf_counter()
-                    if i > 0:
-                        done[(i - 1) % 2].synchronize()   # the caller now holds the scores of step i-1 on the host
+                    if i > 1:
+                        done[(i - 2) % 2].synchronize()   # the caller now holds the scores of step i-2 on the host
                     host_ms.append((round((th1 - th0) * 1e3, 1), round((time.perf_counter() - th0) * 1e3, 1)))
+                sc = drain()
+                scores_host[(n - 1) % 2].copy_(sc, non_blocking=True)
+                done[(n - 1) % 2] = torch.cuda.Event()
+                done[(n - 1) % 2].record(torch.cuda.current_stream())
                 evl = torch.cuda.Event(enable_timing=True)
                 evl.record()
                 step_events.append(evl)
+                if n > 1:
+                    done[(n - 2) % 2].synchronize()
                 done[(n - 1) % 2].synchronize()
 
             run_e2e(max(2, min(args.warmup, 3)))
@@ -384,6 +432,29 @@ def main():
                    "input": "uint8 frames [B,3,224,224] in pinned host memory, normalised on the GPU; H2D double-buffered on a side stream",
                    "d2h_bytes_per_step": scores_host[0].numel() * 4, "ms_per_step": ms_e2e / args.steps}
 
+    # ------------------------------------------------------------------ multi-GPU correctness on the hardware (not timed)
+    check = None
+    if world > 1 and not args.no_check:
+        with torch.no_grad():
+            v_all = retrieval.all_gather_embeddings(retrieval.encode_videos(model, frames_dev, Fv), n_total=V_total)
+            sc_sharded = retrieval.similarity(text_hat, v_all, exact=True)
+            parts = []
+            for r in range(world):   # this rank alone over EVERY rank's frames (regenerated from their seeds)
+                fr = frames_dev if r == rank else synthetic.make_frames(B, S, seed=100 + r, device=dev)
+                parts.append(retrieval.encode_videos(model, fr, Fv))
+                del fr
+            sc_single = retrieval.similarity(text_hat, torch.cat(parts), exact=True)
+            ks = [k for k in (1, 5, 10, 50) if k <= V_total]
+            top_equal = all(torch.equal(sc_sharded.topk(k, dim=1).indices, sc_single.topk(k, dim=1).indices) for k in ks)
+            flags = torch.tensor([int(torch.equal(sc_sharded, sc_single)), int(torch.equal(v_all, torch.cat(parts))), int(top_equal)],
+                                 dtype=torch.int64, device=dev)
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+            check = {"what": f"scores [Q={Q}, V={V_total}] from {world} frame shards + NCCL all-gather vs the same videos encoded by one GPU "
+                             "alone (every rank checks; min over ranks)",
+                     "scores_bit_equal": bool(flags[0]), "gathered_embeddings_bit_equal": bool(flags[1]),
+                     "topk_equal": {"ks": ks, "equal": bool(flags[2])},
+                     "max_abs_diff": float((sc_sharded - sc_single).abs().max())}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -405,7 +476,7 @@ def main():
         "ms_per_step": ms_total / args.steps, "ms_steps": ms_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{model_name} frame encoder, {B}-frame batch per GPU ({B // Fv} videos x {Fv} frames) + mean-pool/L2-norm"
-                               f" + {'NCCL all-gather + ' if world > 1 else ''}cosine scores vs {Q} text queries ({new_q} re-encoded per step)",
+                               f" + {'NCCL all-gather (overlapped with the next step) + ' if world > 1 else ''}cosine scores vs {Q} text queries ({new_q} re-encoded per step)",
                    "frames_per_gpu_per_step": B, "frames_per_video": Fv, "queries": Q, "weights": "seeded random init (synthetic.py)",
                    "residual_stream": "fp32", "gemm_operands": "bf16, fp32 accumulate", "l2": "inputs_larger_than_l2",
                    "parallelism": f"frame-shard dp{world}" if world > 1 else "single GPU"},
@@ -419,6 +490,7 @@ def main():
         "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "check": check,
     }
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(cfg, args.cpu_frames, 2, 1, Fv, Q)

@@ -42,8 +42,52 @@ def frame_index_to_timestamp(frame_index: int, video_duration, n_frames: int = 3
 
 
 def _n_frames(video: dict, n_model_frames: int) -> int:
-    """hirest_dataset.py:149-152: fixed frame count, or one frame per second of video."""
+    """hirest_dataset.py:149-152: fixed frame count, or one frame per second of (rounded) video duration."""
     return n_model_frames if n_model_frames > 0 else int(video["video_duration"])
+
+
+def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
+    """Item indices of `rank`: torch's DistributedSampler(dataset, shuffle=False) as hirest_dataset.py:604-606 builds it
+    (round-robin rank::world over the index list padded to a multiple of world by wrapping around)."""
+    if world <= 1:
+        return list(range(n_items))
+    if n_items == 0:
+        return []
+    per = (n_items + world - 1) // world
+    total = per * world
+    idx = list(range(n_items))
+    while len(idx) < total:
+        idx += idx[:total - len(idx)]
+    return idx[rank:total:world]
+
+
+def all_gather_objects(obj, group=None) -> list:
+    """dist_utils.all_gather (dist_utils.py:145-179): every rank receives the list of every rank's picklable object, in rank order."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return [obj]
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, obj, group=group)
+    return out
+
+
+def _run_sharded(items: List[dict], run_batch, batch_size: int, rank: int, world: int, gather) -> List:
+    """Run `run_batch(chunk) -> list of per-item results` over this rank's items, gather every rank's (index, result) pairs and
+    return the per-item results in ITEM order (padding duplicates dropped).  (The reference extends the gathered lists in rank
+    order, run.py:645-662, which is equivalent for its dictionaries keyed by video and wrong for the caption lists; item order
+    is what the single-process run produces.)"""
+    mine = shard_indices(len(items), rank, world)
+    local = []
+    for c0 in range(0, len(mine), batch_size):
+        ids = mine[c0:c0 + batch_size]
+        res = run_batch([items[i] for i in ids])
+        local += list(zip(ids, res))
+    merged = {}
+    for part in gather(local):
+        for i, r in part:
+            merged.setdefault(i, r)
+    return [merged[i] for i in range(len(items))]
 
 
 def collate(items: Sequence[dict], n_model_frames: int = -1) -> dict:
@@ -81,22 +125,26 @@ def _base_item(video: dict, task: str, n_frames: int) -> dict:
             "video_mask": torch.ones(n_frames, dtype=torch.long)}
 
 
-def _batches(items: List[dict], batch_size: int):
-    for i in range(0, len(items), batch_size):
-        yield items[i:i + batch_size]
-
-
 @torch.no_grad()
 def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beams: int = 5, n_model_frames: int = -1,
-                   tokenize=None) -> Dict:
+                   tokenize=None, rank: int = 0, world: int = 1, group=None, gather=None) -> Dict:
     """Chain the three tasks over ``videos`` (dicts with ``prompt``, ``fname``, ``video_duration``, ``vis_feats [T,1024]``,
     ``asr_feats [T,384]``, ``clip_text_ids [77]``; order = dataset order).  Videos without ``clip_text_ids`` get them from
     ``tokenize(prompt) -> LongTensor[1, 77]`` (e.g. ``hirest_b200.tokenizer.tokenize``), as ``collate_fn`` does with
     ``clip.tokenize`` (hirest_dataset.py:528).  Returns
     ``{"final": {prompt: {fname: {"bounds", "steps": [{"index", "heading", "absolute_bounds"}]}}},
     "moment_retrieval": ..., "moment_segmentation": ..., "step_captioning": ...}`` with the per-task dictionaries the
-    reference dumps next to the final file."""
+    reference dumps next to the final file.
+
+    Multi-GPU: with ``world > 1`` every task's items are sharded over the ranks with DistributedSampler
+    semantics (``shard_indices``), each rank runs its share, and the per-item results are gathered as Python objects
+    (``all_gather_objects`` = dist_utils.all_gather; ``gather`` overrides it, e.g. to simulate ranks in one process), so every rank
+    returns the full dictionaries.  There is no tensor exchange on this path."""
     nmf = n_model_frames
+    if gather is None:
+        gather = (lambda obj: all_gather_objects(obj, group)) if world > 1 else (lambda obj: [obj])
+    # hirest_dataset.py:145: the dataset rounds the annotated duration once; everything downstream uses the rounded value
+    videos = [dict(v, video_duration=round(v["video_duration"])) for v in videos]
     if any("clip_text_ids" not in v for v in videos):
         if tokenize is None:
             raise ValueError("videos without 'clip_text_ids' need a tokenize callable (hirest_b200.tokenizer.tokenize)")
@@ -117,13 +165,12 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
         it["moment_mask"] = torch.ones(n, dtype=torch.long)
         items.append(it)
     mr: Dict[str, Dict[str, dict]] = {}
-    for chunk in _batches(items, batch_size):
-        pred = model.test_step(collate(chunk, nmf))["prediction"]
-        for it, (s, e) in zip(chunk, pred):
-            d = it["video_duration"]
-            mr.setdefault(it["prompt"], {})[it["fname"]] = {
-                "bounds": [frame_index_to_timestamp(s, d, n_frames=nmf), frame_index_to_timestamp(e, d, n_frames=nmf)],
-                "video_duration": d}
+    preds = _run_sharded(items, lambda chunk: model.test_step(collate(chunk, nmf))["prediction"], batch_size, rank, world, gather)
+    for it, (s, e) in zip(items, preds):
+        d = it["video_duration"]
+        mr.setdefault(it["prompt"], {})[it["fname"]] = {
+            "bounds": [frame_index_to_timestamp(s, d, n_frames=nmf), frame_index_to_timestamp(e, d, n_frames=nmf)],
+            "video_duration": d}
     # the rewritten test file (run.py:399-417): predicted bounds + five placeholder steps
     state: Dict[str, Dict[str, dict]] = {}
     for v in videos:
@@ -145,13 +192,12 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
         it["moment_mask"] = mm
         items.append(it)
     ms: Dict[str, dict] = {}
-    for chunk in _batches(items, batch_size):
-        pred = model.test_step(collate(chunk, nmf))["prediction"]
-        for it, raw in zip(chunk, pred):
-            d = it["video_duration"]
-            bounds = [[frame_index_to_timestamp(raw[j], d, n_frames=nmf), frame_index_to_timestamp(raw[j + 1], d, n_frames=nmf)]
-                      for j in range(len(raw) - 1)]
-            ms[it["fname"]] = {"bounds": bounds, "video_duration": d, "pred_bounds": raw}   # keyed by video only (run.py:757)
+    preds = _run_sharded(items, lambda chunk: model.test_step(collate(chunk, nmf))["prediction"], batch_size, rank, world, gather)
+    for it, raw in zip(items, preds):
+        d = it["video_duration"]
+        bounds = [[frame_index_to_timestamp(raw[j], d, n_frames=nmf), frame_index_to_timestamp(raw[j + 1], d, n_frames=nmf)]
+                  for j in range(len(raw) - 1)]
+        ms[it["fname"]] = {"bounds": bounds, "video_duration": d, "pred_bounds": raw}   # keyed by video only (run.py:757)
     for prompt in state:                                                                     # run.py:437-452
         for fname in state[prompt]:
             state[prompt][fname]["steps"] = [{"index": i, "heading": "", "absolute_bounds": b}
@@ -180,12 +226,12 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
             it["moment_mask"] = torch.ones(rows.numel(), dtype=torch.long)
             items.append(it)
     sc: Dict[str, dict] = {}
-    for chunk in _batches(items, batch_size):
-        pred = model.test_step(collate(chunk, -1), num_beams=num_beams)["prediction"]   # ragged (sliced) items: pad path
-        for it, sent in zip(chunk, pred):
-            e = sc.setdefault(it["fname"], {"captions": []})
-            e["captions"].append({"sentence": sent})
-            e["video_duration"] = it["video_duration"]
+    preds = _run_sharded(items, lambda chunk: model.test_step(collate(chunk, -1), num_beams=num_beams)["prediction"],   # ragged items: pad path
+                         batch_size, rank, world, gather)
+    for it, sent in zip(items, preds):
+        e = sc.setdefault(it["fname"], {"captions": []})
+        e["captions"].append({"sentence": sent})
+        e["video_duration"] = it["video_duration"]
     for prompt in state:                                                                     # run.py:466-472
         for fname in state[prompt]:
             if fname in sc:

@@ -100,3 +100,65 @@ def test_feature_store_shards_reassemble(tmp_path):
             names += st.video_ids[lo:hi]
         assert names == st.video_ids
         assert torch.equal(torch.cat(rows), torch.from_numpy(np.array(st.data)))
+
+
+class _FakeMoment:
+    """Deterministic, batch-independent stand-in for MomentModel.test_step (host logic test: sharding + gathering only)."""
+
+    def test_step(self, batch, **kw):
+        task = batch["tasks"][0]
+        n = batch["vis_mask"].sum(1).tolist()
+        key = [int(round(float(v[:k].sum()) * 1000)) for v, k in zip(batch["vis_feats"], n)]
+        if task == "moment_retrieval":
+            return {"prediction": [[1 + k % 3, nn - 2 - k % 2] for k, nn in zip(key, n)]}
+        if task == "moment_segmentation":
+            out = []
+            for k, (a, b) in zip(key, batch["moment_bound_frames"].tolist()):
+                step = 5 + k % 4
+                out.append(list(range(a, b + 1, step)) or [a])
+            return {"prediction": out}
+        return {"prediction": [f"cap-{k}-{nn}" for k, nn in zip(key, n)]}
+
+
+def _fake_videos(n=7):
+    g = torch.Generator().manual_seed(3)
+    vids = []
+    for i in range(n):
+        T = int(torch.randint(30, 60, (1,), generator=g))
+        vids.append({"prompt": f"p{i % 3}", "fname": f"v{i}", "video_duration": T + 0.4, "vis_feats": torch.randn(T, 8, generator=g),
+                     "asr_feats": torch.randn(T, 4, generator=g), "clip_text_ids": torch.zeros(77, dtype=torch.long)})
+    return vids
+
+
+def _worker_pipeline(rank, world, port, out_dir):
+    from hirest_b200 import pipeline
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = pipeline.run_end_to_end(_FakeMoment(), _fake_videos(), batch_size=2, num_beams=3, rank=rank, world=world)
+    torch.save(out, os.path.join(out_dir, f"e2e_{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_end_to_end_chain_equals_single_process(tmp_path):
+    """SURVEY.md §8(e), configs[3]/[4]: items sharded with DistributedSampler semantics (7 videos on 2 ranks: one padded duplicate),
+    results gathered as Python objects -> every rank holds the single-process result."""
+    from hirest_b200 import pipeline
+
+    assert pipeline.shard_indices(7, 0, 2) == [0, 2, 4, 6] and pipeline.shard_indices(7, 1, 2) == [1, 3, 5, 0]
+    assert pipeline.shard_indices(2, 2, 4) == [0] and pipeline.shard_indices(0, 1, 4) == [] and pipeline.shard_indices(5, 0, 1) == [0, 1, 2, 3, 4]
+    import torch.utils.data as tud
+
+    class _DS(tud.Dataset):
+        def __len__(self):
+            return 7
+
+    for r in range(3):   # the reference's sampler (hirest_dataset.py:604-606)
+        assert list(tud.distributed.DistributedSampler(_DS(), num_replicas=3, rank=r, shuffle=False)) == pipeline.shard_indices(7, r, 3)
+    ref = pipeline.run_end_to_end(_FakeMoment(), _fake_videos(), batch_size=2, num_beams=3)
+    assert all(isinstance(v["video_duration"], int) for p in ref["moment_retrieval"].values() for v in p.values())   # round(), dataset :145
+    mp.spawn(_worker_pipeline, args=(2, 32500 + os.getpid() % 1000, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert torch.load(os.path.join(str(tmp_path), f"e2e_{r}.pt")) == ref

@@ -1,0 +1,374 @@
+"""bench.py --config retrieval | moment | e2e: BASELINE.json configs[2] / [3] / [4] as whole jobs, same JSON contract as the
+default line (bench.py imports this module; it is not the driver's headline).
+
+  retrieval  configs[2]: 512 text queries x (videos-per-gpu x N) videos @ 32 frames; whole videos sharded over the ranks, every
+             rank encodes its block chunk by chunk, ONE all-gather of the [V/R, 1024] embeddings, one similarity GEMM, top-k.
+             metric: frames/s encoded+scored.  N > 1: a reduced job is re-run sharded and on one GPU and must agree bit for bit.
+  moment     configs[3]: MomentModel.test_step (moment retrieval + moment segmentation) on clips-per-gpu x 300-frame clips per
+             rank, text features from the repo's own (precise) EVA text tower; predictions gathered as Python objects.
+             metric: clips/s.  Rank 0's predictions are compared with the reference-generated golden (tests/golden/chain.pt).
+  e2e        configs[4]: the in-memory MR -> MS -> step-captioning chain (beam 3) on 256 synthetic videos, items sharded with
+             DistributedSampler semantics, results gathered as Python objects.  metric: videos/s.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def _init_dist(world, dev):
+    import torch
+    import torch.distributed as dist
+
+    if world <= 1:
+        return
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    sys.stdout.flush()
+    saved_fd = os.dup(1)
+    os.dup2(2, 1)   # NCCL's banner goes to stderr: stdout carries exactly one JSON line
+    try:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
+
+
+def _vocab_file():
+    v = [f"[unused{i}]" for i in range(30522)]
+    v[0], v[100], v[101], v[102], v[103] = "[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"
+    for i in range(1000, 30522):
+        v[i] = f"w{i}"
+    p = f"/tmp/hb_vocab_{os.getpid()}.txt"
+    with open(p, "w") as f:
+        f.write("\n".join(v) + "\n")
+    return p, v
+
+
+def _chain_model(dev, max_rows, max_batch, vocab_path=None):
+    """MomentModel whose clip_model is the repo's EVA_CLIP (EVA-CLIP-g/14 text tower, tiny visual tower), seeded weights."""
+    from hirest_b200 import eva_clip, moment, synthetic
+
+    clip = eva_clip.EVA_CLIP(**synthetic.CHAIN_CLIP, max_text_batch=max(64, max_batch))
+    clip.load_state_dict(synthetic.make_chain_clip_state_dict(), strict=True)
+    clip = clip.to(dev).eval()
+    kw = {"bert_vocab_path": vocab_path} if vocab_path else {}
+    m = moment.MomentModel(-1, 384, moment.default_args(**kw), clip_model=clip, max_rows=max_rows, max_batch=max_batch)
+    sd = synthetic.make_moment_state_dict(seed=3)
+    m.load_state_dict(sd, strict=False)
+    return m.to(dev), sd
+
+
+def main(args, cfg, model_name, ClockSampler, load_peaks):
+    import torch
+    import torch.distributed as dist
+
+    from hirest_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            print(json.dumps({"impl": "reference", "unavailable": f"--config {args.config}: the CPU baseline of this config is the "
+                                                                   "cpu_baseline object of the b200 line"}), flush=True)
+        return 0
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200 (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _init_dist(world, dev)
+    lib = _lib.init(local_rank)
+    ctx = {"rank": rank, "world": world, "dev": dev, "lib": lib, "torch": torch, "dist": dist, "peaks": load_peaks(),
+           "sampler": ClockSampler(local_rank)}
+    if rank == 0:
+        ctx["sampler"].start()
+    line = {"retrieval": _retrieval, "moment": _moment, "e2e": _e2e}[args.config](args, cfg, model_name, ctx)
+    ctx["sampler"].stop()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def _barrier(ctx):
+    if ctx["world"] > 1:
+        ctx["dist"].barrier()
+    ctx["torch"].cuda.synchronize()
+
+
+def _max_over_ranks(ctx, x):
+    if ctx["world"] == 1:
+        return x
+    torch = ctx["torch"]
+    t = torch.tensor([x], dtype=torch.float64, device=ctx["dev"])
+    ctx["dist"].all_reduce(t, op=ctx["dist"].ReduceOp.MAX)
+    return float(t.item())
+
+
+def _timed(ctx, fn, steps, warm_fn=None, warmup=0):
+    """K calls of fn bracketed by barrier + synchronize, CUDA events, max over ranks -> (total ms, clocks summary, last result)."""
+    torch = ctx["torch"]
+    for _ in range(warmup):
+        (warm_fn or fn)()
+    _barrier(ctx)
+    m0 = ctx["sampler"].mark()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx["lib"].hb_launch_count()
+    e0.record()
+    out = None
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    _barrier(ctx)
+    ms = _max_over_ranks(ctx, e0.elapsed_time(e1))
+    clocks = ctx["sampler"].summary(m0, ctx["sampler"].mark()) if ctx["rank"] == 0 else None
+    return ms, clocks, out, int(ctx["lib"].hb_launch_count() - launches0)
+
+
+# ------------------------------------------------------------------------------------------------------------- configs[2]
+def _retrieval(args, cfg, model_name, ctx):
+    torch, dist, dev, rank, world = ctx["torch"], ctx["dist"], ctx["dev"], ctx["rank"], ctx["world"]
+    from hirest_b200 import eva_clip, retrieval, synthetic
+
+    S, Fv, Q, E = cfg["vision_cfg"]["image_size"], args.frames_per_video, args.queries, cfg["embed_dim"]
+    Vl, chunk = args.videos_per_gpu, max(1, args.frames // Fv)
+    V = Vl * world
+    sd = synthetic.make_eva_state_dict(cfg, seed=0, device=dev)
+    model = eva_clip.EVA_CLIP(**cfg, max_image_batch=chunk * Fv, max_text_batch=128)
+    model.load_state_dict(sd, strict=True)
+    del sd
+    model = model.to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(300 + rank)
+    frames_dev = torch.randint(0, 256, (Vl * Fv, 3, S, S), generator=g, dtype=torch.uint8, device=dev)
+    tokens = synthetic.make_tokens(Q, cfg, seed=2)
+    tokens_dev = tokens.to(dev)
+
+    def job(frames, toks):
+        with torch.no_grad():
+            text_hat = retrieval.normalize(model.encode_text(toks.to(dev, non_blocking=True)))
+            return retrieval.retrieve(model, frames, Fv, text_hat, n_total=V, chunk_videos=chunk)
+
+    def warm():
+        with torch.no_grad():
+            model.encode_image(frames_dev[:chunk * Fv])
+
+    ms, clocks, out, launches = _timed(ctx, lambda: job(frames_dev, tokens_dev), args.steps, warm, max(3, args.warmup))
+    frames_job = V * Fv
+    value = frames_job * args.steps / (ms * 1e-3)
+    # e2e: frames in pinned host memory, copied chunk by chunk inside the job; scores + top-k lists read back to the host
+    e2e = None
+    if not args.no_e2e:
+        frames_host = torch.empty((Vl * Fv, 3, S, S), dtype=torch.uint8).pin_memory()
+        frames_host.copy_(frames_dev)
+        tokens_host = tokens.pin_memory()
+
+        def job_host():
+            scores, topk, _ = job(frames_host, tokens_host)
+            return scores.cpu(), {k: v.cpu() for k, v in topk.items()}
+
+        ms2, clocks2, out2, _ = _timed(ctx, job_host, args.steps, None, 0)
+        e2e = {"value": frames_job * args.steps / (ms2 * 1e-3), "unit": "frames/s", "ms_per_step": ms2 / args.steps,
+               "h2d_bytes_per_step": frames_host.numel() + tokens_host.numel() * 8,
+               "d2h_bytes_per_step": Q * V * 4 + sum(Q * min(k, V) * 8 for k in (1, 5, 10, 50)), "clocks": clocks2,
+               "input": "uint8 frames in pinned host memory, copied per 1024-frame chunk on the compute stream; token ids from the host"}
+        del frames_host
+    # N > 1: a reduced job (64 videos per rank) sharded vs the same videos on one GPU
+    check = None
+    if world > 1 and not args.no_check:
+        vc = min(64, Vl)
+        with torch.no_grad():
+            text_hat = retrieval.normalize(model.encode_text(tokens_dev))
+            sc_s, tk_s, v_s = retrieval.retrieve(model, frames_dev[:vc * Fv], Fv, text_hat, n_total=vc * world, chunk_videos=chunk)
+            parts = []
+            for r in range(world):
+                if r == rank:
+                    fr = frames_dev[:vc * Fv]
+                else:
+                    gr = torch.Generator(device=dev).manual_seed(300 + r)
+                    fr = torch.randint(0, 256, (Vl * Fv, 3, S, S), generator=gr, dtype=torch.uint8, device=dev)[:vc * Fv]
+                parts.append(retrieval.encode_videos(model, fr, Fv))
+                del fr
+            v_1 = torch.cat(parts)
+            sc_1 = retrieval.similarity(text_hat, v_1, exact=True)
+            ks = [k for k in (1, 5, 10, 50) if k <= vc * world]
+            flags = torch.tensor([int(torch.equal(sc_s, sc_1)), int(torch.equal(v_s, v_1)),
+                                  int(all(torch.equal(tk_s[k], sc_1.topk(k, dim=1).indices) for k in ks))], dtype=torch.int64, device=dev)
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        check = {"what": f"{vc} videos per rank x {world} ranks: sharded job (one all-gather) vs one GPU encoding all {vc * world} videos; "
+                         "every rank checks, min over ranks",
+                 "scores_bit_equal": bool(flags[0]), "embeddings_bit_equal": bool(flags[1]), "topk_equal": {"ks": ks, "equal": bool(flags[2])}}
+    if rank != 0:
+        return None
+    flops = synthetic.encode_image_flops(cfg) * frames_job / world   # per GPU per job
+    achieved = flops * args.steps / (ms * 1e-3) / 1e12
+    peaks = ctx["peaks"]
+    return {"metric": "frames/sec encoded+scored (EVA-CLIP-g/14 224px)", "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"video retrieval job (BASELINE configs[2]): {Q} text queries x {V} videos @ {Fv} frames = {frames_job} "
+                                   f"frames, {Vl} whole videos per GPU, ONE all-gather of the [V/R, {E}] fp32 embeddings, one similarity "
+                                   "GEMM (3-way split bf16, fp32-accurate), top-{1,5,10,50}",
+                       "videos": V, "frames_per_video": Fv, "queries": Q, "chunk_frames": chunk * Fv, "l2": "inputs_larger_than_l2",
+                       "warmup_unit": "one 1024-frame chunk", "parallelism": f"video-shard dp{world}" if world > 1 else "single GPU"},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                         "kernel": "whole job per GPU (encode_image FLOPs / job time)"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "check": check, "cpu_baseline": None}
+
+
+# ------------------------------------------------------------------------------------------------------------- configs[3]
+def _moment(args, cfg, model_name, ctx):
+    torch, dist, dev, rank, world = ctx["torch"], ctx["dist"], ctx["dev"], ctx["rank"], ctx["world"]
+    from hirest_b200 import pipeline, synthetic
+
+    B, T = args.clips_per_gpu, args.clip_frames
+    model, sd = _chain_model(dev, B * T, B)
+    batch = synthetic.make_chain_batch(B, T, seed=12 + rank)   # rank 0 = the batch of tests/golden/chain.pt["cfg4"]
+    batch_dev = {k: (v.to(dev) if torch.is_tensor(v) and k != "moment_bound_frames" else v) for k, v in batch.items()}
+
+    def step(b):
+        out = {}
+        for task in ("moment_retrieval", "moment_segmentation"):
+            bb = dict(b)
+            bb["tasks"] = [task] * B
+            out[task] = model.test_step(bb)["prediction"]
+        return out
+
+    ms, clocks, out, launches = _timed(ctx, lambda: step(batch_dev), args.steps, None, max(3, args.warmup))
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e = None
+    if not args.no_e2e:
+        host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in batch.items()}
+        ms2, clocks2, out2, _ = _timed(ctx, lambda: step(host), args.steps, None, 1)
+        h2d = sum(host[k].numel() * host[k].element_size() for k in ("vis_feats", "asr_feats", "vis_mask", "moment_mask", "clip_text_ids"))
+        e2e = {"value": world * B * args.steps / (ms2 * 1e-3), "unit": "clips/s", "ms_per_step": ms2 / args.steps,
+               "h2d_bytes_per_step": 2 * h2d, "d2h_bytes_per_step": B * 2 * 8 + B * 20 * 2 * 4 + B * 4, "clocks": clocks2,
+               "input": "collate dicts of CPU (pinned) tensors, as hirest_dataset.py:409-531 produces; test_step moves them (modeling.py:275-286)"}
+        assert out2 == out
+    gathered = pipeline.all_gather_objects(out)
+    check = {"gathered_ranks": len(gathered), "clips_gathered": sum(len(g["moment_retrieval"]) for g in gathered)}
+    gpath = os.path.join(ROOT, "tests", "golden", "chain.pt")
+    if rank == 0 and B == 64 and T == 300 and os.path.exists(gpath):
+        g = torch.load(gpath)["cfg4"]
+        check["rank0_mr_equals_reference_golden"] = out["moment_retrieval"] == g["mr_pred"]
+        check["rank0_ms_equals_reference_golden"] = out["moment_segmentation"] == g["ms_pred"]
+    if rank != 0:
+        return None
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import eva_oracle, moment_oracle as mo
+
+        nb = 2
+        torch.set_num_threads(os.cpu_count() or 1)
+        clip_sd = synthetic.make_chain_clip_state_dict()
+        cb = {k: (v[:nb] if torch.is_tensor(v) else v) for k, v in batch.items()}
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            tf = eva_oracle.encode_text(clip_sd, cb["clip_text_ids"], synthetic.CHAIN_CLIP)
+            mr = mo.test_moment_retrieval(sd, cb, tf)[0]
+            msr = mo.test_moment_segmentation(sd, cb, tf)
+        dt = time.perf_counter() - t0
+        cpu = {"value": nb / dt, "unit": "clips/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"first {nb} clips of the batch, encode_text + MR + MS, torch fp32 CPU",
+               "identical_to_gpu": mr == out["moment_retrieval"][:nb] and msr == out["moment_segmentation"][:nb]}
+    flops_clip = 9.874e9 * (T / 300.0) * 21 + 2 * 13.3e9   # 1 shared forward (MR) + 20 (MS) + encode_text twice
+    achieved = flops_clip * B * args.steps / (ms * 1e-3) / 1e12
+    peaks = ctx["peaks"]
+    return {"metric": "clips/sec, moment retrieval + moment segmentation (MomentModel.test_step, 300-frame clips)", "value": value,
+            "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (split-bf16 GEMMs, fp32-accurate)",
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[3]: {B} clips x {T} frames per GPU per step, test_step(moment_retrieval) + "
+                                   "test_step(moment_segmentation, 20 iterations on the device), text features from the repo's EVA text tower",
+                       "clips_per_gpu": B, "frames_per_clip": T, "l2": "working set 0.5 GB per step > L2",
+                       "parallelism": f"clip-shard dp{world}, results gathered as Python objects" if world > 1 else "single GPU"},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                         "kernel": "whole step (algorithmic FLOPs of the reference's fp32 path; the GEMMs execute 3x that as split bf16); "
+                                   "launch / latency bound by design (SURVEY.md §8(d))"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "check": check, "cpu_baseline": cpu}
+
+
+# ------------------------------------------------------------------------------------------------------------- configs[4]
+def _e2e(args, cfg, model_name, ctx):
+    torch, dist, dev, rank, world = ctx["torch"], ctx["dist"], ctx["dev"], ctx["rank"], ctx["world"]
+    from hirest_b200 import pipeline, synthetic
+
+    n, tmin, tmax, bs = args.videos, 120, 600, 64
+    vpath, vlist = _vocab_file()
+    model, sd = _chain_model(dev, bs * tmax, bs, vpath)
+    g = torch.Generator().manual_seed(17)
+    n_prompts = max(1, n // 4)
+    prompt_ids = synthetic.make_tokens(n_prompts, synthetic.EVA_G14, seed=77)
+    videos = []
+    for k in range(n):
+        pi = k % n_prompts
+        T = int(torch.randint(tmin, tmax + 1, (1,), generator=g))
+        vis = torch.randn(T, 1024, generator=g)
+        vis = vis / vis.norm(dim=-1, keepdim=True)
+        videos.append({"prompt": f"prompt {pi}", "fname": f"vid{k:04d}", "video_duration": T, "vis_feats": vis,
+                       "asr_feats": torch.randn(T, 384, generator=g), "clip_text_ids": prompt_ids[pi]})
+
+    def job(vs, batch_size=bs):
+        return pipeline.run_end_to_end(model, vs, batch_size=batch_size, num_beams=args.beam, rank=rank, world=world)
+
+    ms, clocks, out, launches = _timed(ctx, lambda: job(videos), args.steps, lambda: job(videos[:bs]), 1)
+    value = n * args.steps / (ms * 1e-3)
+    n_steps = sum(len(x["steps"]) for p in out["final"].values() for x in p.values())
+    check = {"steps_captioned": n_steps, "videos_in_result": sum(len(p) for p in out["final"].values())}
+    if world > 1 and not args.no_check:
+        # batch size 1 removes the batch-composition dependence the reference has (padded frames are attended to,
+        # module_visual.py:406-414), so the sharded chain must equal the single-process chain exactly
+        sub = videos[:2 * world]
+        sharded = pipeline.run_end_to_end(model, sub, batch_size=1, num_beams=args.beam, rank=rank, world=world)
+        single = pipeline.run_end_to_end(model, sub, batch_size=1, num_beams=args.beam)
+        flag = torch.tensor([int(sharded == single)], dtype=torch.int64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        check["sharded_equals_single_process"] = {"videos": len(sub), "batch_size": 1, "equal": bool(flag[0])}
+    if rank != 0:
+        return None
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import eva_oracle, pipeline_oracle as po
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        nv = 1
+        clip_sd = synthetic.make_chain_clip_state_dict()
+        test, feats = {}, {}
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            for v in videos[:nv]:
+                tf = eva_oracle.encode_text(clip_sd, v["clip_text_ids"][None], synthetic.CHAIN_CLIP)[0]
+                test.setdefault(v["prompt"], {})[v["fname"]] = {"video_duration": v["video_duration"]}
+                feats[v["fname"]] = {"vis_feats": v["vis_feats"], "asr_feats": v["asr_feats"], "text_feat": {v["prompt"]: tf}}
+            ref = po.run_end_to_end(sd, test, feats, vlist, batch_size=bs, num_beams=args.beam)
+        dt = time.perf_counter() - t0
+        cpu = {"value": nv / dt, "unit": "videos/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"first {nv} video(s): encode_text + MR + MS + step captioning (beam {args.beam}), torch fp32 CPU restatement of "
+                         "run.py:383-490"}
+    peaks = ctx["peaks"]
+    return {"metric": "videos/sec, moment retrieval -> segmentation -> step captioning chain (beam 3)", "value": value, "unit": "videos/s",
+            "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16x3 (split-bf16 GEMMs, fp32-accurate)", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[4]: {n} synthetic videos of {tmin}-{tmax} frames, in-memory MR -> MS -> SC chain "
+                                   f"(pipeline.run_end_to_end, batch {bs}, beam {args.beam}, max 48 words), host collate + H2D inside",
+                       "videos": n, "l2": "not applicable (launch / host bound)",
+                       "parallelism": f"item-shard dp{world} (DistributedSampler semantics), results gathered as Python objects"
+                       if world > 1 else "single GPU"},
+            "roofline": {"bound": "tensor", "achieved": None, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": None, "traffic": None,
+                         "kernel": "launch / host bound chain (SURVEY.md §8(d)); see the per-stage seconds in DESIGN.md"},
+            "e2e": {"value": value, "unit": "videos/s", "h2d_bytes_per_step": int(sum(v["vis_feats"].numel() * 4 + v["asr_feats"].numel() * 4
+                                                                                  for v in videos) * 2),
+                    "d2h_bytes_per_step": n * 1024, "note": "the job IS the public-API path with host inputs: features start on the host "
+                                                           "and every task's predictions are read back"},
+            "gpu_launches": launches, "clocks": clocks, "check": check, "cpu_baseline": cpu}
