@@ -287,6 +287,13 @@ class TextTransformer(_ParamTree):
         self._engine_key = key
         return self._engine
 
+    def validate_ids(self, text: torch.Tensor) -> None:
+        """nn.Embedding raises on out-of-range ids (eva_model.py:233); the device kernel clamps them.  Callers that hold the ids on
+        the HOST (MomentModel._inputs, collate output) check them here before the copy -- checking a device tensor would force a
+        host-device synchronisation into every encode_text call."""
+        if text.numel() and (int(text.min()) < 0 or int(text.max()) >= self.vocab_size):
+            raise IndexError(f"token id out of range [0, {self.vocab_size})")
+
     @torch.no_grad()
     def forward(self, text: torch.Tensor) -> torch.Tensor:
         assert text.dim() == 2 and text.shape[1] == self.context_length, \
@@ -296,9 +303,6 @@ class TextTransformer(_ParamTree):
         if text.device != dev:
             raise RuntimeError(f"input is on {text.device}, model on {dev}")
         ids = text.to(torch.int64).contiguous()
-        if ids.numel() and (int(ids.min()) < 0 or int(ids.max()) >= self.vocab_size):
-            # nn.Embedding raises on out-of-range ids (eva_model.py:233); the device kernel would clamp them silently
-            raise IndexError(f"token id out of range [0, {self.vocab_size})")
         out = torch.empty((ids.shape[0], self.embed_dim), dtype=torch.float32, device=dev)
         lib = _lib.load()
         with torch.cuda.device(dev):

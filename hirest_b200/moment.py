@@ -227,7 +227,10 @@ class MomentModel(nn.Module):
         video = batch["vis_feats"].to(dev).float().contiguous()
         vmask = batch["vis_mask"].to(dev).long().contiguous()
         asr = batch["asr_feats"].to(dev).float().contiguous() if self.use_asr else None
-        text_feat = self.clip_model.encode_text(batch["clip_text_ids"].to(dev)).float().contiguous()
+        ids = batch["clip_text_ids"]
+        if ids.device.type == "cpu" and hasattr(getattr(self.clip_model, "text", None), "validate_ids"):
+            self.clip_model.text.validate_ids(ids)   # host-side range check, as nn.Embedding would raise (no device sync)
+        text_feat = self.clip_model.encode_text(ids.to(dev)).float().contiguous()
         return video, vmask, asr, text_feat
 
     def foward_moment_shared(self, video_feats, text_feat, video_mask=None, moment_mask=None, asr_feats=None, boundary_mask=None):

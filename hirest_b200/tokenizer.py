@@ -162,12 +162,18 @@ class ClipBpeTokenizer:
         return out
 
 
-_default = None
+_cache: Dict[str, ClipBpeTokenizer] = {}
+
+
+def get_tokenizer(bpe_path: str = None) -> ClipBpeTokenizer:
+    """One tokenizer per merge-table path per process (building one reads the gzip and indexes 48k merges)."""
+    key = os.path.abspath(bpe_path or os.environ.get("HIREST_BPE_PATH") or "")
+    tok = _cache.get(key)
+    if tok is None:
+        tok = _cache[key] = ClipBpeTokenizer(bpe_path)
+    return tok
 
 
 def tokenize(texts: Union[str, Sequence[str]], context_length: int = 77, truncate: bool = False, bpe_path: str = None) -> torch.LongTensor:
-    """Module-level ``clip.tokenize`` replacement (one cached tokenizer per process)."""
-    global _default
-    if _default is None or bpe_path is not None:
-        _default = ClipBpeTokenizer(bpe_path)
-    return _default.tokenize(texts, context_length, truncate)
+    """Module-level ``clip.tokenize`` replacement."""
+    return get_tokenizer(bpe_path).tokenize(texts, context_length, truncate)

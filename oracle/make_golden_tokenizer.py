@@ -34,6 +34,52 @@ PROMPTS = [
 LONG = "repair the kitchen sink faucet " * 20
 
 
+def train_synthetic_merges(n_merges=600):
+    """A small merge table that TRAVELS with the repo (the real one is CLIP's data file): plain BPE training over the prompts
+    above, in the reference's symbol alphabet (bytes -> printable code points, '</w>' on the last symbol of a word)."""
+    import collections
+    import html
+
+    import regex
+
+    sys.path.insert(0, ROOT)
+    from hirest_b200 import tokenizer as ours   # only its byte table / pre-tokenisation pattern (data, not the algorithm under test)
+
+    byte_syms = ours._byte_symbols()
+    words = collections.Counter()
+    for p in PROMPTS[:8] + [LONG]:   # words of the other prompts are only PARTLY covered by the merges
+        text = regex.sub(r"\s+", " ", html.unescape(html.unescape(p)).strip()).strip().lower()
+        for piece in ours._PATTERN.findall(text):
+            if piece in (ours.SOT, ours.EOT):
+                continue
+            syms = [byte_syms[b] for b in piece.encode("utf-8")]
+            syms[-1] += "</w>"
+            words[tuple(syms)] += 1
+    merges = []
+    for _ in range(n_merges):
+        pairs = collections.Counter()
+        for w, c in words.items():
+            for a, b in zip(w, w[1:]):
+                pairs[(a, b)] += c
+        if not pairs:
+            break
+        best = max(sorted(pairs), key=lambda k: pairs[k])
+        merges.append(best)
+        new_words = collections.Counter()
+        for w, c in words.items():
+            out, i = [], 0
+            while i < len(w):
+                if i + 1 < len(w) and (w[i], w[i + 1]) == best:
+                    out.append(w[i] + w[i + 1])
+                    i += 2
+                else:
+                    out.append(w[i])
+                    i += 1
+            new_words[tuple(out)] += c
+        words = new_words
+    return merges
+
+
 def main():
     sys.modules["ftfy"] = types.SimpleNamespace(fix_text=lambda t: t)
     spec = importlib.util.spec_from_file_location("ref_simple_tokenizer", os.path.join(REF, "simple_tokenizer.py"))
@@ -45,9 +91,21 @@ def main():
            "vocab_size": len(tok.encoder), "prompts": PROMPTS, "ids": [tok.encode(p) for p in PROMPTS],
            "long_prompt": LONG, "long_ids": tok.encode(LONG),
            "decoded": [tok.decode(tok.encode(p)) for p in PROMPTS]}
+    # the same prompts through the reference tokenizer on the synthetic merge table committed next to the golden
+    import gzip
+
+    merges = train_synthetic_merges()
+    syn_path = os.path.join(ROOT, "tests", "golden", "bpe_synthetic.txt.gz")
+    with gzip.open(syn_path, "wt", encoding="utf-8") as f:
+        f.write("#version: synthetic (oracle/make_golden_tokenizer.py)\n" + "\n".join(" ".join(m) for m in merges))
+    tok2 = st.SimpleTokenizer(syn_path)
+    out["synthetic"] = {"n_merges": len(merges), "vocab_size": len(tok2.encoder), "sot": tok2.encoder["<|startoftext|>"],
+                        "eot": tok2.encoder["<|endoftext|>"], "ids": [tok2.encode(p) for p in PROMPTS], "long_ids": tok2.encode(LONG),
+                        "decoded": [tok2.decode(tok2.encode(p)) for p in PROMPTS]}
     with open(os.path.join(ROOT, "tests", "golden", "tokenizer.json"), "w") as f:
         json.dump(out, f, ensure_ascii=False, indent=0)
-    print(len(PROMPTS), "prompts;", sum(len(x) for x in out["ids"]), "tokens")
+    print(len(PROMPTS), "prompts;", sum(len(x) for x in out["ids"]), "tokens;", len(merges), "synthetic merges ->",
+          sum(len(x) for x in out["synthetic"]["ids"]), "tokens")
 
 
 if __name__ == "__main__":

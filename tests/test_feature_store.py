@@ -93,13 +93,16 @@ def test_cached_path_ranking_at_reference_size(hb, tmp_path):
     ref = eva_oracle.similarity(eva_oracle.normalize_text(t), ref_v)
     assert float((scores - ref).abs().max()) < 5e-7
     names = st.video_ids
-    same = 0
+    TIE = 1e-6
+    tie_rows, bad_rows = set(), set()
     for q in range(Q):
+        b = eva_oracle.rank_videos(ref[q].tolist(), names)[:11]
+        if any(abs(float(ref[q, b[j]]) - float(ref[q, b[j + 1]])) < TIE for j in range(10)):
+            tie_rows.add(q)
         a = retrieval.topk(scores[q:q + 1], names, 10)[0]
-        b = eva_oracle.rank_videos(ref[q].tolist(), names)[:10]
-        if a == b:
-            same += 1
-        else:   # any disagreement must be between near-tied scores
-            for x, y in zip(a, b):
-                assert abs(float(ref[q, x]) - float(ref[q, y])) < 1e-6
-    assert same >= Q - 5
+        if a != b[:10]:
+            bad_rows.add(q)
+            for x, y in zip(a, b):   # any disagreement must be between near-tied scores
+                assert abs(float(ref[q, x]) - float(ref[q, y])) < TIE
+    print(f"top-10 identical for {Q - len(bad_rows)}/{Q} queries; near-tie rows {len(tie_rows)}; differing rows {sorted(bad_rows)}")
+    assert bad_rows <= tie_rows

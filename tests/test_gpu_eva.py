@@ -154,18 +154,29 @@ def test_uint8_frames_match_cpu_preprocessing(tiny):
     assert torch.equal(a, b)
 
 
-def test_g14_full_size_properties(hb):
-    """BASELINE configs[1] size (EVA-CLIP-g/14, 1024 frames) through size-independent properties: the 1024-frame batch in one
-    chunk, in chunks of 384 (ragged last chunk) and a sample of single frames give bit-identical embeddings; the retrieval
-    scores of the pooled videos equal the CPU scoring of the same embeddings; uint8 input equals CPU preprocessing."""
+def test_g14_full_size_properties(hb, golden_dir):
+    """BASELINE configs[1] size (EVA-CLIP-g/14, 1024 frames).  (1) The 8 frames of the reference-generated golden (eva_g14.pt)
+    sit INSIDE the 1024-frame batch, at the chunk / tile boundaries {0, 1, 383, 384, 511, 512, 1022, 1023}: their embeddings must
+    match the reference's CPU output within the g/14 tolerance and be bit-identical to the 8-frame run.  (2) Size-independent
+    properties: one chunk, chunks of 384 (ragged last chunk) and single frames give bit-identical embeddings; the retrieval
+    scores of the pooled videos equal the CPU scoring of the same embeddings."""
     cfg = synthetic.EVA_G14
-    sd = synthetic.make_eva_state_dict(cfg, seed=0, device=DEV)
+    sd = synthetic.make_eva_state_dict(cfg, seed=0)   # CPU generator: the weights the golden was made with
+    sd = {k: v.to(DEV) for k, v in sd.items()}
     big = eva_clip.EVA_CLIP(**cfg, max_image_batch=1024, max_text_batch=8)
     big.load_state_dict(sd, strict=True)
     big = big.to(DEV).eval()
     frames = synthetic.make_frames(1024, 224, seed=77, device=DEV)
+    g = torch.load(os.path.join(golden_dir, "eva_g14.pt"))
+    gold_frames = synthetic.make_frames(8, 224, seed=1).to(DEV)
+    pos = [0, 1, 383, 384, 511, 512, 1022, 1023]
+    frames[pos] = gold_frames
     full = big.encode_image(frames)
     assert torch.isfinite(full).all()
+    e_in_batch = rel(full[pos], g["image"])
+    print(f"g14 @1024: golden frames inside the 1024-frame batch: rel {e_in_batch:.3e}")
+    assert e_in_batch < TOL_G14_IMAGE
+    assert torch.equal(full[pos], big.encode_image(gold_frames))
     small = eva_clip.EVA_CLIP(**cfg, max_image_batch=384, max_text_batch=8)
     small.load_state_dict(sd, strict=True)
     small = small.to(DEV).eval()

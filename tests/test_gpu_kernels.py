@@ -185,19 +185,21 @@ def test_similarity_topk_bit_exact_at_baseline_size(hb):
     print(f"similarity exact: max |ours - fp64| {err_ours:.2e}; max |cpu fp32 - fp64| {err_cpu:.2e}")
     assert err_ours < 3e-7 and err_ours < 4 * err_cpu
     names = [f"vid{j:05d}" for j in range(V)]
-    exact_rows = 0
+    TIE = 3e-7   # two fp32 dot products of unit vectors this close cannot be ordered reliably by ANY summation order
+    tie_rows, bad_rows = set(), set()
     for i in range(Q):
+        b = eva_oracle.rank_videos(ref[i].tolist(), names)[:51]
+        if any(abs(float(ref[i, b[j]] - ref[i, b[j + 1]])) < TIE for j in range(50)):
+            tie_rows.add(i)          # the reference's own top-50 order hangs on a sub-rounding gap somewhere
         a = retrieval.rank_videos(got[i].numpy(), names)[:50]
-        b = eva_oracle.rank_videos(ref[i].tolist(), names)[:50]
-        if a == b:
-            exact_rows += 1
-            continue
-        for ka, kb in zip(a, b):
-            if ka != kb:
-                assert abs(float(ref[i, ka] - ref[i, kb])) < 3e-7, (i, ka, kb)
-        assert a[0] == b[0] or abs(float(ref[i, a[0]] - ref[i, b[0]])) < 3e-7
-    print(f"top-50 lists identical for {exact_rows}/{Q} queries")
-    assert exact_rows >= Q - 8
+        if a != b[:50]:
+            bad_rows.add(i)
+            for ka, kb in zip(a, b):
+                if ka != kb:
+                    assert abs(float(ref[i, ka] - ref[i, kb])) < TIE, (i, ka, kb)
+    print(f"top-50 lists identical for {Q - len(bad_rows)}/{Q} queries; rows whose reference order contains a gap < {TIE:g}: "
+          f"{len(tie_rows)}; differing rows: {sorted(bad_rows)}")
+    assert bad_rows <= tie_rows, f"rows {sorted(bad_rows - tie_rows)} differ without a near-tie in the reference scores"
     # the plain single bf16 GEMM is close but not rank-stable; report its error for the record
     fast = retrieval.similarity(t.to(DEV), v.to(DEV), exact=False).cpu()
     assert float((fast - ref).abs().max()) < 5e-3

@@ -10,12 +10,30 @@ import torch
 from hirest_b200 import tokenizer
 
 BPE = os.environ.get("HIREST_BPE_PATH") or "/root/reference/EVA_clip/bpe_simple_vocab_16e6.txt.gz"
-pytestmark = pytest.mark.skipif(not os.path.exists(BPE), reason="CLIP BPE merge table not available on this machine")
+needs_real_table = pytest.mark.skipif(not os.path.exists(BPE), reason="CLIP's own BPE merge table is not available on this machine")
 
 
 @pytest.fixture(scope="module")
 def tok():
+    if not os.path.exists(BPE):
+        pytest.skip("CLIP's own BPE merge table is not available on this machine")
     return tokenizer.ClipBpeTokenizer(BPE)
+
+
+def test_synthetic_merge_table_matches_reference_everywhere(golden, golden_dir):
+    """Runs on every machine (GPU box included): a small merge table committed under tests/golden/ and the ids the REFERENCE
+    tokenizer produced with it (oracle/make_golden_tokenizer.py) -- same algorithm, table-independent."""
+    path = os.path.join(golden_dir, "bpe_synthetic.txt.gz")
+    t = tokenizer.ClipBpeTokenizer(path)
+    g = golden["synthetic"]
+    assert len(t.encoder) == g["vocab_size"] and t.sot_token == g["sot"] and t.eot_token == g["eot"]
+    for prompt, ids, dec in zip(golden["prompts"], g["ids"], g["decoded"]):
+        assert t.encode(prompt) == ids, prompt
+        assert t.decode(ids) == dec, prompt
+    assert t.encode(golden["long_prompt"]) == g["long_ids"]
+    assert tokenizer.get_tokenizer(path) is tokenizer.get_tokenizer(path)            # cached per path (ADVICE r1)
+    row = tokenizer.tokenize("make tea", bpe_path=path)[0].tolist()
+    assert row[0] == g["sot"] and g["eot"] in row and tokenizer.get_tokenizer(path) is tokenizer.get_tokenizer(path)
 
 
 @pytest.fixture(scope="module")
