@@ -799,6 +799,33 @@ int hb_subsample_pool_normalize(const float* feats, const int64_t* offsets, int6
   return HB_OK;
 }
 
+int hb_subsample_pool_normalize_bf16(const void* feats, const int64_t* offsets, int64_t V, int n_sub, int E, float* out, void* stream) {
+  if (V == 0) return HB_OK;
+  if (!feats || !offsets || !out) return fail(HB_ERR_INVALID, "null argument");
+  if (V < 0 || E <= 0 || E > 4096) return fail(HB_ERR_INVALID, "need V >= 0 and 1 <= E <= 4096");
+  HB_LAUNCH(hb::subsample_pool_normalize_bf16_launch(static_cast<const __nv_bfloat16*>(feats), reinterpret_cast<const long long*>(offsets), out,
+                                                     V, n_sub, E, static_cast<cudaStream_t>(stream)));
+  return HB_OK;
+}
+
+int hb_resample_rows(const float* feats, const int64_t* offsets, int64_t V, int n_out, int C, float* out, void* stream) {
+  if (V == 0) return HB_OK;
+  if (!feats || !offsets || !out) return fail(HB_ERR_INVALID, "null argument");
+  if (V < 0 || n_out <= 0 || C <= 0 || C % 4) return fail(HB_ERR_INVALID, "need V >= 0, n_out > 0 and C %% 4 == 0");
+  HB_LAUNCH(hb::resample_rows_launch(feats, reinterpret_cast<const long long*>(offsets), out, V, n_out, C, static_cast<cudaStream_t>(stream)));
+  return HB_OK;
+}
+
+int hb_asr_warp(const float* asr, const int64_t* sub_offsets, const int32_t* starts, const int32_t* ends, const int64_t* frame_offsets,
+                const int32_t* row_video, int64_t rows, int C, float* out, void* stream) {
+  if (rows == 0) return HB_OK;
+  if (!sub_offsets || !frame_offsets || !row_video || !out) return fail(HB_ERR_INVALID, "null argument");
+  if (rows < 0 || C <= 0 || C % 4) return fail(HB_ERR_INVALID, "need rows >= 0 and C %% 4 == 0");
+  HB_LAUNCH(hb::asr_warp_launch(asr, reinterpret_cast<const long long*>(sub_offsets), starts, ends, reinterpret_cast<const long long*>(frame_offsets),
+                                row_video, out, rows, C, static_cast<cudaStream_t>(stream)));
+  return HB_OK;
+}
+
 // ---- frame preprocessing: plans (host tables + device copy) cached per (device, H, W, S) ----
 namespace {
 struct ResizeEntry { hb::ResizePlanHost plan; DevBuf tables; };

@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(256) pool_normalize_kernel(const float* __rest
 // [offsets[v], offsets[v+1]) of one packed [sum T, E] feature blob.  If n_sub > 0 the rows are first subsampled exactly like
 // `np.linspace(0, T - 1, n_sub).astype(int)` (:313: float64 `i * step`, last sample forced to T - 1, truncation), then
 // mean-pooled in fp32 and L2-normalised (:321-326).  One CTA per video; the gather indices are computed on the fly.
-__global__ void __launch_bounds__(256) subsample_pool_normalize_kernel(const float* __restrict__ feats, const long long* __restrict__ offsets,
+template <typename TIn>
+__global__ void __launch_bounds__(256) subsample_pool_normalize_kernel(const TIn* __restrict__ feats, const long long* __restrict__ offsets,
                                                                        float* __restrict__ out, int n_sub, int E) {
   __shared__ float red[8];
   const long long v = blockIdx.x;
@@ -260,11 +261,11 @@ __global__ void __launch_bounds__(256) subsample_pool_normalize_kernel(const flo
   for (int f = 0; f < F; ++f) {
     int row = f;
     if (n_sub > 0) row = (f == n_sub - 1 && n_sub > 1) ? (T - 1) : static_cast<int>(static_cast<double>(f) * step);
-    const float* base = feats + (r0 + row) * E;
+    const TIn* base = feats + (r0 + row) * E;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       const int e = threadIdx.x + i * 256;
-      if (e < E) acc[i] += base[e];
+      if (e < E) acc[i] += static_cast<float>(base[e]);
     }
   }
 #pragma unroll
@@ -283,6 +284,67 @@ __global__ void __launch_bounds__(256) subsample_pool_normalize_kernel(const flo
   for (int i = 0; i < 16; ++i) {
     const int e = threadIdx.x + i * 256;
     if (e < E) out[v * E + e] = acc[i] * inv;
+  }
+}
+
+// Dataset-side frame resampling of cached features (hirest_dataset.py:333-356 for the video features, :383-403 for the warped
+// ASR features): per video, T rows -> n_out rows.  T > n_out: rows np.linspace(0, T-1, n_out).astype(int) (float64 i*step, last
+// sample forced to T-1, truncation); T <= n_out: repeat-pad, source row k fills output slots [(k*n_out)//T, ((k+1)*n_out)//T),
+// i.e. output slot j reads row ceil((j+1)*T / n_out) - 1.  One warp per output row, 16-byte copies.
+__global__ void __launch_bounds__(256) resample_rows_kernel(const float* __restrict__ feats, const long long* __restrict__ offsets,
+                                                            float* __restrict__ out, long long V, int n_out, int C) {
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= V * n_out) return;
+  const long long v = w / n_out;
+  const int j = static_cast<int>(w - v * n_out);
+  const long long r0 = offsets[v];
+  const int T = static_cast<int>(offsets[v + 1] - r0);
+  float4* dst = reinterpret_cast<float4*>(out + w * C);
+  if (T <= 0) {
+    for (int i = lane; i < C / 4; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  int row;
+  if (T > n_out) {
+    const double step = (n_out > 1) ? static_cast<double>(T - 1) / static_cast<double>(n_out - 1) : 0.0;
+    row = (j == n_out - 1 && n_out > 1) ? (T - 1) : static_cast<int>(static_cast<double>(j) * step);
+  } else {
+    row = static_cast<int>((static_cast<long long>(j + 1) * T + n_out - 1) / n_out) - 1;
+  }
+  const float4* src = reinterpret_cast<const float4*>(feats + (r0 + row) * C);
+  for (int i = lane; i < C / 4; i += 32) dst[i] = __ldg(src + i);
+}
+
+// ASR feature warping (hirest_dataset.py:370-381): per video a [len, C] zero tensor in which sentence i's feature row fills the
+// seconds [start_i, end_i) (Python slice semantics: clamped to [0, len]; later sentences overwrite earlier ones).  Output rows
+// are packed like the video features (frame_offsets); one warp per output row scans its video's sentences for the LAST hit.
+__global__ void __launch_bounds__(256) asr_warp_kernel(const float* __restrict__ asr, const long long* __restrict__ sub_offsets,
+                                                       const int* __restrict__ starts, const int* __restrict__ ends,
+                                                       const long long* __restrict__ frame_offsets, const int* __restrict__ row_video,
+                                                       float* __restrict__ out, long long rows, int C) {
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= rows) return;
+  const int v = row_video[w];
+  const int t = static_cast<int>(w - frame_offsets[v]);
+  const int len = static_cast<int>(frame_offsets[v + 1] - frame_offsets[v]);
+  const long long s0 = sub_offsets[v], s1 = sub_offsets[v + 1];
+  int hit = -1;
+  for (long long i = s0 + lane; i < s1; i += 32) {
+    int a = starts[i], b = ends[i];
+    if (a < 0) a = max(0, a + len);   // Python slice: negative indices count from the end
+    if (b < 0) b = max(0, b + len);
+    if (a <= t && t < b) hit = static_cast<int>(i - s0);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) hit = max(hit, __shfl_xor_sync(0xffffffffu, hit, o));
+  float4* dst = reinterpret_cast<float4*>(out + w * C);
+  if (hit < 0) {
+    for (int i = lane; i < C / 4; i += 32) dst[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    const float4* src = reinterpret_cast<const float4*>(asr + (s0 + hit) * C);
+    for (int i = lane; i < C / 4; i += 32) dst[i] = __ldg(src + i);
   }
 }
 
@@ -384,7 +446,30 @@ int subsample_pool_normalize_launch(const float* feats, const long long* offsets
                                     cudaStream_t s) {
   if (V <= 0) return 0;
   if (E > 4096) return -7;
-  subsample_pool_normalize_kernel<<<static_cast<unsigned>(V), 256, 0, s>>>(feats, offsets, out, n_sub, E);
+  subsample_pool_normalize_kernel<float><<<static_cast<unsigned>(V), 256, 0, s>>>(feats, offsets, out, n_sub, E);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int subsample_pool_normalize_bf16_launch(const __nv_bfloat16* feats, const long long* offsets, float* out, long long V, int n_sub, int E,
+                                         cudaStream_t s) {
+  if (V <= 0) return 0;
+  if (E > 4096) return -7;
+  subsample_pool_normalize_kernel<__nv_bfloat16><<<static_cast<unsigned>(V), 256, 0, s>>>(feats, offsets, out, n_sub, E);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int resample_rows_launch(const float* feats, const long long* offsets, float* out, long long V, int n_out, int C, cudaStream_t s) {
+  if (V <= 0 || n_out <= 0) return 0;
+  if (C % 4 != 0) return -7;
+  resample_rows_kernel<<<blocks_for(V * n_out * 32, 256), 256, 0, s>>>(feats, offsets, out, V, n_out, C);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int asr_warp_launch(const float* asr, const long long* sub_offsets, const int* starts, const int* ends, const long long* frame_offsets,
+                    const int* row_video, float* out, long long rows, int C, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  if (C % 4 != 0) return -7;
+  asr_warp_kernel<<<blocks_for(rows * 32, 256), 256, 0, s>>>(asr, sub_offsets, starts, ends, frame_offsets, row_video, out, rows, C);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -30,6 +30,12 @@ int pool_normalize_launch(const float* emb, void* out, long long V, int F, int E
                           cudaStream_t s);
 int subsample_pool_normalize_launch(const float* feats, const long long* offsets, float* out, long long V, int n_sub, int E,
                                     cudaStream_t s);
+int subsample_pool_normalize_bf16_launch(const __nv_bfloat16* feats, const long long* offsets, float* out, long long V, int n_sub, int E,
+                                         cudaStream_t s);
+// dataset-side frame resampling / ASR warping of packed cached features (hirest_dataset.py:328-405), see hb_elem.cu
+int resample_rows_launch(const float* feats, const long long* offsets, float* out, long long V, int n_out, int C, cudaStream_t s);
+int asr_warp_launch(const float* asr, const long long* sub_offsets, const int* starts, const int* ends, const long long* frame_offsets,
+                    const int* row_video, float* out, long long rows, int C, cudaStream_t s);
 int split_bf16_launch(const float* x, __nv_bfloat16* out, long long rows, int E, int mode, cudaStream_t s);
 int f32_to_bf16_launch(const float* x, __nv_bfloat16* y, long long n, cudaStream_t s);
 

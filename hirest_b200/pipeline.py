@@ -23,27 +23,12 @@ import numpy as np
 import torch
 
 
-def timestamp_to_frame_index(timestamp, video_duration, n_frames: int = 32) -> int:
-    """hirest_dataset.py:12-40: index of the linspace bin that contains the timestamp (right-closed), clipped."""
-    video_duration = int(video_duration)
-    if n_frames < 0:
-        n_frames = video_duration
-    bins = np.linspace(0, video_duration - 1, n_frames)
-    return int(min(np.digitize(timestamp, bins, right=True), n_frames - 1))
+from .dataset import build_items, collate as _collate, frame_index_to_timestamp, timestamp_to_frame_index  # noqa: F401  (re-exported)
 
 
-def frame_index_to_timestamp(frame_index: int, video_duration, n_frames: int = 32) -> int:
-    """hirest_dataset.py:42-68."""
-    video_duration = int(video_duration)
-    if n_frames < 0:
-        n_frames = video_duration
-    bins = np.linspace(0, video_duration - 1, n_frames)
-    return int(bins[frame_index])
-
-
-def _n_frames(video: dict, n_model_frames: int) -> int:
-    """hirest_dataset.py:149-152: fixed frame count, or one frame per second of (rounded) video duration."""
-    return n_model_frames if n_model_frames > 0 else int(video["video_duration"])
+def collate(items: Sequence[dict], n_model_frames: int = -1) -> dict:
+    """``collate_fn`` (hirest_dataset.py:409-531) for inference items; see ``hirest_b200.dataset.collate``."""
+    return _collate(items, n_model_frames)
 
 
 def shard_indices(n_items: int, rank: int, world: int) -> List[int]:
@@ -117,14 +102,6 @@ def collate(items: Sequence[dict], n_model_frames: int = -1) -> dict:
     return out
 
 
-def _base_item(video: dict, task: str, n_frames: int) -> dict:
-    if video["vis_feats"].shape[0] != n_frames:
-        raise ValueError(f"{video['fname']}: {video['vis_feats'].shape[0]} feature rows for {n_frames} frames")
-    return {"task": task, "prompt": video["prompt"], "fname": video["fname"], "video_duration": video["video_duration"],
-            "vis_feats": video["vis_feats"], "asr_feats": video["asr_feats"], "clip_text_ids": video["clip_text_ids"],
-            "video_mask": torch.ones(n_frames, dtype=torch.long)}
-
-
 @torch.no_grad()
 def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beams: int = 5, n_model_frames: int = -1,
                    tokenize=None, rank: int = 0, world: int = 1, group=None, gather=None) -> Dict:
@@ -143,8 +120,7 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
     nmf = n_model_frames
     if gather is None:
         gather = (lambda obj: all_gather_objects(obj, group)) if world > 1 else (lambda obj: [obj])
-    # hirest_dataset.py:145: the dataset rounds the annotated duration once; everything downstream uses the rounded value
-    videos = [dict(v, video_duration=round(v["video_duration"])) for v in videos]
+    # (hirest_dataset.py:145 rounds the annotated duration once, inside build_items; everything downstream uses the rounded value)
     if any("clip_text_ids" not in v for v in videos):
         if tokenize is None:
             raise ValueError("videos without 'clip_text_ids' need a tokenize callable (hirest_b200.tokenizer.tokenize)")
@@ -157,13 +133,38 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
                 v = dict(v, clip_text_ids=cache[v["prompt"]])
             filled.append(v)
         videos = filled
+    by_name = {v["fname"]: v for v in videos}
+
+    def annotations(bounds_of, steps_of):
+        """The test JSON the reference (re)writes between tasks (run.py:399-452), grouped by prompt in first-appearance order."""
+        ann: Dict[str, Dict[str, dict]] = {}
+        for v in videos:
+            ann.setdefault(v["prompt"], {})[v["fname"]] = {"relevant": True, "clip": True, "v_duration": v["video_duration"],
+                                                         "bounds": bounds_of(v), "steps": steps_of(v)}
+        return ann
+
+    def with_features(items, slice_to_moment=False):
+        out = []
+        for it in items:
+            v = by_name[it["fname"]]
+            n = it["video_mask"].numel()
+            if v["vis_feats"].shape[0] != n:
+                raise ValueError(f"{v['fname']}: {v['vis_feats'].shape[0]} feature rows for {n} frames")
+            it = dict(it, clip_text_ids=v["clip_text_ids"])
+            if slice_to_moment:
+                # Step captioning only ever reads the frames inside the step (trim_feats, modeling.py:529-554, keeps the rows with
+                # moment_mask == 1, in order), so the item carries just those rows with an all-ones mask instead of the whole video
+                # padded to the longest one in the batch: same trimmed tensor, ~30x fewer bytes collated and copied to the GPU.
+                rows = it["moment_mask"].nonzero(as_tuple=True)[0]
+                it.update(vis_feats=v["vis_feats"][rows], asr_feats=v["asr_feats"][rows],
+                          video_mask=torch.ones(rows.numel(), dtype=torch.long), moment_mask=torch.ones(rows.numel(), dtype=torch.long))
+            else:
+                it.update(vis_feats=v["vis_feats"], asr_feats=v["asr_feats"])
+            out.append(it)
+        return out
+
     # ---- 1. moment retrieval (dataset :153-183, evaluate :704-744) -------------------------------------------------
-    items = []
-    for v in videos:
-        n = _n_frames(v, nmf)
-        it = _base_item(v, "moment_retrieval", n)
-        it["moment_mask"] = torch.ones(n, dtype=torch.long)
-        items.append(it)
+    items = with_features(build_items(annotations(lambda v: [0, 0], lambda v: []), "moment_retrieval", nmf, end_to_end=True))
     mr: Dict[str, Dict[str, dict]] = {}
     preds = _run_sharded(items, lambda chunk: model.test_step(collate(chunk, nmf))["prediction"], batch_size, rank, world, gather)
     for it, (s, e) in zip(items, preds):
@@ -178,19 +179,8 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
             "bounds": mr[v["prompt"]][v["fname"]]["bounds"],
             "steps": [{"index": i, "heading": "", "absolute_bounds": [i, i + 1]} for i in range(5)]}
     # ---- 2. moment segmentation (dataset :239-266 test branch, evaluate :746-782) ----------------------------------
-    items = []
-    for v in videos:
-        n = _n_frames(v, nmf)
-        d = v["video_duration"]
-        b0, b1 = state[v["prompt"]][v["fname"]]["bounds"]
-        f0 = timestamp_to_frame_index(b0, video_duration=d, n_frames=n)
-        f1 = timestamp_to_frame_index(b1, video_duration=d, n_frames=n)
-        it = _base_item(v, "moment_segmentation", n)
-        it["moment_bound_frames"] = [f0, f1]
-        mm = torch.zeros(n, dtype=torch.long)
-        mm[f0:f1 + 1] = 1
-        it["moment_mask"] = mm
-        items.append(it)
+    items = with_features(build_items(annotations(lambda v: state[v["prompt"]][v["fname"]]["bounds"],
+                                                  lambda v: state[v["prompt"]][v["fname"]]["steps"]), "moment_segmentation", nmf, end_to_end=True))
     ms: Dict[str, dict] = {}
     preds = _run_sharded(items, lambda chunk: model.test_step(collate(chunk, nmf))["prediction"], batch_size, rank, world, gather)
     for it, raw in zip(items, preds):
@@ -203,28 +193,10 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
             state[prompt][fname]["steps"] = [{"index": i, "heading": "", "absolute_bounds": b}
                                              for i, b in enumerate(ms[fname]["bounds"])] if fname in ms else []
     # ---- 3. step captioning (dataset :268-312, evaluate :787-830) --------------------------------------------------
-    items = []
-    for v in videos:
-        steps = state[v["prompt"]][v["fname"]]["steps"]
-        n = _n_frames(v, nmf)
-        d = v["video_duration"]
-        for step in steps:   # a video whose segmentation produced no step contributes nothing (the reference indexes steps[0] and raises)
-            s, e = step["absolute_bounds"]
-            sf = timestamp_to_frame_index(s, video_duration=d, n_frames=n)
-            ef = timestamp_to_frame_index(e, video_duration=d, n_frames=n)
-            mm = torch.zeros(n, dtype=torch.long)
-            mm[sf:ef] = 1
-            mm[ef] = 1
-            # Step captioning only ever reads the frames inside the step (trim_feats, modeling.py:529-554, keeps the rows with
-            # moment_mask == 1, in order), so the item carries just those rows with an all-ones mask instead of the whole video
-            # padded to the longest one in the batch: same trimmed tensor, ~30x fewer bytes collated and copied to the GPU.
-            rows = mm.nonzero(as_tuple=True)[0]
-            it = _base_item(v, "step_captioning", n)
-            it["vis_feats"] = v["vis_feats"][rows]
-            it["asr_feats"] = v["asr_feats"][rows]
-            it["video_mask"] = torch.ones(rows.numel(), dtype=torch.long)
-            it["moment_mask"] = torch.ones(rows.numel(), dtype=torch.long)
-            items.append(it)
+    # (a video whose segmentation produced no step contributes nothing; the reference indexes steps[0] and raises)
+    items = with_features(build_items(annotations(lambda v: state[v["prompt"]][v["fname"]]["bounds"],
+                                                  lambda v: state[v["prompt"]][v["fname"]]["steps"]), "step_captioning", nmf, end_to_end=True),
+                          slice_to_moment=True)
     sc: Dict[str, dict] = {}
     preds = _run_sharded(items, lambda chunk: model.test_step(collate(chunk, -1), num_beams=num_beams)["prediction"],   # ragged items: pad path
                          batch_size, rank, world, gather)

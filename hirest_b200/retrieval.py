@@ -136,6 +136,26 @@ def rank_videos(scores_row: Sequence[float], video_names: Sequence[str]) -> List
     return order[::-1].tolist()
 
 
+def recall_at_k(scores, video_names: Sequence[str], gt_videos: Sequence[Sequence[str]], ks: Sequence[int] = (1, 5, 10, 50)) -> dict:
+    """``evaluate_video_retrieval`` (evaluate.py:33-81) for the "all" category: per prompt, rank the videos by (score, name) as
+    ``rank_videos`` does and count a hit at k if ANY of the top-k videos is one of the prompt's ground-truth videos.
+    ``scores`` [Q, V] (tensor / array), ``gt_videos[q]`` = names of prompt q's ground-truth videos.  Returns ``{"R@k": percent}``
+    plus ``total_prompt_count`` like the reference's result dictionary."""
+    sc = scores.detach().float().cpu().numpy() if torch.is_tensor(scores) else np.asarray(scores, dtype=np.float64)
+    names = list(video_names)
+    hits = {k: 0 for k in ks}
+    for q in range(sc.shape[0]):
+        order = rank_videos(sc[q], names)
+        gt = set(gt_videos[q])
+        for k in ks:
+            if any(names[j] in gt for j in order[:k]):
+                hits[k] += 1
+    total = sc.shape[0]
+    out = {"total_prompt_count": total}
+    out.update({f"R@{k}": (hits[k] / total) * 100 for k in ks} if total else {})
+    return out
+
+
 def topk(scores: torch.Tensor, video_names: Optional[Sequence[str]], k: int) -> List[List[int]]:
     """Top-k video indices per query under the reference ranking rule."""
     sc = scores.detach().float().cpu().numpy()

@@ -256,6 +256,19 @@ HB_API int hb_pool_normalize(const float* emb, int64_t V, int F, int E, float* o
  * back to back, offsets int64 [V+1] (device).  Per video: rows np.linspace(0, T-1, n_sub).astype(int) (all rows if
  * n_sub <= 0) -> mean -> L2 normalise.  out fp32 [V,E].  Videos must have T >= 1. */
 HB_API int hb_subsample_pool_normalize(const float* feats, const int64_t* offsets, int64_t V, int n_sub, int E, float* out, void* stream);
+/* Same with the packed features stored as bf16 (half the bytes of the store; the values are the reference's fp32 features rounded
+ * to bf16, so embeddings agree to ~2e-3 relative instead of bit for bit). */
+HB_API int hb_subsample_pool_normalize_bf16(const void* feats, const int64_t* offsets, int64_t V, int n_sub, int E, float* out, void* stream);
+/* Dataset-side frame resampling of cached features for the MomentModel feed (hirest_dataset.py:333-356, 383-403): feats fp32
+ * [sum_T, C] packed per video, offsets int64 [V+1] -> out fp32 [V, n_out, C].  T > n_out: rows np.linspace(0, T-1, n_out).astype(int);
+ * T <= n_out: repeat-pad (row k fills slots [(k*n_out)//T, ((k+1)*n_out)//T)); T == 0: zeros. */
+HB_API int hb_resample_rows(const float* feats, const int64_t* offsets, int64_t V, int n_out, int C, float* out, void* stream);
+/* ASR feature warping (hirest_dataset.py:370-381): asr fp32 [sum_S, C] = one feature row per subtitle sentence, packed per video
+ * (sub_offsets int64 [V+1]); starts / ends int32 [sum_S] = the sentences' start / end seconds; frame_offsets int64 [V+1] = rows of
+ * the output per video (the video lengths); row_video int32 [rows] = video of every output row.  out fp32 [rows, C]: row t of a
+ * video = the feature of the LAST sentence with start <= t < end, zeros if none. */
+HB_API int hb_asr_warp(const float* asr, const int64_t* sub_offsets, const int32_t* starts, const int32_t* ends, const int64_t* frame_offsets,
+                       const int32_t* row_video, int64_t rows, int C, float* out, void* stream);
 /* scores[q,v] = <text[q,:], video[v,:]>; text fp32 [Q,E], video fp32 [V,E], scores fp32 [Q, ld_scores].
  * exact != 0: one bf16 GEMM over 3-way split operands (hi+mid+lo = the fp32 value exactly), K = 6E: fp32-accurate
  * scores, so top-k matches the reference's fp32 matmul up to fp32 rounding ties; exact == 0: single plain bf16 GEMM. */
