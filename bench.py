@@ -220,15 +220,7 @@ def main():
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     lib = _lib.init(local_rank)
-    if os.environ.get("HB_PLAIN_TILES") == "1":  # A/B switch for the GEMM column tiling (same results, see hb_set_gemm_balanced_tiles)
-        _lib.check(lib.hb_set_gemm_balanced_tiles(0))
-
-    if os.environ.get("HB_ATTN_PREFETCH") == "0":
-        _lib.check(lib.hb_set_attention_prefetch(0))
-    if os.environ.get("HB_STATIC_SCHED") == "1":
-        _lib.check(lib.hb_set_gemm_dynamic_schedule(0))
-    if os.environ.get("HB_PREFETCH_CHUNKS"):
-        _lib.check(lib.hb_set_gemm_resid_prefetch_chunks(int(os.environ["HB_PREFETCH_CHUNKS"])))
+    # (kernel-variant A/B switches: HB_DEBUG_* environment variables, include/hirest_b200_debug.h)
 
     sd = synthetic.make_eva_state_dict(cfg, seed=0, device=dev)
     model = eva_clip.EVA_CLIP(**cfg, max_image_batch=args.frames, max_text_batch=max(args.queries, 8))

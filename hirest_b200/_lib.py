@@ -86,13 +86,7 @@ SIGNATURES = {
     "hb_last_error": (C.c_char_p, []),
     "hb_strerror": (C.c_char_p, [C.c_int]),
     "hb_launch_count": (C.c_int64, []),
-    "hb_set_gemm_cta_group": (C.c_int, [C.c_int]),
-    "hb_set_attention_version": (C.c_int, [C.c_int]),
-    "hb_set_attention_prefetch": (C.c_int, [C.c_int]),
-    "hb_set_ln_fold": (C.c_int, [C.c_int]),
-    "hb_set_gemm_balanced_tiles": (C.c_int, [C.c_int]),
-    "hb_set_gemm_resid_prefetch_chunks": (C.c_int, [C.c_int]),
-    "hb_set_gemm_dynamic_schedule": (C.c_int, [C.c_int]),
+    "hb_debug_set": (C.c_int, [C.c_char_p, C.c_int]),
     "hb_gemm_n_tiling": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "hb_profile_start": (C.c_int, []),
     "hb_profile_stop": (C.c_int, [C.POINTER(HbProfileSummary)]),
@@ -163,6 +157,11 @@ def load():
                 fn.argtypes = args
             _lib = lib
     return _lib
+
+
+def debug_set(key: str, value: int) -> None:
+    """Kernel-variant switch for A/B measurements / cross-check tests (include/hirest_b200_debug.h); not part of the boundary."""
+    check(load().hb_debug_set(key.encode(), int(value)), f"hb_debug_set({key})")
 
 
 def check(rc: int, what: str = "") -> None:

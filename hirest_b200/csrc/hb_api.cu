@@ -1,14 +1,17 @@
 // hb_api.cu — the C ABI (include/hirest_b200.h): model handles (weights repacked to bf16 once, workspace,
 // TMA tensor maps) and the per-call kernel sequences for encode_image / encode_text / retrieval scoring.
 #include "../../include/hirest_b200.h"
+#include "../../include/hirest_b200_debug.h"
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -35,6 +38,7 @@ int g_dyn_sched = 1; // ViT GEMMs take their tiles from an atomic counter (in se
 int g_ln_fold = 1;   // fold the ViT block LayerNorms into the QKV / fc1 GEMM epilogues (no LayerNorm kernel)
 int g_num_sms = 148;
 bool g_inited = false;
+int g_device = -1;
 
 int vit_attn_dispatch(const hb::AttnParams& ap, cudaStream_t s) {
   if (g_attn_version == 1) return hb::vit_attn_launch(ap, s);
@@ -331,13 +335,31 @@ int hb_init(int device) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return fail(HB_ERR_NODEVICE, "no CUDA device visible");
   if (device < 0 || device >= n) return fail(HB_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+  if (g_inited && device != g_device)
+    return fail(HB_ERR_INVALID, "already initialised for device %d: one process per GPU (per-device kernel attributes and the SM count are "
+                                "process-wide); start another process for device %d", g_device, device);
+  int prev_device = -1;
+  HB_CUDA(cudaGetDevice(&prev_device));
   HB_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   HB_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(HB_ERR_NODEVICE, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major, prop.minor);
   g_num_sms = prop.multiProcessorCount;
   if (hb::tmap_init() != 0) return fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  if (!g_inited) {   // A/B switches from the environment (hirest_b200_debug.h), once
+    static const char* keys[] = {"gemm_cta_group", "attention_version", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
+                                 "gemm_dynamic_schedule", "gemm_resid_prefetch_chunks"};
+    for (const char* key : keys) {
+      std::string env = std::string("HB_DEBUG_") + key;
+      for (auto& ch : env) ch = static_cast<char>(toupper(static_cast<unsigned char>(ch)));
+      if (const char* v = getenv(env.c_str())) {
+        if (int r = hb_debug_set(key, atoi(v))) return r;
+      }
+    }
+  }
   g_inited = true;
+  g_device = device;
+  if (prev_device >= 0 && prev_device != device) HB_CUDA(cudaSetDevice(prev_device));   // leave the caller's current device alone
   return HB_OK;
 }
 
@@ -356,46 +378,34 @@ const char* hb_strerror(int code) {
 
 int64_t hb_launch_count(void) { return g_launches.load(); }
 
-int hb_set_ln_fold(int on) {
-  g_ln_fold = on ? 1 : 0;
-  return HB_OK;
-}
-
-int hb_set_gemm_balanced_tiles(int on) {
-  hb::gemm_set_balanced_tiles(on);
-  return HB_OK;
-}
-
 int hb_gemm_n_tiling(int N, int cta_group, int balanced, int* n0, int* width, int cap) {
   const int r = hb::gemm_n_tiling(N, cta_group, balanced, n0, width, cap);
   if (r < 0) return fail(HB_ERR_INVALID, "need N > 0 and cta_group 1 or 2");
   return r;
 }
 
-int hb_set_gemm_dynamic_schedule(int on) {
-  g_dyn_sched = on ? 1 : 0;
-  return HB_OK;
-}
-
-int hb_set_gemm_resid_prefetch_chunks(int k) {
-  hb::gemm_set_resid_prefetch_chunks(k);
-  return HB_OK;
-}
-
-int hb_set_attention_version(int v) {
-  if (v < 1 || v > 3) return fail(HB_ERR_INVALID, "attention version must be 1, 2 or 3");
-  g_attn_version = v;
-  return HB_OK;
-}
-
-int hb_set_attention_prefetch(int on) {
-  g_attn_prefetch = on ? 1 : 0;
-  return HB_OK;
-}
-
-int hb_set_gemm_cta_group(int cg) {
-  if (cg != 1 && cg != 2) return fail(HB_ERR_INVALID, "cta group must be 1 or 2");
-  g_cg = cg;
+int hb_debug_set(const char* key, int value) {
+  if (!key) return fail(HB_ERR_INVALID, "null key");
+  const std::string k(key);
+  if (k == "gemm_cta_group") {
+    if (value != 1 && value != 2) return fail(HB_ERR_INVALID, "cta group must be 1 or 2");
+    g_cg = value;
+  } else if (k == "attention_version") {
+    if (value < 1 || value > 3) return fail(HB_ERR_INVALID, "attention version must be 1, 2 or 3");
+    g_attn_version = value;
+  } else if (k == "attention_prefetch") {
+    g_attn_prefetch = value ? 1 : 0;
+  } else if (k == "ln_fold") {
+    g_ln_fold = value ? 1 : 0;
+  } else if (k == "gemm_balanced_tiles") {
+    hb::gemm_set_balanced_tiles(value);
+  } else if (k == "gemm_dynamic_schedule") {
+    g_dyn_sched = value ? 1 : 0;
+  } else if (k == "gemm_resid_prefetch_chunks") {
+    hb::gemm_set_resid_prefetch_chunks(value);
+  } else {
+    return fail(HB_ERR_INVALID, "unknown debug key '%s'", key);
+  }
   return HB_OK;
 }
 

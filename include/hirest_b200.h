@@ -14,6 +14,10 @@
  * `stream` is a cudaStream_t passed as void*.  Handles own only repacked bf16 weights + workspace.  No hidden
  * synchronisation: results are ready when `stream` reaches the call's last kernel.  A handle is not
  * thread-safe; use one handle per stream / rank (one process per GPU, as run.py:846-856 does).
+ *
+ * Scope of state: hb_init binds the PROCESS to one device (the reference's model: one process per GPU); handles are independent
+ * of each other.  There are no tuning switches in this header: the kernel-variant knobs used for A/B measurements live in
+ * hirest_b200_debug.h (hb_debug_set / HB_DEBUG_* environment variables) and are not part of the drop-in boundary.
  */
 #ifndef HIREST_B200_H_
 #define HIREST_B200_H_
@@ -37,39 +41,14 @@ extern "C" {
 #define HB_ERR_NODEVICE (-19)  /* no sm_100 device */
 
 /* ---- library ------------------------------------------------------------------------------- */
-/* Binds the calling thread to `device`, checks it is compute capability 10.x, resolves the driver
- * entry points.  Must be called once per process before anything else. */
+/* Checks that `device` is compute capability 10.x, resolves the driver entry points and binds the PROCESS to that device (a second
+ * call with another device fails: one process per GPU).  The calling thread's current device is left as it was; callers make
+ * `device` current around the other calls (torch.cuda.device / cudaSetDevice).  Must be called before anything else. */
 HB_API int hb_init(int device);
 HB_API const char* hb_last_error(void);
 HB_API const char* hb_strerror(int code);
 /* Number of kernels launched by this library since process start (bench.py's gpu_launches). */
 HB_API int64_t hb_launch_count(void);
-/* cta_group used by the GEMMs: 2 (CTA pairs, default) or 1. */
-HB_API int hb_set_gemm_cta_group(int cg);
-/* ViT attention kernel: 3 (default: one persistent CTA per SM pipelined over (frame, head) items, TMA-store output), 2 (one CTA
- * per 128-query tile, two CTAs per SM, P kept in TMEM) or 1 (one CTA per (frame, head), P staged through shared memory).
- * Same results up to bf16 rounding of the output. */
-HB_API int hb_set_attention_version(int v);
-/* Attention v2: every CTA L2-prefetches the Q / K / V boxes of the CTA one wave (2 x #SMs blocks) ahead (1) or not (0, default:
- * measured slower, 1.05 -> 1.14 ms per layer; kept as an A/B knob). */
-HB_API int hb_set_attention_prefetch(int on);
-/* ViT handles created after this call fold the block LayerNorms into the QKV / fc1 GEMM epilogues (1, default) or run
- * separate LayerNorm kernels (0). */
-HB_API int hb_set_ln_fold(int on);
-/* GEMM column tiling: 1 (default) = equal-cost N tiles (1408 = 2 x 256 + 4 x 224), 0 = 256-wide tiles + narrow tail.
- * Same arithmetic per output element; with the LayerNorm fold the per-row statistics are summed in a different grouping, so
- * results differ by fp32 summation order (then bf16 rounding).  Process-wide; exists for A/B measurements. */
-HB_API int hb_set_gemm_balanced_tiles(int on);
-/* Host-only: the column tiling the GEMM kernel uses for an N-wide output (first column and width of up to `cap` tiles);
- * returns the number of tiles or < 0.  For verification. */
-HB_API int hb_gemm_n_tiling(int N, int cta_group, int balanced, int* n0, int* width, int cap);
-/* ViT GEMM tile hand-out: 1 (default) = dynamic (atomic tile counter, tiles start in sequence order so the workers sharing an
- * A block through L2 stay together), 0 = static round-robin.  Same results bit for bit; process-wide. */
-HB_API int hb_set_gemm_dynamic_schedule(int on);
-/* fp32-residual epilogues (proj, fc2) pull their residual lines into L2 k chunks of 32 columns ahead of use
- * (default 0 = off, max 3; measured: no gain inside the power-capped step). */
-HB_API int hb_set_gemm_resid_prefetch_chunks(int k);
-
 /* Per-launch timing for bench.py's roofline: while enabled every kernel launch of this library is bracketed
  * by CUDA events on its own stream.  hb_profile_stop synchronises the device and sums per category:
  * 0 GEMM bf16-out (qkv), 1 GEMM GELU (fc1), 2 GEMM fp32-out (patch/proj/fc2/head/similarity), 3 ViT attention,

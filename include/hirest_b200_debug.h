@@ -1,0 +1,35 @@
+/* hirest_b200_debug.h — kernel-variant switches for A/B measurements and cross-check tests.  NOT part of the drop-in boundary
+ * (include/hirest_b200.h): nothing a caller of the reference's API needs, process-wide, and free to change between builds.
+ * Every key can also be given as an environment variable HB_DEBUG_<KEY in upper case>, read once by hb_init.
+ */
+#ifndef HIREST_B200_DEBUG_H_
+#define HIREST_B200_DEBUG_H_
+
+#include "hirest_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* key                          values                default   meaning
+ * "gemm_cta_group"             1 | 2                 2         tcgen05 cta_group of the GEMMs (2 = CTA pairs, 256 x 256 tiles)
+ * "attention_version"          1 | 2 | 3             3         ViT attention kernel: 3 persistent pipelined CTA per SM (hb_attn3.cu),
+ *                                                              2 one CTA per 128-query tile (hb_attn2.cu), 1 one CTA per (frame, head)
+ * "attention_prefetch"         0 | 1                 0         v2 only: L2-prefetch the operands of the CTA one wave ahead (measured slower)
+ * "ln_fold"                    0 | 1                 1         ViT handles created afterwards fold the block LayerNorms into the QKV / fc1
+ *                                                              GEMM epilogues (1) or run separate LayerNorm kernels (0)
+ * "gemm_balanced_tiles"        0 | 1                 1         equal-cost N tiles (1408 = 2 x 256 + 4 x 224) vs 256-wide tiles + narrow tail;
+ *                                                              regroups the LayerNorm-fold partial sums (fp32 summation order)
+ * "gemm_dynamic_schedule"      0 | 1                 1         ViT GEMM tiles from an atomic counter (in sequence order) vs static round-robin;
+ *                                                              bit-identical results
+ * "gemm_resid_prefetch_chunks" 0..3                  0         fp32-residual epilogues L2-prefetch their residual k chunks ahead (no gain)
+ * Returns HB_OK or HB_ERR_INVALID (unknown key / value). */
+HB_API int hb_debug_set(const char* key, int value);
+/* Host-only: the column tiling the GEMM kernel uses for an N-wide output (first column and width of up to `cap` tiles);
+ * returns the number of tiles or < 0.  For verification. */
+HB_API int hb_gemm_n_tiling(int N, int cta_group, int balanced, int* n0, int* width, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIREST_B200_DEBUG_H_ */

@@ -8,9 +8,19 @@ from hirest_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "hirest_b200.h")).read()
+def _declared_symbols(headers=("hirest_b200.h", "hirest_b200_debug.h")):
+    text = "".join(open(os.path.join(ROOT, "include", h)).read() for h in headers)
     return sorted(set(re.findall(r"HB_API[^;(]*?\b(hb_\w+)\s*\(", text)))
+
+
+def test_boundary_header_has_no_tuning_switches():
+    """A/B knobs do not belong in the drop-in boundary; they live in hirest_b200_debug.h (hb_debug_set)."""
+    syms = _declared_symbols(("hirest_b200.h",))
+    assert not [s for s in syms if s.startswith("hb_set_") or s.startswith("hb_debug")]
+    assert "hb_debug_set" in _declared_symbols(("hirest_b200_debug.h",))
+    lib = _lib.load()
+    assert lib.hb_debug_set(b"no_such_key", 1) == -22 and lib.hb_debug_set(b"attention_version", 7) == -22
+    assert lib.hb_debug_set(b"attention_version", 3) == 0
 
 
 def test_header_declares_the_path():

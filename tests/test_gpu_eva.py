@@ -200,13 +200,13 @@ def test_layernorm_fold_matches_separate_layernorm(hb, golden_dir):
         frames = synthetic.make_frames(n, 224, seed=1).to(DEV)
         errs = {}
         for fold in (1, 0):
-            _lib.check(hb.hb_set_ln_fold(fold))
+            _lib.check(hb.hb_debug_set(b"ln_fold", fold))
             model = eva_clip.EVA_CLIP(**cfg, max_image_batch=8, max_text_batch=8)
             model.load_state_dict(sd, strict=True)
             model = model.to(DEV).eval()
             errs[fold] = rel(model.encode_image(frames), g["image"])
             del model
-        _lib.check(hb.hb_set_ln_fold(1))
+        _lib.check(hb.hb_debug_set(b"ln_fold", 1))
         print(f"{gname}: rel err folded {errs[1]:.3e}, separate LayerNorm {errs[0]:.3e}")
         assert errs[1] < (TOL_TINY_IMAGE if cfg is synthetic.EVA_TINY else TOL_G14_IMAGE)
         assert errs[1] <= errs[0] * 1.25 + 1e-4
@@ -228,13 +228,13 @@ def test_schedule_and_tiling_knobs(hb):
     try:
         for dyn in (1, 0):
             for bal in (1, 0):
-                _lib.check(hb.hb_set_gemm_dynamic_schedule(dyn))
-                _lib.check(hb.hb_set_gemm_balanced_tiles(bal))
+                _lib.check(hb.hb_debug_set(b"gemm_dynamic_schedule", dyn))
+                _lib.check(hb.hb_debug_set(b"gemm_balanced_tiles", bal))
                 outs[(dyn, bal)] = model.encode_image(frames).clone()
                 assert torch.equal(outs[(dyn, bal)], model.encode_image(frames)), "not reproducible run to run"
     finally:
-        _lib.check(hb.hb_set_gemm_dynamic_schedule(1))
-        _lib.check(hb.hb_set_gemm_balanced_tiles(1))
+        _lib.check(hb.hb_debug_set(b"gemm_dynamic_schedule", 1))
+        _lib.check(hb.hb_debug_set(b"gemm_balanced_tiles", 1))
     assert torch.isfinite(outs[(1, 1)]).all()
     assert torch.equal(outs[(1, 1)], outs[(0, 1)]) and torch.equal(outs[(1, 0)], outs[(0, 0)])
     assert rel(outs[(1, 0)], outs[(1, 1)]) < 3e-3

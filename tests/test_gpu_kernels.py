@@ -29,7 +29,7 @@ def linear(hb, x, w, bias, epi, resid=None):
 @pytest.mark.parametrize("cg", [2, 1])
 @pytest.mark.parametrize("M,N,K", [(1, 16, 8), (257, 1408, 1408), (549, 4224, 352), (1000, 96, 592), (300, 1024, 6144)])
 def test_linear_f32(hb, cg, M, N, K):
-    _lib.check(hb.hb_set_gemm_cta_group(cg))
+    _lib.check(hb.hb_debug_set(b"gemm_cta_group", cg))
     torch.manual_seed(M + N + K)
     x = torch.randn(M, K, device=DEV).bfloat16()
     w = (torch.randn(N, K, device=DEV) * K ** -0.5).bfloat16()
@@ -38,7 +38,7 @@ def test_linear_f32(hb, cg, M, N, K):
     ref = x.float() @ w.float().T + b
     assert rel(linear(hb, x, w, b, 2), ref) < 1e-5
     assert rel(linear(hb, x, w, None, 2, resid=r), ref - b + r) < 1e-5
-    _lib.check(hb.hb_set_gemm_cta_group(2))
+    _lib.check(hb.hb_debug_set(b"gemm_cta_group", 2))
 
 
 @pytest.mark.parametrize("epi", [0, 1])
@@ -86,9 +86,9 @@ ATTN_DEFAULT = 3
 
 @pytest.fixture(params=[3, 2, 1], ids=["attn_v3", "attn_v2", "attn_v1"])
 def attn_version(request, hb):
-    _lib.check(hb.hb_set_attention_version(request.param))
+    _lib.check(hb.hb_debug_set(b"attention_version", request.param))
     yield request.param
-    _lib.check(hb.hb_set_attention_version(ATTN_DEFAULT))
+    _lib.check(hb.hb_debug_set(b"attention_version", ATTN_DEFAULT))
 
 
 @pytest.mark.parametrize("B,H", [(1, 1), (3, 4), (2, 16), (40, 16)])

@@ -17,7 +17,7 @@ ref = ((q[0] @ q[1].transpose(-2, -1)).softmax(-1) @ q[2]).transpose(1, 2).resha
 qe = qkv[(B - 1) * 257:].float().reshape(1, 257, 3, H, 88).permute(2, 0, 3, 1, 4)
 ref_last = ((qe[0] @ qe[1].transpose(-2, -1)).softmax(-1) @ qe[2]).transpose(1, 2).reshape(257, D)
 for v in versions:
-    _lib.check(lib.hb_set_attention_version(v))
+    _lib.check(lib.hb_debug_set(b"attention_version", v))
     out.zero_()
     try:
         for _ in range(2):

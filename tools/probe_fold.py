@@ -9,7 +9,7 @@ sd = synthetic.make_eva_state_dict(cfg, 0)
 frames = synthetic.make_frames(5, 224, seed=9).to(dev)
 D = cfg["vision_cfg"]["width"]
 for fold in (1, 0):
-    _lib.check(lib.hb_set_ln_fold(fold))
+    _lib.check(lib.hb_debug_set(b"ln_fold", fold))
     m = eva_clip.EVA_CLIP(**cfg, max_image_batch=8, max_text_batch=8); m.load_state_dict(sd); m = m.to(dev).eval()
     a = m.encode_image(frames); b = m.encode_image(frames); c = m.encode_image(frames[:1])
     print("fold", fold, "run-to-run max diff", float((a - b).abs().max()), "single-vs-batch", float((a[:1] - c).abs().max()))

@@ -6,7 +6,7 @@ from hirest_b200 import _lib
 lib = _lib.init(0)
 B, H = int(sys.argv[1]) if len(sys.argv) > 1 else 64, 16
 if len(sys.argv) > 2:
-    _lib.check(lib.hb_set_attention_version(int(sys.argv[2])))
+    _lib.check(lib.hb_debug_set(b"attention_version", int(sys.argv[2])))
 D = H * 88
 qkv = (torch.randn(B * 257, 3 * D, device="cuda") * 0.7).bfloat16()
 out = torch.empty(B * 257, D, device="cuda", dtype=torch.bfloat16)

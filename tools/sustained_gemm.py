@@ -69,7 +69,7 @@ def main():
     a = ap.parse_args()
     dev = "cuda:0"
     hb = _lib.init(0)
-    _lib.check(hb.hb_set_gemm_cta_group(a.cg))
+    _lib.check(hb.hb_debug_set(b"gemm_cta_group", a.cg))
     M = a.frames * 257
     shapes = [("qkv", 4224, 1408, 0), ("fc1", 6144, 1408, 1), ("proj", 1408, 1408, 2), ("fc2", 1408, 6144, 2), ("square8192", 8192, 8192, 0)]
     res = {}
