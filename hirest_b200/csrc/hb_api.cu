@@ -33,6 +33,7 @@ thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 int g_cg = 2;
 int g_attn_version = 3;
+int g_small_attn_tc = 1;   // fp32 small-sequence attention on tensor cores (hb_attn_tc.cu) instead of CUDA cores
 int g_attn_prefetch = 0;   // attention v2: L2-prefetch the operands of the CTA one wave ahead (measured: 1.05 -> 1.14 ms, off)
 int g_dyn_sched = 1; // ViT GEMMs take their tiles from an atomic counter (in sequence order) instead of a static round-robin
 int g_ln_fold = 1;   // fold the ViT block LayerNorms into the QKV / fc1 GEMM epilogues (no LayerNorm kernel)
@@ -305,6 +306,18 @@ int ln_f32(const float* x, float* y, const F32Vec& w, const F32Vec& b, float eps
   return 0;
 }
 
+// fp32 attention of the small sequence models: tensor-core kernel when a whole query tile is worth it and the handle's workspace
+// fits, CUDA-core kernel otherwise (decode steps with one query, shared K / V across beams).
+int small_attn_f32_auto(const hb::SmallAttnF32Params& ap, const DevBuf& ws, cudaStream_t s) {
+  if (g_small_attn_tc && ap.Tq >= 16 && ap.kv_div == 1 && ws.p != nullptr && ws.bytes >= hb::small_attn_tc_workspace(ap.B, ap.H, ap.Tq, ap.Tk)) {
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::small_attn_tc_launch(ap, ws.p, ws.bytes, s));
+    g_launches.fetch_add(1, std::memory_order_relaxed);   // split prologue + main kernel
+    return 0;
+  }
+  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::small_attn_f32_launch(ap, s));
+  return 0;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -347,7 +360,7 @@ int hb_init(int device) {
   g_num_sms = prop.multiProcessorCount;
   if (hb::tmap_init() != 0) return fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   if (!g_inited) {   // A/B switches from the environment (hirest_b200_debug.h), once
-    static const char* keys[] = {"gemm_cta_group", "attention_version", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
+    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
                                  "gemm_dynamic_schedule", "gemm_resid_prefetch_chunks"};
     for (const char* key : keys) {
       std::string env = std::string("HB_DEBUG_") + key;
@@ -393,6 +406,8 @@ int hb_debug_set(const char* key, int value) {
   } else if (k == "attention_version") {
     if (value < 1 || value > 3) return fail(HB_ERR_INVALID, "attention version must be 1, 2 or 3");
     g_attn_version = value;
+  } else if (k == "small_attention_tc") {
+    g_small_attn_tc = value ? 1 : 0;
   } else if (k == "attention_prefetch") {
     g_attn_prefetch = value ? 1 : 0;
   } else if (k == "ln_fold") {
@@ -639,7 +654,7 @@ struct HbText {
   struct PLayer { SplitLinear qkv, out, fc, cproj; };
   std::vector<std::unique_ptr<PLayer>> players;
   SplitLinear proj_s;
-  DevBuf op, opE, lnb, qkvf, att, mid, eotf;
+  DevBuf op, opE, lnb, qkvf, att, mid, eotf, attn_ws;
   CUtensorMap tm_w, tm_4w, tm_eot;
 };
 
@@ -696,6 +711,7 @@ int hb_text_create(const HbTextConfig* cfg, const HbTextWeights* w, int max_batc
     if ((r = m->att.alloc(static_cast<size_t>(rows) * W * 4))) return r;
     if ((r = m->mid.alloc(static_cast<size_t>(rows) * 4 * W * 4))) return r;
     if ((r = m->eotf.alloc(static_cast<size_t>(m->chunk) * W * 4))) return r;
+    if ((r = m->attn_ws.alloc(hb::small_attn_tc_workspace(m->chunk, cfg->heads, C, C)))) return r;
     if (hb::make_tmap_bf16(&m->tm_w, m->op.p, rows, 3 * W, 3 * W, hb::gemm_a_box_rows()) ||
         hb::make_tmap_bf16(&m->tm_4w, m->op.p, rows, 12 * W, 12 * W, hb::gemm_a_box_rows()) ||
         hb::make_tmap_bf16(&m->tm_eot, m->opE.p, m->chunk, 3 * W, 3 * W, hb::gemm_a_box_rows()))
@@ -735,7 +751,7 @@ static int text_encode_chunk(HbText* m, const int64_t* ids, int Q, float* out, c
       ap.ldq = ap.ldk = ap.ldv = 3 * W; ap.ldo = W;
       ap.bsq = ap.bsk = ap.bsv = static_cast<long long>(C) * 3 * W; ap.bso = static_cast<long long>(C) * W;
       ap.scale = 0.125f; ap.mask_mode = 1;   // causal, eva_model.py:224-230
-      HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::small_attn_f32_launch(ap, s));
+      if ((r = small_attn_f32_auto(ap, m->attn_ws, s))) return r;
       if ((r = split_gemm_op(op, att, M, W, 0, m->tm_w, P.out, x, hb::EPI_F32, s, x))) return r;
       if ((r = ln_f32(x, lnb, L.l2w, L.l2b, c.ln_eps, M, W, s))) return r;
       if ((r = split_gemm_op(op, lnb, M, W, 0, m->tm_w, P.fc, mid, hb::EPI_F32, s))) return r;
@@ -973,6 +989,30 @@ int hb_vit_attention(const void* qkv, void* out, int64_t B, int H, void* stream)
   return HB_OK;
 }
 
+int hb_small_attention_f32(const float* q, const float* k, const float* v, float* out, int B, int H, int Tq, int Tk, int ldq, int ldk, int ldv,
+                           int ldo, int64_t bsq, int64_t bsk, int64_t bsv, int64_t bso, float scale, int mask_mode, float mask_const,
+                           int causal_soft, int use_tensor_cores, void* stream) {
+  if (!g_inited) return fail(HB_ERR_INVALID, "hb_init() not called");
+  if (!q || !k || !v || !out) return fail(HB_ERR_INVALID, "null argument");
+  hb::SmallAttnF32Params ap;
+  ap.q = q; ap.k = k; ap.v = v; ap.out = out; ap.B = B; ap.H = H; ap.Tq = Tq; ap.Tk = Tk;
+  ap.ldq = ldq; ap.ldk = ldk; ap.ldv = ldv; ap.ldo = ldo; ap.bsq = bsq; ap.bsk = bsk; ap.bsv = bsv; ap.bso = bso;
+  ap.scale = scale; ap.mask_mode = mask_mode; ap.mask_const = mask_const; ap.causal_soft = causal_soft;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!use_tensor_cores) {
+    HB_LAUNCH(hb::small_attn_f32_launch(ap, s));
+    return HB_OK;
+  }
+  const size_t bytes = hb::small_attn_tc_workspace(B, H, Tq, Tk);
+  void* ws = nullptr;
+  HB_CUDA(cudaMallocAsync(&ws, bytes, s));
+  const int r = hb::small_attn_tc_launch(ap, ws, bytes, s);
+  cudaFreeAsync(ws, s);
+  if (r != 0) return fail(r > 0 ? HB_ERR_CUDA : HB_ERR_INVALID, "small_attn_tc_launch failed: %d", r);
+  g_launches.fetch_add(2, std::memory_order_relaxed);
+  return HB_OK;
+}
+
 int hb_small_attention(const void* q, const void* k, const void* v, void* out, int B, int H, int Tq, int Tk, int ldq, int ldk,
                        int ldv, int ldo, int64_t bsq, int64_t bsk, int64_t bsv, int64_t bso, float scale, int mask_mode,
                        float mask_const, int causal_soft, void* stream) {
@@ -1004,7 +1044,7 @@ struct HbMoment {
   };
   std::vector<std::unique_ptr<Layer>> layers;
   DevBuf op, opT;                 // bf16 split operands [max_rows, 3*ffn], [max_batch, 3*clip_dim]
-  DevBuf vlin, asr_ln, asr_lin, tanh_in, temporal, base, f, tlin, that, e_lin, x, qkv, att, t1, h, mid;
+  DevBuf vlin, asr_ln, asr_lin, tanh_in, temporal, base, f, tlin, that, e_lin, x, qkv, att, t1, h, mid, attn_ws;
   // A-operand maps over `op` for each K in use
   CUtensorMap tm_clip, tm_asr, tm_e, tm_hd, tm_ffn, tm_text;
 };
@@ -1075,6 +1115,8 @@ int hb_moment_create(const HbMomentConfig* cfg, const HbMomentWeights* w, int64_
   ALLOCF(vlin, E); if (use_asr) { ALLOCF(asr_ln, A); ALLOCF(asr_lin, E); } ALLOCF(tanh_in, E); ALLOCF(temporal, E); ALLOCF(base, E); ALLOCF(f, E);
   ALLOCF(e_lin, Hd); ALLOCF(x, Hd); ALLOCF(qkv, 3 * Hd); ALLOCF(att, Hd); ALLOCF(t1, Hd); ALLOCF(h, Hd); ALLOCF(mid, Ff);
 #undef ALLOCF
+  // tensor-core attention workspace: bf16 split copies of q / k / v for max_rows tokens (any B x T with B * T <= max_rows)
+  if ((r = m->attn_ws.alloc(static_cast<size_t>(max_rows) * cfg->heads * (192 + 192 + 128) * 2 + 4096))) return r;
   if ((r = m->tlin.alloc(static_cast<size_t>(max_batch) * E * 4))) return r;
   if ((r = m->that.alloc(static_cast<size_t>(max_batch) * E * 4))) return r;
   auto amap = [&](CUtensorMap* tm, void* ptr, long long rows, int K) {
@@ -1139,7 +1181,7 @@ int hb_moment_forward(HbMoment* m, const float* video, const float* text_feat, c
     ap.ldq = ap.ldk = ap.ldv = 3 * Hd; ap.ldo = Hd;
     ap.bsq = ap.bsk = ap.bsv = static_cast<long long>(T) * 3 * Hd; ap.bso = static_cast<long long>(T) * Hd;
     ap.scale = 0.125f; ap.mask_mode = 2; ap.mask_const = -10000.0f;  // all-zeros mask quirk, modeling.py:208
-    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::small_attn_f32_launch(ap, s));
+    if ((r = small_attn_f32_auto(ap, m->attn_ws, s))) return r;
     if ((r = split_gemm(m, m->att.as<float>(), R, Hd, 0, m->tm_hd, L.ao, m->t1.as<float>(), hb::EPI_F32, s, x))) return r;
     if ((r = ln_f32(m->t1.as<float>(), m->h.as<float>(), L.ao_ln_w, L.ao_ln_b, 1e-12f, R, Hd, s))) return r;
     if ((r = split_gemm(m, m->h.as<float>(), R, Hd, 0, m->tm_hd, L.inter, m->mid.as<float>(), hb::EPI_F32, s))) return r;

@@ -58,5 +58,10 @@ struct SmallAttnF32Params {
   int kv_div = 1;  // K/V batch index = b / kv_div (beams of one instance share the encoder keys / values)
 };
 int small_attn_f32_launch(const SmallAttnF32Params& p, cudaStream_t stream);
+// Same contract on the tensor cores (hb_attn_tc.cu: split-bf16 UMMAs for q.k^T and p.v, fp32 softmax; fp32-accurate).  Needs a
+// device workspace of small_attn_tc_workspace() bytes (bf16 split copies of q / k / v); kv_div must be 1.  Returns -8 if the
+// workspace is too small.
+size_t small_attn_tc_workspace(int B, int H, int Tq, int Tk);
+int small_attn_tc_launch(const SmallAttnF32Params& p, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 }  // namespace hb

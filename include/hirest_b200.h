@@ -293,6 +293,13 @@ HB_API int hb_small_attention(const void* q, const void* k, const void* v, void*
                        int ldk, int ldv, int ldo, int64_t bsq, int64_t bsk, int64_t bsv, int64_t bso, float scale,
                        int mask_mode, float mask_const, int causal_soft, void* stream);
 
+/* fp32 in / fp32 out variant (MomentModel encoder, precise text tower, caption decoder): same arguments with fp32 pointers.
+ * use_tensor_cores != 0: split-bf16 tcgen05 UMMAs for q.k^T and p.v with fp32 softmax (fp32-accurate, hb_attn_tc.cu);
+ * 0: CUDA-core kernel.  Any Tq / Tk. */
+HB_API int hb_small_attention_f32(const float* q, const float* k, const float* v, float* out, int B, int H, int Tq, int Tk, int ldq,
+                                  int ldk, int ldv, int ldo, int64_t bsq, int64_t bsk, int64_t bsv, int64_t bso, float scale,
+                                  int mask_mode, float mask_const, int causal_soft, int use_tensor_cores, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,8 @@ extern "C" {
  * "gemm_cta_group"             1 | 2                 2         tcgen05 cta_group of the GEMMs (2 = CTA pairs, 256 x 256 tiles)
  * "attention_version"          1 | 2 | 3             3         ViT attention kernel: 3 persistent pipelined CTA per SM (hb_attn3.cu),
  *                                                              2 one CTA per 128-query tile (hb_attn2.cu), 1 one CTA per (frame, head)
+ * "small_attention_tc"         0 | 1                 1         fp32 attention of the small sequence models on tensor cores (hb_attn_tc.cu)
+ *                                                              instead of CUDA cores (hb_attn_small.cu); same results to ~1e-6
  * "attention_prefetch"         0 | 1                 0         v2 only: L2-prefetch the operands of the CTA one wave ahead (measured slower)
  * "ln_fold"                    0 | 1                 1         ViT handles created afterwards fold the block LayerNorms into the QKV / fc1
  *                                                              GEMM epilogues (1) or run separate LayerNorm kernels (0)

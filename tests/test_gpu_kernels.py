@@ -153,6 +153,52 @@ def test_small_attention(hb, mode, Tq, Tk):
     assert rel(out, ref) < 4e-3
 
 
+@pytest.mark.parametrize("tc", [1, 0], ids=["tensor_cores", "cuda_cores"])
+@pytest.mark.parametrize("mode", ["none", "causal", "const", "const_causal"])
+@pytest.mark.parametrize("Tq,Tk", [(77, 77), (300, 300), (40, 40), (130, 600), (1, 20), (257, 129)])
+def test_small_attention_f32(hb, tc, mode, Tq, Tk):
+    """fp32 attention of the small sequence models (MomentModel encoder, precise text tower): the split-bf16 tcgen05 kernel
+    (hb_attn_tc.cu) and the CUDA-core kernel against float64 torch, incl. the reference's -10000 fp32-add quirk
+    (module_visual.py:406-414), ragged tiles (T % 128 != 0), several key tiles with online softmax, and strided q / k / v views
+    of one fused qkv buffer as the models use them."""
+    if "causal" in mode and Tq != Tk:
+        pytest.skip("causal is self-attention only")
+    torch.manual_seed(Tq * 7 + Tk)
+    B, H = 3, 5
+    W = H * 64
+    qkv = torch.randn(B, max(Tq, Tk), 3 * W, device=DEV) * 1.5
+    q, k, v = qkv[:, :Tq, :W], qkv[:, :Tk, W:2 * W], qkv[:, :Tk, 2 * W:]
+    out = torch.full((B, Tq, W), float("nan"), device=DEV)
+    mask_mode = {"none": 0, "causal": 1, "const": 2, "const_causal": 2}[mode]
+    const = -10000.0 if mask_mode == 2 else 0.0
+    soft = 1 if mode == "const_causal" else 0
+    ld, bs = 3 * W, max(Tq, Tk) * 3 * W
+    _lib.check(hb.hb_small_attention_f32(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Tq, Tk, ld, ld, ld, W,
+                                         bs, bs, bs, Tq * W, 0.125, mask_mode, const, soft, tc, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    qh = q.double().reshape(B, Tq, H, 64).transpose(1, 2)
+    kh = k.double().reshape(B, Tk, H, 64).transpose(1, 2)
+    vh = v.double().reshape(B, Tk, H, 64).transpose(1, 2)
+    s = (qh @ kh.transpose(-2, -1)).float() * 0.125          # logits in fp32, like the reference
+    if mode == "causal":
+        s = s + torch.full((Tq, Tk), float("-inf"), device=DEV).triu_(1)
+    if mask_mode == 2:
+        s = s + const                                         # fp32 add quantises the logits exactly as module_visual.py:414 does
+        if soft:
+            s = s + torch.full((Tq, Tk), -10000.0, device=DEV).triu_(1)
+    ref = (s.double().softmax(-1) @ vh).transpose(1, 2).reshape(B, Tq, W)
+    assert torch.isfinite(out).all()
+    err = float((out.double() - ref).abs().max())
+    # with the -10000 add the logits are quantised to 2^-10: a logit that lands on the other side of a rounding boundary than the
+    # float64-accumulated one moves its weight by 0.1 %.  Without it the CUDA-core kernel is at fp32 round-off and the tensor-core
+    # kernel at the 3-term split's level (the dropped lo.lo products: ~2^-18 |q||k| per term -> ~1e-5 in the logits at this
+    # input scale of 1.5 sigma, the same precision class as the split GEMMs that produce q / k / v in the models)
+    r = rel(out, ref.float())
+    print(f"small_attention_f32 {'tc' if tc else 'cc'} {mode} {Tq}x{Tk}: max abs err {err:.2e}, rel {r:.2e}")
+    assert err < (3e-3 if mask_mode == 2 else (2e-4 if tc else 2e-5)), (mode, Tq, Tk, err)
+    assert r < (3e-4 if mask_mode == 2 else (2e-5 if tc else 2e-6))
+
+
 def test_small_attention_rejects_long_sequences(hb):
     t = torch.zeros(1, 800, 64, device=DEV, dtype=torch.bfloat16)
     rc = hb.hb_small_attention(t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), 1, 1, 800, 800, 64, 64, 64, 64, 0, 0, 0, 0,
