@@ -1234,7 +1234,7 @@ struct HbDecoder {
   std::vector<std::unique_ptr<Layer>> layers;
   int cur = 0;             // which ping-pong cache holds the live data
   DevBuf op, x, qkv, att, t1, s1, qc, c1, mid, th, logits;
-  DevBuf tok, scores, done, nsteps, prev_k, ys;
+  DevBuf tok, scores, done, nsteps, prev_k, ys, cand_v, cand_i;
   CUtensorMap tm_hd, tm_ffn, tm_enc;
 };
 
@@ -1318,6 +1318,8 @@ int hb_decoder_create(const HbDecoderConfig* cfg, const HbDecoderWeights* w, int
 #undef ALLOCD
   if ((r = d->tok.alloc(R * 8))) return r;
   if ((r = d->scores.alloc(R * 4))) return r;
+  if ((r = d->cand_v.alloc(R * max_beam * 4))) return r;
+  if ((r = d->cand_i.alloc(R * max_beam * 4))) return r;
   if ((r = d->done.alloc(static_cast<size_t>(max_inst) * 4))) return r;
   if ((r = d->nsteps.alloc(static_cast<size_t>(max_inst) * 4))) return r;
   if ((r = d->prev_k.alloc(static_cast<size_t>(cfg->max_words) * R * 4))) return r;
@@ -1420,7 +1422,8 @@ int hb_decoder_step(HbDecoder* d, void* stream) {
   int* pk = d->prev_k.as<int>() + static_cast<size_t>(pos) * R;
   HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::beam_advance_launch(d->logits.as<float>(), d->Vpad, c.vocab, d->scores.as<float>(), d->done.as<int>(),
                                                          d->nsteps.as<int>(), d->prev_k.as<int>(), d->ys.as<int>(), d->tok.as<long long>(),
-                                                         pos, d->n_inst, d->beam, c.eos, s));
+                                                         pos, d->n_inst, d->beam, c.eos, d->cand_v.as<float>(), d->cand_i.as<int>(), s));
+  g_launches.fetch_add(1, std::memory_order_relaxed);   // beam_advance is two kernels
   // beams re-order: new beam j continues old beam prev_k[j]
   for (auto& Lp : d->layers) {
     HbDecoder::Layer& L = *Lp;

@@ -230,10 +230,76 @@ __global__ void __launch_bounds__(SA_THREADS) small_attn_f32_kernel(const SmallA
   }
 }
 
+// Decode step (Tq == 1): one WARP per (batch row, head) — the caption decoder's self-attention over the KV cache (<= 48 keys)
+// and its cross-attention over the 20 clip frames (module_decoder.py:220-247).  Lanes take keys for q.k (fp32, q broadcast from
+// registers), the softmax is a warp reduction, lanes take dimension pairs for p.v.  The tiled kernel above staged a 256-key tile
+// with two __syncthreads per CTA for ONE query: 74 us per call, 24 % of step captioning.
+__global__ void __launch_bounds__(256) decode_attn_f32_kernel(const SmallAttnF32Params p) {
+  // Tk <= 64: every lane owns keys `lane` and `lane + 32`.  Operation order (4-way split dot product, max, exp, lane-major sum,
+  // key-ordered p.v) is that of small_attn_f32_kernel for a single tile, so both kernels give bit-identical results.
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= p.B * p.H) return;
+  const int b = w / p.H, h = w - b * p.H;
+  const float* qg = p.q + b * p.bsq + h * DH;
+  const float* kg = p.k + (b / p.kv_div) * p.bsk + h * DH;
+  const float* vg = p.v + (b / p.kv_div) * p.bsv + h * DH;
+  const float2 q2 = *reinterpret_cast<const float2*>(qg + lane * 2);   // lane holds q[2 lane], q[2 lane + 1]
+  float s[2];
+  float m = -INFINITY;
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    const int key = jj * 32 + lane;
+    s[jj] = -INFINITY;
+    const float* kr = kg + static_cast<size_t>(key < p.Tk ? key : 0) * p.ldk;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 16; ++ch) {
+      const float4 kv = __ldg(reinterpret_cast<const float4*>(kr + ch * 4));
+      const float qa = __shfl_sync(0xffffffffu, q2.x, ch * 2), qb = __shfl_sync(0xffffffffu, q2.y, ch * 2);
+      const float qc = __shfl_sync(0xffffffffu, q2.x, ch * 2 + 1), qd = __shfl_sync(0xffffffffu, q2.y, ch * 2 + 1);
+      a0 = fmaf(qa, kv.x, a0); a1 = fmaf(qb, kv.y, a1); a2 = fmaf(qc, kv.z, a2); a3 = fmaf(qd, kv.w, a3);
+    }
+    if (key < p.Tk) {
+      float acc = ((a0 + a1) + (a2 + a3)) * p.scale;
+      if (p.mask_mode == 2) acc = acc + p.mask_const;   // fp32 add, as the reference's mask add (the single query sees every key)
+      s[jj] = acc;
+      m = fmaxf(m, acc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float ts = 0.f;
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    s[jj] = expf(s[jj] - m);   // exp(-inf) = 0 for absent keys
+    ts += s[jj];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ts += __shfl_xor_sync(0xffffffffu, ts, o);
+  float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    const int nk = min(32, p.Tk - jj * 32);
+    for (int j = 0; j < nk; ++j) {
+      const float pw = __shfl_sync(0xffffffffu, s[jj], j);
+      const float2 vv = __ldg(reinterpret_cast<const float2*>(vg + static_cast<size_t>(jj * 32 + j) * p.ldv + lane * 2));
+      o0 = fmaf(pw, vv.x, o0);
+      o1 = fmaf(pw, vv.y, o1);
+    }
+  }
+  const float inv = 1.0f / ts;
+  *reinterpret_cast<float2*>(p.out + b * p.bso + h * DH + lane * 2) = make_float2(o0 * inv, o1 * inv);
+}
+
 }  // namespace
 
 int small_attn_f32_launch(const SmallAttnF32Params& p, cudaStream_t stream) {
   if (p.B <= 0 || p.H <= 0 || p.Tq <= 0 || p.Tk <= 0) return -3;
+  if (p.Tq == 1 && p.Tk <= 64 && p.mask_mode != 1 && !p.causal_soft) {
+    const long long warps = static_cast<long long>(p.B) * p.H;
+    decode_attn_f32_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, stream>>>(p);
+    return static_cast<int>(cudaGetLastError());
+  }
   const size_t smem = static_cast<size_t>(KT_F32) * (KF_STRIDE + VF_STRIDE);
   static bool attr_set = false;
   if (!attr_set) {

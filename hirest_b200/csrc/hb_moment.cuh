@@ -51,7 +51,8 @@ int gelu_f32_launch(float* x, long long n, cudaStream_t s);
 // Beam.advance for every still-active instance (one CTA each): log_softmax over V per beam row, + beam scores (row 0 only
 // at the first step), flat top-`beam` (sorted), prev_k = id / V, y = id % V; instance done when the best beam emits `eos`.
 // step is 0-based.  Records prev_k / ys of this step at [step, inst, :]; for finished instances prev_k is the identity.
+// cand_v / cand_i: device scratch of n_inst * beam * beam floats / ints (per-row candidates between the two kernels).
 int beam_advance_launch(const float* logits, int ldl, int V, float* scores, int* done, int* nsteps, int* prev_k_rec, int* ys_rec,
-                        long long* tok, int step, int n_inst, int beam, int eos, cudaStream_t s);
+                        long long* tok, int step, int n_inst, int beam, int eos, float* cand_v, int* cand_i, cudaStream_t s);
 
 }  // namespace hb
