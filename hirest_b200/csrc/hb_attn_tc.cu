@@ -9,10 +9,11 @@
 //                 is exact in fp32; only the lo.lo term (2^-16 relative) is dropped, as in the split GEMMs of hb_api.cu;
 //   O = p v     : p = hi + lo written back into the S columns it came from as packed bf16 (TS-form UMMA, A operand from TMEM),
 //                 v = hi + lo as MN-major B operands: p_lo.v_hi + p_hi.v_lo + p_hi.v_hi;
-//   softmax in fp32 with expf, online over 128-key tiles (running max / sum per query row; O rescaled in TMEM when the max moves).
+//   softmax in fp32 (ex2.approx on exactly formed differences), online over 128-key tiles (running max / sum per query row; O rescaled in TMEM when the max moves).
 // A prologue kernel splits q / k / v once per call into bf16 workspace buffers laid out [row, head, {192 | 192 | 64 | 64}], so the
-// main kernel's operands arrive by TMA in SWIZZLE_128B slabs.  One CTA per (batch, head, 128-query tile); warps 0-3 softmax
-// (thread = query row), warp 4 MMA issue, warp 5 TMA producer; K / V double-buffered, S double-buffered in TMEM.
+// main kernel's operands arrive by TMA in SWIZZLE_128B slabs.  One CTA per (batch, head, 128-query tile); warps 0-7 softmax (two
+// threads per query row, 64 keys of the tile each: with one thread per row the exp pass of a single warp per scheduler was
+// the critical path, 7 us per key tile), warp 8 MMA issue, warp 9 TMA producer; K / V double-buffered, S double-buffered in TMEM.
 #include "hb_attn.cuh"
 #include "hb_gemm.cuh"
 #include "hb_ptx.cuh"
@@ -23,13 +24,15 @@ namespace hb {
 namespace {
 
 constexpr int DH = 64;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // warps 0-7 softmax (2 threads per query row), warp 8 MMA issue, warp 9 TMA producer
 constexpr uint32_t SLAB = 16384;                       // 128 rows x 128 B
 constexpr uint32_t Q_OFF = 0;                          // 3 slabs
 constexpr uint32_t KV_OFF = 3 * SLAB;                  // per stage: K 3 slabs | V_hi | V_lo
 constexpr uint32_t STAGE = 5 * SLAB;
-constexpr uint32_t BAR_OFF = KV_OFF + 2 * STAGE;
+constexpr uint32_t XM_OFF = KV_OFF + 2 * STAGE;          // [2 halves][128] floats: row maxima / row sums exchanged between the halves
+constexpr uint32_t BAR_OFF = XM_OFF + 1024;
 constexpr uint32_t TC_SMEM = BAR_OFF + 256 + 1024;
+constexpr float LOG2E = 1.4426950408889634f;
 
 enum { B_Q = 0, B_KV_FULL0, B_KV_FULL1, B_KV_FREE0, B_KV_FREE1, B_S0, B_S1, B_P0, B_P1, B_O, B_N };
 
@@ -141,14 +144,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) small_attn_tc_kernel(const __gr
   int n_kt = (p.Tk + 127) / 128;
   if (p.mask_mode == 1) n_kt = min(n_kt, (min(p.Tq, q0 + 128) + 127) / 128);   // hard causal: no key beyond the tile's last query
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_init(bars + B_Q, 1);
       for (int s = 0; s < 2; ++s) {
         mbar_init(bars + B_KV_FULL0 + s, 1);
         mbar_init(bars + B_KV_FREE0 + s, 1);
         mbar_init(bars + B_S0 + s, 1);
-        mbar_init(bars + B_P0 + s, 4);
+        mbar_init(bars + B_P0 + s, 8);
       }
       mbar_init(bars + B_O, 1);
       fence_mbar_init();
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) small_attn_tc_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 5) {
+  if (warp == 9) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
       mbar_arrive_expect_tx(bars + B_Q, 3 * SLAB);
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) small_attn_tc_kernel(const __gr
       }
       __syncwarp();
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ------------------------------------------------------------------ MMA issue (whole warp walks, one elected lane issues)
     const uint32_t sb = __shfl_sync(0xffffffffu, sbase, 0);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -227,18 +230,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) small_attn_tc_kernel(const __gr
       __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------------ softmax: thread = query row
-    const int r = threadIdx.x;          // 0..127
+    // ------------------------------------------------------------------ softmax: two threads per query row
+    const int hf = warp >> 2;           // keys [64 hf, 64 hf + 64) of every tile; O columns [32 hf, 32 hf + 32)
+    const int r = (warp & 3) * 32 + lane;
     const int i = q0 + r;               // query index inside the sequence
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    float* xm = reinterpret_cast<float*>(smem + XM_OFF);
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_kt; ++j) {
       const int st = j & 1;
-      const uint32_t t_s = t_row + st * 128;
-      const int key0 = j * 128;
+      const uint32_t t_s = t_row + st * 128 + hf * 64;
+      const int key0 = j * 128 + hf * 64;
       mbar_wait(bars + B_S0 + st, (j >> 1) & 1);
       tc_fence_after();
-      auto logit = [&](uint32_t raw, int key) -> float {
+      // logits of this thread's 64 keys; masked keys -> -inf.  exp(x - m) is evaluated as exp2((x - m) * log2 e): the difference is
+      // taken FIRST, in natural units (exact for the -10000-shifted logits, which are multiples of 2^-10), then scaled
+      auto logit2 = [&](uint32_t raw, int key) -> float {
         float s = __uint_as_float(raw) * p.scale;
         if (p.mask_mode == 2) {
           s = s + p.mask_const;                               // fp32 add: quantises the logit exactly as the reference's mask add
@@ -251,42 +258,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) small_attn_tc_kernel(const __gr
       {
         uint32_t v[32];
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           tmem_ld_32x32(t_s + c * 32, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 32; ++k) tmax = fmaxf(tmax, logit(v[k], key0 + c * 32 + k));
+          for (int k = 0; k < 32; ++k) tmax = fmaxf(tmax, logit2(v[k], key0 + c * 32 + k));
         }
       }
+      xm[hf * 128 + r] = tmax;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      tmax = fmaxf(tmax, xm[(hf ^ 1) * 128 + r]);
       const float m_new = fmaxf(m_run, tmax);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;        // a row with no visible key yet: every p is exp(-inf) = 0
-      const float alpha = (m_run == -INFINITY) ? 0.f : expf(m_run - m_use);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;        // a row with no visible key yet: every p is exp2(-inf) = 0
+      float alpha;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(alpha) : "f"((m_run - m_use) * LOG2E));   // 0 while m_run = -inf
       if (j > 0) {
         // O holds sum_j' p v relative to m_run: bring it to m_new before this tile's P.V accumulates on top
         mbar_wait(bars + B_O, (j - 1) & 1);
         tc_fence_after();
         uint32_t o[32];
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          tmem_ld_32x32(t_row + 256 + c * 32, o);
-          tmem_ld_wait();
+        tmem_ld_32x32(t_row + 256 + hf * 32, o);
+        tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
-          tmem_st_32x32(t_row + 256 + c * 32, o);
-        }
+        for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+        tmem_st_32x32(t_row + 256 + hf * 32, o);
       }
       float tsum = 0.f;
       {
         uint32_t v[32];
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 2; ++c) {
           tmem_ld_32x32(t_s + c * 32, v);
           tmem_ld_wait();
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
-            const float p0 = expf(logit(v[2 * k], key0 + c * 32 + 2 * k) - m_use);
-            const float p1 = expf(logit(v[2 * k + 1], key0 + c * 32 + 2 * k + 1) - m_use);
+            float p0, p1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"((logit2(v[2 * k], key0 + c * 32 + 2 * k) - m_use) * LOG2E));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"((logit2(v[2 * k + 1], key0 + c * 32 + 2 * k + 1) - m_use) * LOG2E));
             tsum += p0 + p1;
             const __nv_bfloat16 h0 = __float2bfloat16(p0), h1 = __float2bfloat16(p1);
             hi[k] = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
@@ -302,29 +311,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) small_attn_tc_kernel(const __gr
       if (lane == 0) mbar_arrive(bars + B_P0 + st);
       l_run = l_run * alpha + tsum;
       m_run = m_new;
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // both halves have read xm before the next tile overwrites it
     }
-    // ---- output
+    // ---- output: this thread's 32 columns of O / (row sum over both halves)
+    xm[hf * 128 + r] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float inv = 1.0f / (l_run + xm[(hf ^ 1) * 128 + r]);
     mbar_wait(bars + B_O, (n_kt - 1) & 1);
     tc_fence_after();
-    const float inv = 1.0f / l_run;
-    float* og = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(i) * p.ldo + h * DH;
+    float* og = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(i) * p.ldo + h * DH + hf * 32;
     uint32_t o[32];
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
-      tmem_ld_32x32(t_row + 256 + c * 32, o);
-      tmem_ld_wait();
-      if (i < p.Tq) {
+    tmem_ld_32x32(t_row + 256 + hf * 32, o);
+    tmem_ld_wait();
+    if (i < p.Tq) {
 #pragma unroll
-        for (int k = 0; k < 32; k += 4)
-          *reinterpret_cast<float4*>(og + c * 32 + k) = make_float4(__uint_as_float(o[k]) * inv, __uint_as_float(o[k + 1]) * inv,
-                                                                    __uint_as_float(o[k + 2]) * inv, __uint_as_float(o[k + 3]) * inv);
-      }
+      for (int k = 0; k < 32; k += 4)
+        *reinterpret_cast<float4*>(og + k) = make_float4(__uint_as_float(o[k]) * inv, __uint_as_float(o[k + 1]) * inv,
+                                                         __uint_as_float(o[k + 2]) * inv, __uint_as_float(o[k + 3]) * inv);
     }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 4) tmem_dealloc<1>(tmem_base, 512);
+  if (warp == 8) tmem_dealloc<1>(tmem_base, 512);
 }
 
 }  // namespace
