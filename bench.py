@@ -29,11 +29,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "frames/sec encoded+scored (EVA-CLIP-g/14 224px)"
-# dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, mean over the four GEMMs of one ViT layer at 1024 frames
-# (QKV 2.95, proj 4.42, fc1 3.97, fc2 6.96 GB) from the `ncu --set full` capture in profiles/r01_one_layer_ncu_full.txt;
-# algorithmic bytes of the same four launches: 2.96 + 4.44 + 3.97 + 6.93 GB (fp32 residual in/out + bf16 copy counted for
-# proj / fc2): every GEMM now moves its algorithmic bytes and nothing else.
-GEMM_TRAFFIC_BYTES_PER_LAUNCH = 4.57e9
+
+
+def gemm_traffic():
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch (mean over the four GEMMs of one ViT layer at
+    1024 frames) READ from the committed summary of the `ncu --set full` capture (profiles/gemm_traffic.json, written by
+    tools/profile_layer.sh -> tools/ncu_summary.py --json); null if the file is missing — never a literal in this script."""
+    path = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["gemm_dram_bytes_per_launch_mean"]), f"profiles/gemm_traffic.json ({d.get('source', 'ncu')})"
+    except Exception:
+        return None, "profiles/gemm_traffic.json missing"
+
+
 UNIT = "frames/s"
 
 
@@ -473,7 +483,8 @@ def main():
                    "residual_stream": "fp32", "gemm_operands": "bf16, fp32 accumulate", "l2": "inputs_larger_than_l2",
                    "parallelism": f"frame-shard dp{world}" if world > 1 else "single GPU"},
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_tflops"], "traffic": GEMM_TRAFFIC_BYTES_PER_LAUNCH, "peak_source": peaks["source"],
+                     "frac": achieved / peaks["bf16_tflops"], "traffic": gemm_traffic()[0], "traffic_source": gemm_traffic()[1],
+                     "peak_source": peaks["source"],
                      "kernel": "hb::gemm_kernel<CG=2,*> (all tcgen05 GEMM launches)", "launches_per_step": gemm_launches / args.steps,
                      "gemm_share_of_kernel_time": gemm_ms / kernel_ms_total if kernel_ms_total else None,
                      "whole_step_tflops": flops_frame * B / (ms_total / args.steps * 1e-3) / 1e12,

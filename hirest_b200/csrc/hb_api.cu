@@ -4,6 +4,7 @@
 #include "../../include/hirest_b200_debug.h"
 
 #include <cuda_bf16.h>
+#include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -33,7 +34,8 @@ thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
 int g_cg = 2;
 int g_attn_version = 3;
-int g_small_attn_tc = 1;   // fp32 small-sequence attention on tensor cores (hb_attn_tc.cu) instead of CUDA cores
+int g_small_attn_tc = 1;
+int g_profile_layer = -1;   // debug: cudaProfilerStart/Stop around this ViT layer (ncu --profile-from-start off)   // fp32 small-sequence attention on tensor cores (hb_attn_tc.cu) instead of CUDA cores
 int g_attn_prefetch = 0;   // attention v2: L2-prefetch the operands of the CTA one wave ahead (measured: 1.05 -> 1.14 ms, off)
 int g_dyn_sched = 1; // ViT GEMMs take their tiles from an atomic counter (in sequence order) instead of a static round-robin
 int g_ln_fold = 1;   // fold the ViT block LayerNorms into the QKV / fc1 GEMM epilogues (no LayerNorm kernel)
@@ -360,7 +362,7 @@ int hb_init(int device) {
   g_num_sms = prop.multiProcessorCount;
   if (hb::tmap_init() != 0) return fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   if (!g_inited) {   // A/B switches from the environment (hirest_b200_debug.h), once
-    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
+    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "profile_layer", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
                                  "gemm_dynamic_schedule", "gemm_resid_prefetch_chunks"};
     for (const char* key : keys) {
       std::string env = std::string("HB_DEBUG_") + key;
@@ -408,6 +410,8 @@ int hb_debug_set(const char* key, int value) {
     g_attn_version = value;
   } else if (k == "small_attention_tc") {
     g_small_attn_tc = value ? 1 : 0;
+  } else if (k == "profile_layer") {
+    g_profile_layer = value;
   } else if (k == "attention_prefetch") {
     g_attn_prefetch = value ? 1 : 0;
   } else if (k == "ln_fold") {
@@ -560,6 +564,7 @@ static int vit_encode_chunk(HbVit* m, const float* frames, const uint8_t* frames
     lp1.xb_out = m->xb.ptr(); lp1.ld_xb = D; lp1.stats_out = m->stats1.as<float>();   // fc2   -> statistics for the next LN1
     for (int i = 0; i < c.layers; ++i) {
       HbVit::Layer& L = *m->layers[i];
+      if (i == g_profile_layer) { cudaStreamSynchronize(s); cudaProfilerStart(); }
       if ((r = run_gemm(m->xb.tm, L.qkv, M, qkv, 3 * D, hb::EPI_BF16_LN, s, nullptr, qscale, D, nullptr, 0, 0, 0, &lf1, sched))) return r;
       hb::AttnParams ap;
       ap.qkv = qkv; ap.out = m->h.ptr(); ap.B = B; ap.H = c.heads; ap.prefetch_ahead = g_attn_prefetch ? 2 * g_num_sms : 0;
@@ -567,6 +572,7 @@ static int vit_encode_chunk(HbVit* m, const float* frames, const uint8_t* frames
       if ((r = run_gemm(m->h.tm, L.proj, M, x, D, hb::EPI_F32_STATS, s, x, 1.f, 0, nullptr, 0, 0, 0, &lp2, sched))) return r;
       if ((r = run_gemm(m->xb.tm, L.fc1, M, m->hid.ptr(), F, hb::EPI_GELU_BF16_LN, s, nullptr, 1.f, 0, nullptr, 0, 0, 0, &lf2, sched))) return r;
       if ((r = run_gemm(m->hid.tm, L.fc2, M, x, D, hb::EPI_F32_STATS, s, x, 1.f, 0, nullptr, 0, 0, 0, &lp1, sched))) return r;
+      if (i == g_profile_layer) { cudaStreamSynchronize(s); cudaProfilerStop(); }
       if (m->tap_layer == i + 1 && m->tap_dst)
         HB_CUDA(cudaMemcpyAsync(m->tap_dst, x, static_cast<size_t>(M) * D * 4, cudaMemcpyDeviceToDevice, s));
     }

@@ -145,3 +145,60 @@ def test_prompts_are_tokenized_when_ids_are_missing():
     assert calls == ["aaaaa", "bbbbbbbb"]
     with pytest.raises(ValueError):
         pipeline.run_end_to_end(Probe(), vids)
+
+
+@pytest.mark.gpu
+def test_cfg5_chain_eight_videos_match_oracle_with_real_text_tower(hb, tmp_path):
+    """BASELINE configs[4] shapes (120-600 frame videos, beam 3, 48 words): 8 videos through the in-memory chain with the repo's own
+    precise EVA text tower, against the CPU restatement of the reference flow fed with the ORACLE's text features — bounds and step
+    boundaries must be identical, captions identical up to beam near-ties (see the comment at the end)."""
+    from hirest_b200 import eva_clip, moment
+    from oracle import eva_oracle, pipeline_oracle as po
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(17)
+    prompt_ids = synthetic.make_tokens(3, synthetic.EVA_G14, seed=77)
+    clip_sd = synthetic.make_chain_clip_state_dict()
+    with torch.no_grad():
+        tfeat = eva_oracle.encode_text(clip_sd, prompt_ids, synthetic.CHAIN_CLIP)
+    test, feats, videos = {}, {}, []
+    for k in range(8):
+        pi = k // 3                      # grouped by prompt, like the annotation file
+        p = f"prompt {pi}"
+        T = int(torch.randint(120, 601, (1,), generator=g))
+        vis = torch.randn(T, 1024, generator=g)
+        vis = vis / vis.norm(dim=-1, keepdim=True)
+        asr = torch.randn(T, 384, generator=g)
+        fn = f"vid{k:02d}"
+        videos.append({"prompt": p, "fname": fn, "video_duration": T, "vis_feats": vis, "asr_feats": asr, "clip_text_ids": prompt_ids[pi]})
+        test.setdefault(p, {})[fn] = {"video_duration": T}
+        feats[fn] = {"vis_feats": vis, "asr_feats": asr, "text_feat": {p: tfeat[pi]}}
+    vocab_path, vocab = _write_vocab(tmp_path)
+    clip = eva_clip.EVA_CLIP(**synthetic.CHAIN_CLIP)
+    clip.load_state_dict(clip_sd, strict=True)
+    sd = synthetic.make_moment_state_dict(seed=3)
+    m = moment.MomentModel(-1, 384, moment.default_args(bert_vocab_path=vocab_path), clip_model=clip.to(dev).eval(), max_rows=8 * 600, max_batch=8)
+    m.load_state_dict(sd, strict=False)
+    m = m.to(dev)
+    got = pipeline.run_end_to_end(m, videos, batch_size=8, num_beams=3)
+    with torch.no_grad():
+        ref = po.run_end_to_end(sd, test, feats, vocab, batch_size=8, num_beams=3)
+    assert got["moment_retrieval"] == ref["moment_retrieval"]
+    assert {k: v["pred_bounds"] for k, v in got["moment_segmentation"].items()} == {k: v["pred_bounds"] for k, v in ref["moment_segmentation"].items()}
+    bad = []
+    for p in ref["final"]:
+        for fn, a in ref["final"][p].items():
+            assert got["final"][p][fn]["bounds"] == a["bounds"], (p, fn)
+            assert [s["absolute_bounds"] for s in got["final"][p][fn]["steps"]] == [s["absolute_bounds"] for s in a["steps"]], (p, fn)
+            for sg, sr in zip(got["final"][p][fn]["steps"], a["steps"]):
+                if sg["heading"] != sr["heading"]:
+                    wg, wr = sg["heading"].split(), sr["heading"].split()
+                    first = next((i for i, (x, y) in enumerate(zip(wg, wr)) if x != y), min(len(wg), len(wr)))
+                    bad.append((fn, sg["index"], first, len(wg), len(wr)))
+    n_steps = sum(len(a["steps"]) for p in got["final"] for a in got["final"][p].values())
+    print(f"cfg5 x 8 videos: {n_steps} steps captioned, captions differing from the CPU oracle: {bad}")
+    # Moment bounds and step boundaries must be identical.  Captions: with RANDOM-INIT decoder weights the 30522-way distributions
+    # are nearly flat, so beam search meets genuine near-ties; the fp32-accurate GPU path (1e-5 relative on the text feature, 2^-17 on
+    # the GEMMs) may take the other branch of such a tie.  Measured: 96 of 97 captions identical (one diverges at word 11 of 48, with
+    # the CUDA-core attention as well as with the tensor-core one); the gate allows 5 %.
+    assert n_steps >= 16 and len(bad) <= 0.05 * n_steps

@@ -6,11 +6,11 @@
 # A number printed by a run under ncu is never a bench value.
 set -e
 mkdir -p gpurun_out
-KERNELS='gemm_kernel|vit_attn|layernorm|row_stats|small_attn|im2col|pool_norm|text_embed|split_bf16|cls_row'
+KERNELS='gemm_kernel|vit_attn|layernorm|row_stats|small_attn|im2col|pool_norm|text_embed|split_bf16|cls_row|split3|attn_split'
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"$KERNELS" -c 1400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_list.log 2>&1
-# with the filter below the patch-embed GEMM is launch 98 of the run (text tower first), layer 0 starts at 99, 5 launches per layer
-ncu --set full --clock-control none --import-source on -k regex:"gemm_kernel|vit_attn2" -s 119 -c 5 -o gpurun_out/layer -f \
+# one ViT layer (layer 4) of an encode_image call: the library brackets it with cudaProfilerStart / Stop (HB_DEBUG_PROFILE_LAYER)
+HB_DEBUG_PROFILE_LAYER=4 ncu --profile-from-start off --set full --clock-control none --import-source on -c 5 -o gpurun_out/layer -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_full.log 2>&1
-python tools/ncu_summary.py gpurun_out/layer.ncu-rep "one ViT layer, see profiles/r01_one_layer_ncu_full.txt" > gpurun_out/layer_summary.txt
+python tools/ncu_summary.py gpurun_out/layer.ncu-rep --json gpurun_out/gemm_traffic.json "one ViT layer (layer 4), EVA-CLIP-g/14, 1024 frames" > gpurun_out/layer_summary.txt
 python tools/sustained_gemm.py > gpurun_out/sustained.json
