@@ -35,6 +35,7 @@ std::atomic<int64_t> g_launches{0};
 int g_cg = 2;
 int g_attn_version = 3;
 int g_small_attn_tc = 1;
+int g_decoder_graphs = 1;   // replay the caption decoder's steps as CUDA graphs (from the second search of a shape on)
 int g_profile_layer = -1;   // debug: cudaProfilerStart/Stop around this ViT layer (ncu --profile-from-start off)   // fp32 small-sequence attention on tensor cores (hb_attn_tc.cu) instead of CUDA cores
 int g_attn_prefetch = 0;   // attention v2: L2-prefetch the operands of the CTA one wave ahead (measured: 1.05 -> 1.14 ms, off)
 int g_dyn_sched = 1; // ViT GEMMs take their tiles from an atomic counter (in sequence order) instead of a static round-robin
@@ -362,7 +363,7 @@ int hb_init(int device) {
   g_num_sms = prop.multiProcessorCount;
   if (hb::tmap_init() != 0) return fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   if (!g_inited) {   // A/B switches from the environment (hirest_b200_debug.h), once
-    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "profile_layer", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
+    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "decoder_graphs", "profile_layer", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
                                  "gemm_dynamic_schedule", "gemm_resid_prefetch_chunks"};
     for (const char* key : keys) {
       std::string env = std::string("HB_DEBUG_") + key;
@@ -410,6 +411,8 @@ int hb_debug_set(const char* key, int value) {
     g_attn_version = value;
   } else if (k == "small_attention_tc") {
     g_small_attn_tc = value ? 1 : 0;
+  } else if (k == "decoder_graphs") {
+    g_decoder_graphs = value ? 1 : 0;
   } else if (k == "profile_layer") {
     g_profile_layer = value;
   } else if (k == "attention_prefetch") {
@@ -1242,6 +1245,18 @@ struct HbDecoder {
   DevBuf op, x, qkv, att, t1, s1, qc, c1, mid, th, logits;
   DevBuf tok, scores, done, nsteps, prev_k, ys, cand_v, cand_i;
   CUtensorMap tm_hd, tm_ffn, tm_enc;
+  // CUDA graphs of the decode steps, valid for one (n_inst, beam, enc_len) shape
+  std::vector<cudaGraphExec_t> graphs;
+  std::vector<int64_t> graph_launches;   // kernels per step graph (hb_launch_count stays the number of kernels run)
+  int g_n_inst = -1, g_beam = -1, g_enc_len = -1, searches_with_shape = 0;
+  cudaStream_t cap_stream = nullptr;     // capture happens here: the caller's stream may be the legacy default stream, which cannot capture
+  void drop_graphs() {
+    for (auto& e : graphs) if (e) { cudaGraphExecDestroy(e); e = nullptr; }
+  }
+  ~HbDecoder() {
+    drop_graphs();
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+  }
 };
 
 extern "C" {
@@ -1365,6 +1380,12 @@ int hb_decoder_begin(HbDecoder* d, const float* enc, int n_inst, int enc_len, in
   if (n_inst <= 0 || n_inst > d->max_inst || beam <= 0 || beam > d->max_beam || enc_len <= 0 || enc_len > d->max_enc)
     return fail(HB_ERR_INVALID, "decoder batch (%d instances, beam %d, %d frames) exceeds the handle's capacity", n_inst, beam, enc_len);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (n_inst != d->g_n_inst || beam != d->g_beam || enc_len != d->g_enc_len) {
+    d->drop_graphs();
+    d->g_n_inst = n_inst; d->g_beam = beam; d->g_enc_len = enc_len; d->searches_with_shape = 0;
+  } else {
+    d->searches_with_shape += 1;
+  }
   d->n_inst = n_inst; d->beam = beam; d->enc_len = enc_len; d->step = 0; d->cur = 0;
   const int R = n_inst * beam, Hd = d->cfg.hidden;
   int r;
@@ -1381,10 +1402,11 @@ int hb_decoder_begin(HbDecoder* d, const float* enc, int n_inst, int enc_len, in
   return HB_OK;
 }
 
-int hb_decoder_step(HbDecoder* d, void* stream) {
-  if (!d || d->n_inst <= 0) return fail(HB_ERR_INVALID, "hb_decoder_begin() not called");
-  if (d->step >= d->cfg.max_words) return fail(HB_ERR_INVALID, "max_words steps already taken");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+}  // extern "C"
+
+// The ~50 launches of one decode step (everything below reads / writes handle-owned buffers only, so a step is a pure function
+// of (step index, n_inst, beam, enc_len) and can be replayed as a CUDA graph).
+static int decoder_step_launches(HbDecoder* d, cudaStream_t s) {
   const HbDecoderConfig& c = d->cfg;
   const int R = d->n_inst * d->beam, Hd = c.hidden, Ff = c.ffn, pos = d->step, Tmax = c.max_words;
   float* x = d->x.as<float>();
@@ -1435,6 +1457,48 @@ int hb_decoder_step(HbDecoder* d, void* stream) {
     HbDecoder::Layer& L = *Lp;
     HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::dec_cache_reorder_launch(L.kc[d->cur].as<float>(), L.vc[d->cur].as<float>(), L.kc[d->cur ^ 1].as<float>(),
                                                                 L.vc[d->cur ^ 1].as<float>(), pk, pos + 1, R, d->beam, Tmax, Hd, s));
+  }
+  return HB_OK;
+}
+
+extern "C" {
+
+int hb_decoder_step(HbDecoder* d, void* stream) {
+  if (!d || d->n_inst <= 0) return fail(HB_ERR_INVALID, "hb_decoder_begin() not called");
+  if (d->step >= d->cfg.max_words) return fail(HB_ERR_INVALID, "max_words steps already taken");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int r = HB_OK;
+  // CUDA graphs: the first search with a given (n_inst, beam, enc_len) runs eagerly (it also warms every lazily set kernel
+  // attribute); from the second search on each step index is captured once and then replayed with one cudaGraphLaunch instead of
+  // ~50 kernel launches (launch-bound: a step is ~0.85 ms of 15-us kernels).  Per-launch profiling bypasses the graphs.
+  const bool use_graph = g_decoder_graphs && !g_prof_on && d->searches_with_shape >= 1;
+  if (use_graph) {
+    if (d->graphs.size() != static_cast<size_t>(d->cfg.max_words)) d->graphs.assign(d->cfg.max_words, nullptr);
+    cudaGraphExec_t& exec = d->graphs[d->step];
+    if (exec == nullptr) {
+      cudaGraph_t g = nullptr;
+      const int64_t n0 = g_launches.load();
+      // recording only: nothing runs on cap_stream, the instantiated graph is launched on the caller's stream below
+      if (!d->cap_stream) HB_CUDA(cudaStreamCreateWithFlags(&d->cap_stream, cudaStreamNonBlocking));
+      HB_CUDA(cudaStreamBeginCapture(d->cap_stream, cudaStreamCaptureModeThreadLocal));
+      r = decoder_step_launches(d, d->cap_stream);
+      if (d->graph_launches.size() != d->graphs.size()) d->graph_launches.assign(d->graphs.size(), 0);
+      d->graph_launches[d->step] = g_launches.exchange(n0) - n0;   // kernels recorded, not yet run: counted at every replay below
+      cudaError_t e = cudaStreamEndCapture(d->cap_stream, &g);
+      if (r != HB_OK || e != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        if (r == HB_OK) return fail(HB_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+        return r;
+      }
+      e = cudaGraphInstantiate(&exec, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) { exec = nullptr; return fail(HB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
+    }
+    HB_CUDA(cudaGraphLaunch(exec, s));
+    g_launches.fetch_add(d->graph_launches[d->step], std::memory_order_relaxed);
+  } else {
+    r = decoder_step_launches(d, s);
+    if (r != HB_OK) return r;
   }
   d->cur ^= 1;
   d->step += 1;

@@ -17,6 +17,8 @@ extern "C" {
  *                                                              2 one CTA per 128-query tile (hb_attn2.cu), 1 one CTA per (frame, head)
  * "small_attention_tc"         0 | 1                 1         fp32 attention of the small sequence models on tensor cores (hb_attn_tc.cu)
  *                                                              instead of CUDA cores (hb_attn_small.cu); same results to ~1e-6
+ * "decoder_graphs"             0 | 1                 1         caption decoder: replay each decode step as a CUDA graph from the second
+ *                                                              beam search of a (n_inst, beam, enc_len) shape on; same results
  * "profile_layer"              -1 | layer            -1        cudaProfilerStart / Stop around this ViT layer of every encode_image chunk
  *                                                              (ncu --profile-from-start off captures exactly its 5 kernels)
  * "attention_prefetch"         0 | 1                 0         v2 only: L2-prefetch the operands of the CTA one wave ahead (measured slower)
