@@ -35,6 +35,7 @@ std::atomic<int64_t> g_launches{0};
 int g_cg = 2;
 int g_attn_version = 3;
 int g_small_attn_tc = 1;
+int g_dec_split_kbs = 6;    // caption decoder: k-blocks (64 bf16) per split-K slice of the hidden-width linears; 0 = no split-K
 int g_decoder_graphs = 1;   // replay the caption decoder's steps as CUDA graphs (from the second search of a shape on)
 int g_profile_layer = -1;   // debug: cudaProfilerStart/Stop around this ViT layer (ncu --profile-from-start off)   // fp32 small-sequence attention on tensor cores (hb_attn_tc.cu) instead of CUDA cores
 int g_attn_prefetch = 0;   // attention v2: L2-prefetch the operands of the CTA one wave ahead (measured: 1.05 -> 1.14 ms, off)
@@ -363,7 +364,7 @@ int hb_init(int device) {
   g_num_sms = prop.multiProcessorCount;
   if (hb::tmap_init() != 0) return fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   if (!g_inited) {   // A/B switches from the environment (hirest_b200_debug.h), once
-    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "decoder_graphs", "profile_layer", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
+    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "decoder_graphs", "decoder_split_k", "profile_layer", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
                                  "gemm_dynamic_schedule", "gemm_resid_prefetch_chunks"};
     for (const char* key : keys) {
       std::string env = std::string("HB_DEBUG_") + key;
@@ -413,6 +414,9 @@ int hb_debug_set(const char* key, int value) {
     g_small_attn_tc = value ? 1 : 0;
   } else if (k == "decoder_graphs") {
     g_decoder_graphs = value ? 1 : 0;
+  } else if (k == "decoder_split_k") {
+    if (value < 0) return fail(HB_ERR_INVALID, "decoder_split_k must be >= 0");
+    g_dec_split_kbs = value;
   } else if (k == "profile_layer") {
     g_profile_layer = value;
   } else if (k == "attention_prefetch") {
@@ -1244,6 +1248,8 @@ struct HbDecoder {
   int cur = 0;             // which ping-pong cache holds the live data
   DevBuf op, x, qkv, att, t1, s1, qc, c1, mid, th, logits;
   DevBuf tok, scores, done, nsteps, prev_k, ys, cand_v, cand_i;
+  static constexpr int MAX_SPLITS = 16;
+  DevBuf skws;             // split-K partial sums [MAX_SPLITS, max rows, hidden] fp32
   CUtensorMap tm_hd, tm_ffn, tm_enc;
   // CUDA graphs of the decode steps, valid for one (n_inst, beam, enc_len) shape
   std::vector<cudaGraphExec_t> graphs;
@@ -1341,6 +1347,7 @@ int hb_decoder_create(const HbDecoderConfig* cfg, const HbDecoderWeights* w, int
   if ((r = d->scores.alloc(R * 4))) return r;
   if ((r = d->cand_v.alloc(R * max_beam * 4))) return r;
   if ((r = d->cand_i.alloc(R * max_beam * 4))) return r;
+  if ((r = d->skws.alloc(static_cast<size_t>(HbDecoder::MAX_SPLITS) * R * Hd * 4))) return r;
   if ((r = d->done.alloc(static_cast<size_t>(max_inst) * 4))) return r;
   if ((r = d->nsteps.alloc(static_cast<size_t>(max_inst) * 4))) return r;
   if ((r = d->prev_k.alloc(static_cast<size_t>(cfg->max_words) * R * 4))) return r;
@@ -1361,13 +1368,51 @@ void hb_decoder_destroy(HbDecoder* d) { delete d; }
 namespace {
 
 // act [rows, K] fp32 -> split operand -> GEMM with SplitLinear -> out fp32 [rows, N] (+ fp32 residual)
+// GEMM of a decoder linear whose split operand already sits in d->op
+int dec_gemm_raw(HbDecoder* d, long long rows, int K, const CUtensorMap& tmA, const SplitLinear& L, float* out, cudaStream_t s,
+                 const float* resid = nullptr) {
+  hb::GemmParams p;
+  p.M = static_cast<int>(rows); p.N = L.N; p.K = 3 * K;
+  {  // wide outputs (the vocabulary projection): whole rounds of N tiles over the workers; depends on N only
+    const int workers = g_num_sms / L.cg, min_tiles = (L.N + 255) / 256;
+    if (min_tiles > workers) p.n_tiles = (min_tiles + workers - 1) / workers * workers;
+  }
+  p.bias = L.has_bias ? L.b.as<float>() : nullptr; p.out = out; p.ldo = L.N; p.resid = resid;
+  HB_LAUNCH_P(CAT_GEMM_F32, 2.0 * rows * L.N * 3.0 * K, s, hb::gemm_launch(tmA, L.tm, p, hb::EPI_F32, L.cg, g_num_sms, s));
+  return 0;
+}
+
 int dec_gemm(HbDecoder* d, const float* act, long long rows, int K, int gelu, const CUtensorMap& tmA, const SplitLinear& L, float* out,
              cudaStream_t s, const float* resid = nullptr) {
   HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(act, d->op.as<__nv_bfloat16>(), rows, K, gelu, s));
+  return dec_gemm_raw(d, rows, K, tmA, L, out, s, resid);
+}
+
+// Split-K form for the decode steps' narrow linears (N = hidden: 3 column tiles, so 3 CTA pairs streamed the whole K = 2304 /
+// 9216 operand at one SM's L2 bandwidth — 20 / 51 us per GEMM at R = 192 rows).  The slice count depends on K only, never on
+// the number of rows, so a beam's arithmetic is the same whatever else shares the batch.  Operand in d->op; partial sums go
+// to d->skws and are reduced by dec_finish.
+int dec_split_count(int K) {
+  if (g_dec_split_kbs <= 0) return 1;
+  const int k_blocks = (3 * K + 63) / 64;
+  int S = k_blocks / g_dec_split_kbs;
+  S = S < 1 ? 1 : (S > HbDecoder::MAX_SPLITS ? HbDecoder::MAX_SPLITS : S);
+  const int kbs = (k_blocks + S - 1) / S;
+  return (k_blocks + kbs - 1) / kbs;   // every slice non-empty
+}
+int dec_gemm_split(HbDecoder* d, long long rows, int K, const CUtensorMap& tmA, const SplitLinear& L, int S, cudaStream_t s) {
   hb::GemmParams p;
   p.M = static_cast<int>(rows); p.N = L.N; p.K = 3 * K;
-  p.bias = L.has_bias ? L.b.as<float>() : nullptr; p.out = out; p.ldo = L.N; p.resid = resid;
+  p.out = d->skws.p; p.ldo = L.N; p.k_splits = S; p.split_stride = rows * L.N;
   HB_LAUNCH_P(CAT_GEMM_F32, 2.0 * rows * L.N * 3.0 * K, s, hb::gemm_launch(tmA, L.tm, p, hb::EPI_F32, L.cg, g_num_sms, s));
+  return 0;
+}
+int dec_finish(HbDecoder* d, long long rows, const SplitLinear& L, int S, const float* resid, int gelu, const F32Vec* lnw, const F32Vec* lnb,
+               float* y, bool emit_op, cudaStream_t s) {
+  HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s,
+              hb::splitk_finish_launch(d->skws.as<float>(), rows * L.N, S, L.has_bias ? L.b.as<float>() : nullptr, resid,
+                                       lnw ? lnw->ptr() : nullptr, lnb ? lnb->ptr() : nullptr, 1e-12f, gelu, y,
+                                       emit_op ? d->op.as<__nv_bfloat16>() : nullptr, static_cast<int>(rows), L.N, s));
   return 0;
 }
 
@@ -1413,11 +1458,17 @@ static int decoder_step_launches(HbDecoder* d, cudaStream_t s) {
   int r;
   HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::dec_embed_launch(d->tok.as<long long>(), d->word_emb.ptr(), d->pos_emb.ptr(), d->emb_ln_w.ptr(),
                                                       d->emb_ln_b.ptr(), pos, x, R, Hd, s));
+  // sk: the hidden-width linears run as split-K GEMM + finish (bias, residual, LayerNorm and the next GEMM's split operand in
+  // one kernel); `op_ready`: d->op already holds the split operand of the next linear's input
+  const bool sk = g_dec_split_kbs > 0 && Hd % 4 == 0 && Hd <= 1536;
+  const int S_hd = dec_split_count(Hd), S_ff = dec_split_count(Ff);
+  bool op_ready = false;
   for (auto& Lp : d->layers) {
     HbDecoder::Layer& L = *Lp;
     float* kc = L.kc[d->cur].as<float>();
     float* vc = L.vc[d->cur].as<float>();
-    if ((r = dec_gemm(d, x, R, Hd, 0, d->tm_hd, L.sqkv, d->qkv.as<float>(), s))) return r;
+    if (op_ready) { if ((r = dec_gemm_raw(d, R, Hd, d->tm_hd, L.sqkv, d->qkv.as<float>(), s))) return r; }
+    else if ((r = dec_gemm(d, x, R, Hd, 0, d->tm_hd, L.sqkv, d->qkv.as<float>(), s))) return r;
     HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::dec_cache_append_launch(d->qkv.as<float>(), kc, vc, pos, R, Tmax, Hd, s));
     hb::SmallAttnF32Params ap;  // one query (the new token) over the cached prefix: every cached key is <= the query position
     ap.q = d->qkv.as<float>(); ap.k = kc; ap.v = vc; ap.out = d->att.as<float>();
@@ -1426,9 +1477,18 @@ static int decoder_step_launches(HbDecoder* d, cudaStream_t s) {
     ap.bsq = 3 * Hd; ap.bsk = ap.bsv = static_cast<long long>(Tmax) * Hd; ap.bso = Hd;
     ap.scale = 0.125f; ap.mask_mode = 0;
     HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::small_attn_f32_launch(ap, s));
-    if ((r = dec_gemm(d, d->att.as<float>(), R, Hd, 0, d->tm_hd, L.so, d->t1.as<float>(), s, x))) return r;
-    if ((r = ln_f32(d->t1.as<float>(), d->s1.as<float>(), L.so_ln_w, L.so_ln_b, 1e-12f, R, Hd, s))) return r;
-    if ((r = dec_gemm(d, d->s1.as<float>(), R, Hd, 0, d->tm_hd, L.eq, d->qc.as<float>(), s))) return r;
+    // self-attention output: s1 = LN(dense(att) + x); cross-attention query: qc = dense(s1)
+    if (sk) {
+      HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(d->att.as<float>(), d->op.as<__nv_bfloat16>(), R, Hd, 0, s));
+      if ((r = dec_gemm_split(d, R, Hd, d->tm_hd, L.so, S_hd, s))) return r;
+      if ((r = dec_finish(d, R, L.so, S_hd, x, 0, &L.so_ln_w, &L.so_ln_b, d->s1.as<float>(), true, s))) return r;
+      if ((r = dec_gemm_split(d, R, Hd, d->tm_hd, L.eq, S_hd, s))) return r;
+      if ((r = dec_finish(d, R, L.eq, S_hd, nullptr, 0, nullptr, nullptr, d->qc.as<float>(), false, s))) return r;
+    } else {
+      if ((r = dec_gemm(d, d->att.as<float>(), R, Hd, 0, d->tm_hd, L.so, d->t1.as<float>(), s, x))) return r;
+      if ((r = ln_f32(d->t1.as<float>(), d->s1.as<float>(), L.so_ln_w, L.so_ln_b, 1e-12f, R, Hd, s))) return r;
+      if ((r = dec_gemm(d, d->s1.as<float>(), R, Hd, 0, d->tm_hd, L.eq, d->qc.as<float>(), s))) return r;
+    }
     hb::SmallAttnF32Params cp;  // cross attention; the all-zeros video mask puts -10000 on every key (modeling.py:591)
     cp.q = d->qc.as<float>(); cp.k = L.ekv_buf.as<float>(); cp.v = L.ekv_buf.as<float>() + Hd; cp.out = d->att.as<float>();
     cp.B = R; cp.H = c.heads; cp.Tq = 1; cp.Tk = d->enc_len;
@@ -1436,17 +1496,36 @@ static int decoder_step_launches(HbDecoder* d, cudaStream_t s) {
     cp.bsq = Hd; cp.bsk = cp.bsv = static_cast<long long>(d->enc_len) * 2 * Hd; cp.bso = Hd;
     cp.scale = 0.125f; cp.mask_mode = 2; cp.mask_const = -10000.0f; cp.kv_div = d->beam;
     HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::small_attn_f32_launch(cp, s));
-    if ((r = dec_gemm(d, d->att.as<float>(), R, Hd, 0, d->tm_hd, L.eo, d->t1.as<float>(), s, d->s1.as<float>()))) return r;
-    if ((r = ln_f32(d->t1.as<float>(), d->c1.as<float>(), L.eo_ln_w, L.eo_ln_b, 1e-12f, R, Hd, s))) return r;
-    if ((r = dec_gemm(d, d->c1.as<float>(), R, Hd, 0, d->tm_hd, L.inter, d->mid.as<float>(), s))) return r;
-    if ((r = dec_gemm(d, d->mid.as<float>(), R, Ff, 1, d->tm_ffn, L.out, d->t1.as<float>(), s, d->c1.as<float>()))) return r;
-    if ((r = ln_f32(d->t1.as<float>(), x, L.o_ln_w, L.o_ln_b, 1e-12f, R, Hd, s))) return r;
+    // c1 = LN(dense(att) + s1); feed-forward: x = LN(dense(gelu(dense(c1))) + c1)
+    if (sk) {
+      HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(d->att.as<float>(), d->op.as<__nv_bfloat16>(), R, Hd, 0, s));
+      if ((r = dec_gemm_split(d, R, Hd, d->tm_hd, L.eo, S_hd, s))) return r;
+      if ((r = dec_finish(d, R, L.eo, S_hd, d->s1.as<float>(), 0, &L.eo_ln_w, &L.eo_ln_b, d->c1.as<float>(), true, s))) return r;
+      if ((r = dec_gemm_raw(d, R, Hd, d->tm_hd, L.inter, d->mid.as<float>(), s))) return r;
+      HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(d->mid.as<float>(), d->op.as<__nv_bfloat16>(), R, Ff, 1, s));
+      if ((r = dec_gemm_split(d, R, Ff, d->tm_ffn, L.out, S_ff, s))) return r;
+      if ((r = dec_finish(d, R, L.out, S_ff, d->c1.as<float>(), 0, &L.o_ln_w, &L.o_ln_b, x, true, s))) return r;
+      op_ready = true;
+    } else {
+      if ((r = dec_gemm(d, d->att.as<float>(), R, Hd, 0, d->tm_hd, L.eo, d->t1.as<float>(), s, d->s1.as<float>()))) return r;
+      if ((r = ln_f32(d->t1.as<float>(), d->c1.as<float>(), L.eo_ln_w, L.eo_ln_b, 1e-12f, R, Hd, s))) return r;
+      if ((r = dec_gemm(d, d->c1.as<float>(), R, Hd, 0, d->tm_hd, L.inter, d->mid.as<float>(), s))) return r;
+      if ((r = dec_gemm(d, d->mid.as<float>(), R, Ff, 1, d->tm_ffn, L.out, d->t1.as<float>(), s, d->c1.as<float>()))) return r;
+      if ((r = ln_f32(d->t1.as<float>(), x, L.o_ln_w, L.o_ln_b, 1e-12f, R, Hd, s))) return r;
+    }
   }
   // classifier on the last position only: transform (dense -> GELU -> LN) then the tied vocabulary projection
-  if ((r = dec_gemm(d, x, R, Hd, 0, d->tm_hd, d->cls_dense, d->th.as<float>(), s))) return r;
-  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::gelu_f32_launch(d->th.as<float>(), static_cast<long long>(R) * Hd, s));
-  if ((r = ln_f32(d->th.as<float>(), d->t1.as<float>(), d->cls_ln_w, d->cls_ln_b, 1e-12f, R, Hd, s))) return r;
-  if ((r = dec_gemm(d, d->t1.as<float>(), R, Hd, 0, d->tm_hd, d->cls_vocab, d->logits.as<float>(), s))) return r;
+  if (sk) {
+    if (!op_ready) HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(x, d->op.as<__nv_bfloat16>(), R, Hd, 0, s));
+    if ((r = dec_gemm_split(d, R, Hd, d->tm_hd, d->cls_dense, S_hd, s))) return r;
+    if ((r = dec_finish(d, R, d->cls_dense, S_hd, nullptr, 1, &d->cls_ln_w, &d->cls_ln_b, nullptr, true, s))) return r;
+    if ((r = dec_gemm_raw(d, R, Hd, d->tm_hd, d->cls_vocab, d->logits.as<float>(), s))) return r;
+  } else {
+    if ((r = dec_gemm(d, x, R, Hd, 0, d->tm_hd, d->cls_dense, d->th.as<float>(), s))) return r;
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::gelu_f32_launch(d->th.as<float>(), static_cast<long long>(R) * Hd, s));
+    if ((r = ln_f32(d->th.as<float>(), d->t1.as<float>(), d->cls_ln_w, d->cls_ln_b, 1e-12f, R, Hd, s))) return r;
+    if ((r = dec_gemm(d, d->t1.as<float>(), R, Hd, 0, d->tm_hd, d->cls_vocab, d->logits.as<float>(), s))) return r;
+  }
   int* pk = d->prev_k.as<int>() + static_cast<size_t>(pos) * R;
   HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::beam_advance_launch(d->logits.as<float>(), d->Vpad, c.vocab, d->scores.as<float>(), d->done.as<int>(),
                                                          d->nsteps.as<int>(), d->prev_k.as<int>(), d->ys.as<int>(), d->tok.as<long long>(),

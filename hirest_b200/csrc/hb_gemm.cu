@@ -68,9 +68,12 @@ struct TileIter {
 // worker count that is even, the odd workers got all the tails, ran ~17 % faster and pulled the A k-blocks through DRAM twice).
 struct NTiling {
   int n_tiles, base, rem, unit;
-  __host__ __device__ NTiling(int N, int cg, int balanced) {
+  // want > 0 (GemmParams::n_tiles): that many tiles instead of the minimum, e.g. a multiple of the worker count so that a
+  // single-M-block GEMM over a huge N (the tied vocabulary projection, 120 tiles on 74 workers) has no half-empty last round
+  __host__ __device__ NTiling(int N, int cg, int balanced, int want = 0) {
     n_tiles = (N + BN - 1) / BN;
     unit = 16 * cg;
+    if (want > n_tiles && balanced && N % unit == 0 && want <= N / unit) n_tiles = want;
     if (balanced && N % unit == 0) {
       base = (N / n_tiles) / unit * unit;
       rem = (N - base * n_tiles) / unit;
@@ -201,9 +204,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int tile_m = BM * CG;
   const int m_tiles = (p.M + tile_m - 1) / tile_m;
-  const NTiling nt(p.N, CG, p.balanced_n);
+  const NTiling nt(p.N, CG, p.balanced_n, p.n_tiles);
   const int n_tiles = nt.n_tiles;
   const int k_blocks = (p.K + BK - 1) / BK;
+  // split-K (EPI_F32 only, GemmParams::k_splits): the split index rides on the N-tile index of the schedule — work item
+  // (m, n') covers N tile n' % n_tiles and k-blocks [ks * kbs, ks * kbs + kbs) with ks = n' / n_tiles, and stores its raw
+  // partial sums to out + ks * split_stride.  The host guarantees that every slice is non-empty.
+  const int k_splits = p.k_splits > 1 ? p.k_splits : 1;
+  const int kbs = (k_blocks + k_splits - 1) / k_splits;
+  const int n_items = n_tiles * k_splits;
   const int worker = blockIdx.x / CG;
   const int num_workers = gridDim.x / CG;
 
@@ -242,13 +251,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint64_t hint_a = p.a_hint == 1 ? kEvictFirst : (p.a_hint == 2 ? kEvictLast : kEvictNormal);
     const uint64_t hint_w = p.w_hint == 1 ? kEvictFirst : (p.w_hint == 2 ? kEvictLast : kEvictNormal);
     (void)hint_a; (void)hint_w;
-    auto load_tile = [&](int m_blk, int n_blk) {
+    auto load_tile = [&](int m_blk, int n_item) {
+      const int ks = n_item / n_tiles, n_blk = n_item - ks * n_tiles;
+      const int kb0 = ks * kbs, kb1 = min(k_blocks, kb0 + kbs);
       const int n0 = nt.n0(n_blk);
       const int n_eff = nt.width(n_blk, p.N);
       const int row_a = m_blk * tile_m + static_cast<int>(cta_rank) * BM;
       const int row_w = n0 + static_cast<int>(cta_rank) * (n_eff / CG);
       // (Tried and dropped: TMA L2-prefetch of the A boxes 8 k-blocks ahead — no measurable change; the ring is not latency-starved.)
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         if (elect_one()) {
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
@@ -271,7 +282,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     };
     if (dyn && leader) {
       // ---- scheduler: this warp hands tile ids to every consumer warp of the pair, one tile ahead of its own loads ----
-      const int total = m_tiles * n_tiles;
+      const int total = m_tiles * n_items;
       auto publish = [&](int it, int t) {
         const int slot = it % SCHED_RING;
         if (it >= SCHED_RING) mbar_wait(&sched_empty[slot], static_cast<uint32_t>(it / SCHED_RING - 1) & 1u);
@@ -290,8 +301,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) v = num_workers + atomicAdd(p.sched, 1);
         const int t_next = min(__shfl_sync(0xffffffffu, v, 0), total);   // `total` is the end marker
         publish(it + 1, t_next);
-        const int m_blk = t / n_tiles;
-        load_tile(m_blk, t - m_blk * n_tiles);
+        const int m_blk = t / n_items;
+        load_tile(m_blk, t - m_blk * n_items);
         t = t_next;
         ++it;
       }
@@ -300,7 +311,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       __syncwarp();
     } else {
-      TileFeed feed(dyn, worker, num_workers, m_tiles, n_tiles, sched_full, sched_empty, sched_tile, /*arm=*/true, /*remote=*/true);
+      TileFeed feed(dyn, worker, num_workers, m_tiles, n_items, sched_full, sched_empty, sched_tile, /*arm=*/true, /*remote=*/true);
       int m_blk, n_blk;
       while (feed.next(m_blk, n_blk)) load_tile(m_blk, n_blk);
     }
@@ -311,16 +322,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    TileFeed it(dyn, worker, num_workers, m_tiles, n_tiles, sched_full, sched_empty, sched_tile, /*arm=*/true, /*remote=*/false);
+    TileFeed it(dyn, worker, num_workers, m_tiles, n_items, sched_full, sched_empty, sched_tile, /*arm=*/true, /*remote=*/false);
     int m_blk, n_blk;
     constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B (umma_desc_sw128)
     while (it.next(m_blk, n_blk)) {
+      const int ks = n_blk / n_tiles;
+      n_blk -= ks * n_tiles;
+      const int n_kb = min(k_blocks, ks * kbs + kbs) - ks * kbs;
       const int n_eff = nt.width(n_blk, p.N);
       const uint32_t idesc = umma_idesc_bf16(BM * CG, static_cast<uint32_t>(n_eff));
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = 0; kb < n_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         // descriptor low words: (address >> 4) | LBO(1) << 16; advancing K by 16 bf16 = 32 bytes adds 2
@@ -334,7 +348,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             umma_bf16<CG>(d_tmem, adesc, wdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit<CG>(&empty_bar[stage]);  // smem slot free once these MMAs retire
-          if (kb == k_blocks - 1) umma_commit<CG>(&tmem_full_bar[acc]);
+          if (kb == n_kb - 1) umma_commit<CG>(&tmem_full_bar[acc]);
         }
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -349,9 +363,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = (warp - 4) >> 2;     // column half of the tile
     int acc = 0;
     uint32_t acc_phase = 0;
-    TileFeed it(dyn, worker, num_workers, m_tiles, n_tiles, sched_full, sched_empty, sched_tile, /*arm=*/false, /*remote=*/!leader);
+    TileFeed it(dyn, worker, num_workers, m_tiles, n_items, sched_full, sched_empty, sched_tile, /*arm=*/false, /*remote=*/!leader);
     int m_blk, n_blk;
     while (it.next(m_blk, n_blk)) {
+      const int ks = n_blk / n_tiles;
+      n_blk -= ks * n_tiles;
       const int n0 = nt.n0(n_blk);
       const int n_eff = nt.width(n_blk, p.N);
       const int row_in = m_blk * tile_m + static_cast<int>(cta_rank) * BM + q * 32 + lane;
@@ -380,6 +396,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int rr_base = lane >> 3, cc = lane & 7;
         const uint32_t stage = smem_u32(smem + C::STAGES * C::STAGE_BYTES + 256) + static_cast<uint32_t>(warp - 4) * C::EPI_STAGE_BYTES;
         const int row_base = m_blk * tile_m + static_cast<int>(cta_rank) * BM + q * 32;
+        float* out_f32 = reinterpret_cast<float*>(p.out) + static_cast<long long>(ks) * p.split_stride;
         uint32_t okmask = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -449,7 +466,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             v.x += b4.x + res[i].x; v.y += b4.y + res[i].y; v.z += b4.z + res[i].z; v.w += b4.w + res[i].w;
             if (((okmask >> i) & 1u) && cc * 4 < n_valid) {
               int radd;
-              __stcs(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row_off(i, radd) + col0 + cc * 4), v);
+              __stcs(reinterpret_cast<float4*>(out_f32 + row_off(i, radd) + col0 + cc * 4), v);
               if constexpr (EPI == EPI_F32_STATS) {
                 psum[i] += (v.x + v.y) + (v.z + v.w);
                 psq[i] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
@@ -627,9 +644,14 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmW, const GemmParams
   }
   const int tile_m = BM * CG;
   const int m_tiles = (p.M + tile_m - 1) / tile_m;
-  const int n_tiles = (p.N + BN - 1) / BN;
+  const int n_tiles = NTiling(p.N, CG, p.balanced_n, p.n_tiles).n_tiles;
   if ((EPI == EPI_F32_STATS) && p.ln_slots < 2 * n_tiles) return -8;
-  const int total = m_tiles * n_tiles;
+  if (p.k_splits > 1) {
+    const int k_blocks = (p.K + BK - 1) / BK, kbs = (k_blocks + p.k_splits - 1) / p.k_splits;
+    // raw partial sums only (the caller reduces the slices), every slice non-empty
+    if (EPI != EPI_F32 || p.bias || p.resid || p.remap_in > 0 || p.split_stride <= 0 || (p.k_splits - 1) * kbs >= k_blocks) return -9;
+  }
+  const int total = m_tiles * n_tiles * (p.k_splits > 1 ? p.k_splits : 1);
   int workers = num_sms / CG;
   if (workers > total) workers = total;
   if (workers < 1) workers = 1;

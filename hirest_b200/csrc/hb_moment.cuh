@@ -10,6 +10,11 @@ namespace hb {
 // fp32 rows [R, K] -> bf16 [R, 3K] = [lo | hi | hi] (activation side of the ~fp32-accurate split GEMM; the weight side is
 // [hi | lo | hi], so A'.W'^T = lo.hi + hi.lo + hi.hi, smallest terms first).  gelu != 0 applies erf-GELU first.
 int split3_act_launch(const float* x, __nv_bfloat16* out, long long rows, int K, int gelu, cudaStream_t s);
+// Finish of a split-K GEMM: y = [LayerNorm]([gelu](sum_s part[s*split_stride + .] + bias) + resid) for rows x N (N <= 1536,
+// N % 4 == 0); y (fp32) and / or op (the [lo | hi | hi] operand of the next split GEMM, [rows, 3N]) may be null.
+int splitk_finish_launch(const float* part, long long split_stride, int splits, const float* bias, const float* resid,
+                         const float* ln_w, const float* ln_b, float eps, int gelu, float* y, __nv_bfloat16* op, int rows, int N,
+                         cudaStream_t s);
 // weight repack for the split GEMM: fp32 [N, K] -> bf16 [N, 3K] = [hi | lo | hi]
 int split3_weight_launch(const float* w, __nv_bfloat16* out, int N, int K, cudaStream_t s);
 

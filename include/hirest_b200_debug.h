@@ -19,6 +19,9 @@ extern "C" {
  *                                                              instead of CUDA cores (hb_attn_small.cu); same results to ~1e-6
  * "decoder_graphs"             0 | 1                 1         caption decoder: replay each decode step as a CUDA graph from the second
  *                                                              beam search of a (n_inst, beam, enc_len) shape on; same results
+ * "decoder_split_k"            0 | k-blocks          6         caption decoder: the hidden-width linears of a decode step run as split-K GEMMs
+ *                                                              with this many 64-element k-blocks per slice (slice count depends on K only)
+ *                                                              + one finish kernel (bias, residual, LayerNorm, next split operand); 0 = off
  * "profile_layer"              -1 | layer            -1        cudaProfilerStart / Stop around this ViT layer of every encode_image chunk
  *                                                              (ncu --profile-from-start off captures exactly its 5 kernels)
  * "attention_prefetch"         0 | 1                 0         v2 only: L2-prefetch the operands of the CTA one wave ahead (measured slower)

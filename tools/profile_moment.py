@@ -18,7 +18,8 @@ res = {}
 for task, kw in (("moment_retrieval", {}), ("moment_segmentation", {}), ("step_captioning", {"num_beams": 3})):
     b = dict(batch)
     b["tasks"] = [task] * B
-    model.test_step(b, **kw)
+    for _ in range(3):   # the second search of a shape records the decoder's CUDA graphs: keep that out of the timing
+        model.test_step(b, **kw)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(3):
