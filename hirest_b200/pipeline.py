@@ -17,7 +17,7 @@ Output: the structure the reference writes to ``final_end_to_end_results.json``.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence
+from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 import torch
@@ -104,7 +104,8 @@ def collate(items: Sequence[dict], n_model_frames: int = -1) -> dict:
 
 @torch.no_grad()
 def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beams: int = 5, n_model_frames: int = -1,
-                   tokenize=None, rank: int = 0, world: int = 1, group=None, gather=None) -> Dict:
+                   tokenize=None, rank: int = 0, world: int = 1, group=None, gather=None,
+                   caption_batch_size: Optional[int] = None) -> Dict:
     """Chain the three tasks over ``videos`` (dicts with ``prompt``, ``fname``, ``video_duration``, ``vis_feats [T,1024]``,
     ``asr_feats [T,384]``, ``clip_text_ids [77]``; order = dataset order).  Videos without ``clip_text_ids`` get them from
     ``tokenize(prompt) -> LongTensor[1, 77]`` (e.g. ``hirest_b200.tokenizer.tokenize``), as ``collate_fn`` does with
@@ -116,7 +117,12 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
     Multi-GPU: with ``world > 1`` every task's items are sharded over the ranks with DistributedSampler
     semantics (``shard_indices``), each rank runs its share, and the per-item results are gathered as Python objects
     (``all_gather_objects`` = dist_utils.all_gather; ``gather`` overrides it, e.g. to simulate ranks in one process), so every rank
-    returns the full dictionaries.  There is no tensor exchange on this path."""
+    returns the full dictionaries.  There is no tensor exchange on this path.
+
+    ``caption_batch_size`` (default: ``batch_size``) batches the step-captioning items separately: a step item is at most 20
+    trimmed frames, and the 48 decode steps of a beam search are latency-bound, so several hundred steps per search cost little
+    more than 64.  A caption does not depend on what else is in its batch (trimmed items carry no padding; every decoder kernel
+    computes a row from that row's inputs only), so this is a throughput knob, not a semantic one."""
     nmf = n_model_frames
     if gather is None:
         gather = (lambda obj: all_gather_objects(obj, group)) if world > 1 else (lambda obj: [obj])
@@ -199,7 +205,7 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
                           slice_to_moment=True)
     sc: Dict[str, dict] = {}
     preds = _run_sharded(items, lambda chunk: model.test_step(collate(chunk, -1), num_beams=num_beams)["prediction"],   # ragged items: pad path
-                         batch_size, rank, world, gather)
+                         caption_batch_size or batch_size, rank, world, gather)
     for it, sent in zip(items, preds):
         e = sc.setdefault(it["fname"], {"captions": []})
         e["captions"].append({"sentence": sent})

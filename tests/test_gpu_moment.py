@@ -135,14 +135,16 @@ def test_mr_decode_masks_padded_frames(hb):
 def test_trim_feats(model):
     m, _ = model
     g = torch.Generator().manual_seed(2)
-    x = torch.randn(4, 50, 768, generator=g)
-    mask = torch.zeros(4, 50, dtype=torch.long)
+    x = torch.randn(5, 50, 768, generator=g)
+    mask = torch.zeros(5, 50, dtype=torch.long)
     mask[0, 3:10] = 1      # 7 frames  -> repeat-padded to 20
     mask[1, 0:45] = 1      # 45 frames -> first 20
     mask[2, 10:30] = 1     # exactly 20
     mask[3, 7] = 1         # a single frame
+    #   [4]: empty moment -> zeros (modeling.py:537-549: `for j in range(N)` never runs with N = 0, x stays zeros)
     got = m.trim_feats(x, mask).cpu()
     assert torch.equal(got, mo.trim_feats(x, mask, 20))
+    assert not got[4].any()
 
 
 def test_long_clip_matches_oracle(hb):
@@ -216,6 +218,43 @@ def test_step_captioning_early_finish(hb, golden, tmp_path):
     assert [len(x) for x in g["ids"]] == [48, 48, 2, 17]
     assert out["token_ids"] == g["ids"]
     assert out["prediction"] == g["text"]
+
+
+def test_decoder_graph_replay_and_kernel_variants_agree(hb, golden, tmp_path):
+    """The same beam search run eagerly (first search of a shape), while its steps are captured into CUDA graphs (second) and as
+    graph replays (third) gives the reference's token ids every time and the same kernel count; so do the variants without graphs
+    and without the split-K GEMM + finish kernels (include/hirest_b200_debug.h)."""
+    clip = FixedText()
+    sd = synthetic.make_moment_state_dict(seed=3)
+    bias = sd["clip4cap_model.decoder.classifier.cls.predictions.bias"].clone()
+    bias[102] += 2.0
+    sd["clip4cap_model.decoder.classifier.cls.predictions.bias"] = bias
+    b = synthetic.make_moment_batch(4, 40, seed=7)
+    clip.feat = b["text_feat"]
+    b["tasks"] = ["step_captioning"] * 4
+    g = golden["caption_eos"]
+
+    def fresh():
+        m = moment.MomentModel(-1, 384, moment.default_args(bert_vocab_path=_write_vocab(tmp_path)), clip_model=clip, max_rows=1024, max_batch=8)
+        m.load_state_dict(sd, strict=True)
+        return m.to(DEV)
+
+    try:
+        m = fresh()
+        counts = []
+        for _ in range(3):   # eager, capture + replay, replay
+            n0 = hb.hb_launch_count()
+            assert m.test_step(b, num_beams=3)["token_ids"] == g["ids"]
+            counts.append(hb.hb_launch_count() - n0)
+        assert counts[0] == counts[1] == counts[2], counts
+        for key in ("decoder_graphs", "decoder_split_k"):
+            _lib.debug_set(key, 0)
+            m = fresh()
+            for _ in range(2):
+                assert m.test_step(b, num_beams=3)["token_ids"] == g["ids"], key
+    finally:
+        _lib.debug_set("decoder_graphs", 1)
+        _lib.debug_set("decoder_split_k", 6)
 
 
 def test_config4_size_determinism_and_oracle_subset(hb):

@@ -118,6 +118,10 @@ def test_end_to_end_chain_matches_reference_flow(hb, tmp_path):
             assert got["final"][p][fn]["steps"] == a["steps"], (p, fn)   # step bounds (ints) and captions (strings)
     n_steps = sum(len(a["steps"]) for p in got["final"] for a in got["final"][p].values())
     assert n_steps >= 8 and all(s["heading"] for p in got["final"] for a in got["final"][p].values() for s in a["steps"])
+    # captions do not depend on how the step items are batched: one search over all of them gives the same dictionaries
+    m2 = moment.MomentModel(-1, 384, moment.default_args(bert_vocab_path=vocab_path), clip_model=TableText(table), max_rows=4 * 96, max_batch=64)
+    m2.load_state_dict(sd, strict=True)
+    assert pipeline.run_end_to_end(m2.to(dev), videos, batch_size=4, num_beams=3, caption_batch_size=64) == got
 
 
 def test_prompts_are_tokenized_when_ids_are_missing():
