@@ -75,34 +75,6 @@ def _run_sharded(items: List[dict], run_batch, batch_size: int, rank: int, world
     return [merged[i] for i in range(len(items))]
 
 
-def collate(items: Sequence[dict], n_model_frames: int = -1) -> dict:
-    """``collate_fn`` (hirest_dataset.py:409-531) for inference items: zero-pad every per-frame tensor to the longest video."""
-    if n_model_frames > 0:
-        vis = torch.stack([d["vis_feats"] for d in items]).float()
-        vmask = torch.stack([d["video_mask"] for d in items])
-        mmask = torch.stack([d["moment_mask"] for d in items])
-        asr = torch.stack([d["asr_feats"] for d in items]).float()
-    else:
-        max_len = max(d["vis_feats"].shape[0] for d in items)
-
-        def pad(x, d):
-            n_pad = max_len - d["vis_feats"].shape[0]
-            return torch.cat([x, torch.zeros((n_pad,) + tuple(x.shape[1:]), dtype=x.dtype)], dim=0)
-
-        vis = torch.stack([pad(d["vis_feats"], d) for d in items])
-        vmask = torch.stack([pad(d["video_mask"], d) for d in items])
-        mmask = torch.stack([pad(d["moment_mask"], d) for d in items])
-        asr = torch.stack([pad(d["asr_feats"], d) for d in items]).float()
-    out = {"vis_feats": vis, "vis_mask": vmask.long(), "moment_mask": mmask.long(), "asr_feats": asr,
-           "video_duration": [d["video_duration"] for d in items], "video_fnames": [d["fname"] for d in items],
-           "tasks": [d["task"] for d in items], "prompts": [d["prompt"] for d in items],
-           "clip_text_ids": torch.stack([d["clip_text_ids"] for d in items])}
-    if "moment_bound_frames" in items[0]:
-        out["moment_bound_frames"] = torch.LongTensor([d["moment_bound_frames"] for d in items])
-    return out
-
-
-@torch.no_grad()
 def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beams: int = 5, n_model_frames: int = -1,
                    tokenize=None, rank: int = 0, world: int = 1, group=None, gather=None,
                    caption_batch_size: Optional[int] = None) -> Dict:
@@ -172,7 +144,34 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
     # ---- 1. moment retrieval (dataset :153-183, evaluate :704-744) -------------------------------------------------
     items = with_features(build_items(annotations(lambda v: [0, 0], lambda v: []), "moment_retrieval", nmf, end_to_end=True))
     mr: Dict[str, Dict[str, dict]] = {}
-    preds = _run_sharded(items, lambda chunk: model.test_step(collate(chunk, nmf))["prediction"], batch_size, rank, world, gather)
+    # Retrieval and segmentation see the same videos in the same batches (one item per video, same order, same shards): the padded
+    # feature tensors of a batch are collated and copied to the GPU once and reused by the segmentation pass (the reference
+    # re-reads every feature file and re-collates, run.py:419-435); only the masks / bounds of the items differ.
+    feat_cache: Dict[tuple, dict] = {}
+    cache_budget = [8 << 30]   # bytes of device memory the cache may hold; beyond it batches are collated again
+    try:
+        dev = next(model.parameters()).device
+    except (AttributeError, StopIteration, TypeError):
+        dev = None   # not a torch module (tests drive the glue with stand-ins): no device cache
+
+    def run_video_batch(chunk):
+        key = tuple(it["fname"] for it in chunk)
+        hit = feat_cache.get(key)
+        if hit is None:
+            b = collate(chunk, nmf)
+            nbytes = (b["vis_feats"].numel() + b["asr_feats"].numel()) * 4
+            if dev is not None and dev.type == "cuda" and nbytes <= cache_budget[0]:
+                cache_budget[0] -= nbytes
+                b["vis_feats"], b["asr_feats"] = b["vis_feats"].to(dev), b["asr_feats"].to(dev)
+                feat_cache[key] = {"vis_feats": b["vis_feats"], "asr_feats": b["asr_feats"]}
+        else:   # masks and bounds from the items, features from the cache (placeholders keep collate's padding logic in one place)
+            light = [dict(it, vis_feats=it["vis_feats"].new_empty((it["vis_feats"].shape[0], 0)),
+                          asr_feats=it["asr_feats"].new_empty((it["asr_feats"].shape[0], 0))) for it in chunk]
+            b = collate(light, nmf)
+            b.update(hit)
+        return model.test_step(b)["prediction"]
+
+    preds = _run_sharded(items, run_video_batch, batch_size, rank, world, gather)
     for it, (s, e) in zip(items, preds):
         d = it["video_duration"]
         mr.setdefault(it["prompt"], {})[it["fname"]] = {
@@ -188,7 +187,8 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
     items = with_features(build_items(annotations(lambda v: state[v["prompt"]][v["fname"]]["bounds"],
                                                   lambda v: state[v["prompt"]][v["fname"]]["steps"]), "moment_segmentation", nmf, end_to_end=True))
     ms: Dict[str, dict] = {}
-    preds = _run_sharded(items, lambda chunk: model.test_step(collate(chunk, nmf))["prediction"], batch_size, rank, world, gather)
+    preds = _run_sharded(items, run_video_batch, batch_size, rank, world, gather)
+    feat_cache.clear()
     for it, raw in zip(items, preds):
         d = it["video_duration"]
         bounds = [[frame_index_to_timestamp(raw[j], d, n_frames=nmf), frame_index_to_timestamp(raw[j + 1], d, n_frames=nmf)]
