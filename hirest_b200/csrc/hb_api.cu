@@ -1375,7 +1375,7 @@ int dec_gemm_raw(HbDecoder* d, long long rows, int K, const CUtensorMap& tmA, co
   p.M = static_cast<int>(rows); p.N = L.N; p.K = 3 * K;
   {  // wide outputs (the vocabulary projection): whole rounds of N tiles over the workers; depends on N only
     const int workers = g_num_sms / L.cg, min_tiles = (L.N + 255) / 256;
-    if (min_tiles > workers) p.n_tiles = (min_tiles + workers - 1) / workers * workers;
+    if (min_tiles > workers) { p.n_tiles = (min_tiles + workers - 1) / workers * workers; p.m_fastest = 1; }
   }
   p.bias = L.has_bias ? L.b.as<float>() : nullptr; p.out = out; p.ldo = L.N; p.resid = resid;
   HB_LAUNCH_P(CAT_GEMM_F32, 2.0 * rows * L.N * 3.0 * K, s, hb::gemm_launch(tmA, L.tm, p, hb::EPI_F32, L.cg, g_num_sms, s));

@@ -252,6 +252,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint64_t hint_w = p.w_hint == 1 ? kEvictFirst : (p.w_hint == 2 ? kEvictLast : kEvictNormal);
     (void)hint_a; (void)hint_w;
     auto load_tile = [&](int m_blk, int n_item) {
+      if (p.m_fastest) {   // same flat index, M-block fastest (see GemmParams::m_fastest)
+        const int t = m_blk * n_items + n_item;
+        n_item = t / m_tiles; m_blk = t - n_item * m_tiles;
+      }
       const int ks = n_item / n_tiles, n_blk = n_item - ks * n_tiles;
       const int kb0 = ks * kbs, kb1 = min(k_blocks, kb0 + kbs);
       const int n0 = nt.n0(n_blk);
@@ -326,6 +330,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int m_blk, n_blk;
     constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B, version 1, SWIZZLE_128B (umma_desc_sw128)
     while (it.next(m_blk, n_blk)) {
+      if (p.m_fastest) {
+        const int t = m_blk * n_items + n_blk;
+        n_blk = t / m_tiles; m_blk = t - n_blk * m_tiles;
+      }
       const int ks = n_blk / n_tiles;
       n_blk -= ks * n_tiles;
       const int n_kb = min(k_blocks, ks * kbs + kbs) - ks * kbs;
@@ -366,6 +374,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     TileFeed it(dyn, worker, num_workers, m_tiles, n_items, sched_full, sched_empty, sched_tile, /*arm=*/false, /*remote=*/!leader);
     int m_blk, n_blk;
     while (it.next(m_blk, n_blk)) {
+      if (p.m_fastest) {
+        const int t = m_blk * n_items + n_blk;
+        n_blk = t / m_tiles; m_blk = t - n_blk * m_tiles;
+      }
       const int ks = n_blk / n_tiles;
       n_blk -= ks * n_tiles;
       const int n0 = nt.n0(n_blk);

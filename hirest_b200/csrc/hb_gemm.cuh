@@ -50,6 +50,8 @@ struct GemmParams {
   int* sched = nullptr;           // optional dynamic tile scheduler: 2 zero-initialised device ints owned by the caller (one
                                   // pair per stream; the kernel re-zeroes them).  nullptr = static round-robin schedule.
   int n_tiles = 0;                // > minimum: use this many (balanced) N tiles, e.g. a multiple of the worker count; 0 = fewest
+  int m_fastest = 0;              // tile order: consecutive work items share the N tile (W operand) instead of the M block (A operand):
+                                  // for a few M blocks over a huge N (vocabulary projection at M = 768: W was read once per M block)
   int k_splits = 1;               // EPI_F32 only, bias / resid null: slice ks of K (k-blocks [ks*kbs, ks*kbs+kbs), kbs = ceil(k_blocks /
   long long split_stride = 0;     // k_splits)) writes its raw partial sums to out + ks * split_stride (elements); caller reduces
   int balanced_n = 1;             // N tiling: equal-cost tiles (see NTiling in hb_gemm.cu) instead of 256-wide tiles + narrow tail

@@ -557,15 +557,16 @@ __global__ void __launch_bounds__(BR_THREADS) beam_rows_generic_kernel(const flo
 
 // Same result rules as beam_rows_generic_kernel, with the row held in registers: ONE pass over the logits (float4 loads, up to
 // BR_NV per thread in flight) instead of three scalar passes — the generic kernel was 47 us per decode step at 192 rows x 30522.
-constexpr int BR_NV = 16;   // float4 per thread -> V <= 4 * BR_NV * BR_THREADS = 32768
+constexpr int BRR_THREADS = 1024;   // 32 warps: ~60 registers per thread with 8 float4 of logits each (512 x 16 float4 needed 97 registers:
+constexpr int BR_NV = 8;            // one CTA per SM either way, but twice the threads share a row); V <= 4 * BR_NV * BRR_THREADS = 32768
 template <int BEAM>         // compile-time beam width: the running top-BEAM list stays in registers
-__global__ void __launch_bounds__(BR_THREADS) beam_rows_kernel(const float* __restrict__ logits, int ldl, int V, const float* __restrict__ scores,
+__global__ void __launch_bounds__(BRR_THREADS) beam_rows_kernel(const float* __restrict__ logits, int ldl, int V, const float* __restrict__ scores,
                                                                const int* __restrict__ done, float* __restrict__ cand_v, int* __restrict__ cand_i,
                                                                int step) {
   constexpr int beam = BEAM;
-  __shared__ float red_m[BR_THREADS / 32], red_s[BR_THREADS / 32];
-  __shared__ float wv[(BR_THREADS / 32) * BEAM_MAX];
-  __shared__ int wi[(BR_THREADS / 32) * BEAM_MAX];
+  __shared__ float red_m[BRR_THREADS / 32], red_s[BRR_THREADS / 32];
+  __shared__ float wv[(BRR_THREADS / 32) * BEAM_MAX];
+  __shared__ int wi[(BRR_THREADS / 32) * BEAM_MAX];
   const int row = blockIdx.x, inst = row / beam, k = row - inst * beam;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (done[inst] || (step == 0 && k > 0)) return;   // Beam.advance uses word_prob[0] only before any back-pointer exists
@@ -573,7 +574,7 @@ __global__ void __launch_bounds__(BR_THREADS) beam_rows_kernel(const float* __re
   float4 x[BR_NV];
 #pragma unroll
   for (int i = 0; i < BR_NV; ++i) {
-    const int j = (i * BR_THREADS + tid) * 4;
+    const int j = (i * BRR_THREADS + tid) * 4;
     x[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     if (j < V) {   // ldl >= round_up(V, 4): the load stays inside the row; columns >= V are padding
       const float4 t = *reinterpret_cast<const float4*>(lr + j);
@@ -592,7 +593,7 @@ __global__ void __launch_bounds__(BR_THREADS) beam_rows_kernel(const float* __re
   __syncthreads();
   float M = red_m[0];
 #pragma unroll
-  for (int w = 1; w < BR_THREADS / 32; ++w) M = fmaxf(M, red_m[w]);
+  for (int w = 1; w < BRR_THREADS / 32; ++w) M = fmaxf(M, red_m[w]);
   float ssum = 0.f;
 #pragma unroll
   for (int i = 0; i < BR_NV; ++i) ssum += (expf(x[i].x - M) + expf(x[i].y - M)) + (expf(x[i].z - M) + expf(x[i].w - M));   // exp(-inf) = 0
@@ -601,7 +602,7 @@ __global__ void __launch_bounds__(BR_THREADS) beam_rows_kernel(const float* __re
   __syncthreads();
   float tot = 0.f;
 #pragma unroll
-  for (int w = 0; w < BR_THREADS / 32; ++w) tot += red_s[w];
+  for (int w = 0; w < BRR_THREADS / 32; ++w) tot += red_s[w];
   const float lse = M + logf(tot);
   const float add = (step == 0) ? 0.f : scores[row];
   // top-`beam` of val = log_softmax + beam score (beam.py:76), flat index = k * V + word; a thread meets its words in index order
@@ -611,7 +612,7 @@ __global__ void __launch_bounds__(BR_THREADS) beam_rows_kernel(const float* __re
   for (int i = 0; i < BEAM; ++i) { tv[i] = -INFINITY; ti[i] = 0x7fffffff; }
 #pragma unroll
   for (int i = 0; i < BR_NV; ++i) {
-    const int j = (i * BR_THREADS + tid) * 4;
+    const int j = (i * BRR_THREADS + tid) * 4;
     const float xs[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -641,7 +642,7 @@ __global__ void __launch_bounds__(BR_THREADS) beam_rows_kernel(const float* __re
   if (warp == 0) {
 #pragma unroll
     for (int i = 0; i < BEAM_MAX; ++i) { bv[i] = -INFINITY; bi[i] = 0x7fffffff; }
-    if (lane < BR_THREADS / 32)
+    if (lane < BRR_THREADS / 32)
       for (int i = 0; i < beam; ++i) { bv[i] = wv[lane * BEAM_MAX + i]; bi[i] = wi[lane * BEAM_MAX + i]; }
     warp_topk(bv, bi, beam, ov, oi);
     if (lane == 0)
@@ -771,9 +772,9 @@ int gelu_f32_launch(float* x, long long n, cudaStream_t s) {
 int beam_advance_launch(const float* logits, int ldl, int V, float* scores, int* done, int* nsteps, int* prev_k_rec, int* ys_rec,
                         long long* tok, int step, int n_inst, int beam, int eos, float* cand_v, int* cand_i, cudaStream_t s) {
   if (beam < 1 || beam > BEAM_MAX || cand_v == nullptr || cand_i == nullptr) return -7;
-  if (V <= 4 * BR_NV * BR_THREADS && ldl % 4 == 0 && ldl >= (V + 3) / 4 * 4 && (reinterpret_cast<uintptr_t>(logits) & 15u) == 0)
+  if (V <= 4 * BR_NV * BRR_THREADS && ldl % 4 == 0 && ldl >= (V + 3) / 4 * 4 && (reinterpret_cast<uintptr_t>(logits) & 15u) == 0)
     switch (beam) {
-#define HB_BR(B) case B: beam_rows_kernel<B><<<n_inst * beam, BR_THREADS, 0, s>>>(logits, ldl, V, scores, done, cand_v, cand_i, step); break;
+#define HB_BR(B) case B: beam_rows_kernel<B><<<n_inst * beam, BRR_THREADS, 0, s>>>(logits, ldl, V, scores, done, cand_v, cand_i, step); break;
       HB_BR(1) HB_BR(2) HB_BR(3) HB_BR(4) HB_BR(5) HB_BR(6) HB_BR(7) HB_BR(8)
 #undef HB_BR
     }
