@@ -220,6 +220,29 @@ def test_step_captioning_early_finish(hb, golden, tmp_path):
     assert out["prediction"] == g["text"]
 
 
+@pytest.mark.parametrize("beam", [1, 5])
+def test_step_captioning_other_beam_widths_match_oracle(hb, tmp_path, beam):
+    """Beam widths other than the golden's 3 (run.py's default is 5; 1 = greedy): best-hypothesis token ids vs the CPU restatement
+    of the reference beam search (oracle/caption_oracle.py) on the early-finishing weights."""
+    from oracle import caption_oracle as co
+
+    clip = FixedText()
+    m = moment.MomentModel(-1, 384, moment.default_args(bert_vocab_path=_write_vocab(tmp_path)), clip_model=clip, max_rows=1024, max_batch=8)
+    sd = synthetic.make_moment_state_dict(seed=3)
+    bias = sd["clip4cap_model.decoder.classifier.cls.predictions.bias"].clone()
+    bias[102] += 2.0
+    sd["clip4cap_model.decoder.classifier.cls.predictions.bias"] = bias
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+    b = synthetic.make_moment_batch(2, 40, seed=11)
+    clip.feat = b["text_feat"]
+    b["tasks"] = ["step_captioning"] * 2
+    out = m.test_step(b, num_beams=beam)
+    with torch.no_grad():
+        ref_ids, _ = co.test_step_captioning(sd, b, b["text_feat"], beam=beam)
+    assert out["token_ids"] == ref_ids
+
+
 def test_decoder_graph_replay_and_kernel_variants_agree(hb, golden, tmp_path):
     """The same beam search run eagerly (first search of a shape), while its steps are captured into CUDA graphs (second) and as
     graph replays (third) gives the reference's token ids every time and the same kernel count; so do the variants without graphs
