@@ -45,9 +45,12 @@ int g_num_sms = 148;
 bool g_inited = false;
 int g_device = -1;
 
-int vit_attn_dispatch(const hb::AttnParams& ap, cudaStream_t s) {
-  if (g_attn_version == 1) return hb::vit_attn_launch(ap, s);
-  if (g_attn_version == 2) return hb::vit_attn2_launch(ap, s);
+int g_attn_dots_late = 0;   // attention v3: per-tile bit mask, see AttnParams::dots_late
+int vit_attn_dispatch(const hb::AttnParams& ap_in, cudaStream_t s) {
+  if (g_attn_version == 1) return hb::vit_attn_launch(ap_in, s);
+  if (g_attn_version == 2) return hb::vit_attn2_launch(ap_in, s);
+  hb::AttnParams ap = ap_in;
+  ap.dots_late = g_attn_dots_late;
   return hb::vit_attn3_launch(ap, g_num_sms, s);
 }
 
@@ -364,7 +367,7 @@ int hb_init(int device) {
   g_num_sms = prop.multiProcessorCount;
   if (hb::tmap_init() != 0) return fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   if (!g_inited) {   // A/B switches from the environment (hirest_b200_debug.h), once
-    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "decoder_graphs", "decoder_split_k", "profile_layer", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
+    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "decoder_graphs", "decoder_split_k", "attention_dots_late", "profile_layer", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
                                  "gemm_dynamic_schedule", "gemm_resid_prefetch_chunks"};
     for (const char* key : keys) {
       std::string env = std::string("HB_DEBUG_") + key;
@@ -419,6 +422,9 @@ int hb_debug_set(const char* key, int value) {
     g_dec_split_kbs = value;
   } else if (k == "profile_layer") {
     g_profile_layer = value;
+  } else if (k == "attention_dots_late") {
+    if (value < 0 || value > 3) return fail(HB_ERR_INVALID, "attention_dots_late is a 2-bit tile mask");
+    g_attn_dots_late = value;
   } else if (k == "attention_prefetch") {
     g_attn_prefetch = value ? 1 : 0;
   } else if (k == "ln_fold") {

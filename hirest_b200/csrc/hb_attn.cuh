@@ -16,6 +16,7 @@ struct AttnParams {
   int H = 0;
   long long* timing = nullptr;  // debug (HB_ATTN_TIMING builds): 16 clock64 stamps per CTA
   int prefetch_ahead = 0;       // v2: L2-prefetch the operands of block (blockIdx + prefetch_ahead); 0 = off
+  int dots_late = 0;            // v3: bit t set = tile t computes the next item's extra-token dot products AFTER its output phase
 };
 int vit_attn_launch(const AttnParams& p, cudaStream_t stream);   // v1: one CTA per (frame, head), P through smem
 int vit_attn2_launch(const AttnParams& p, cudaStream_t stream);  // v2: one CTA per 128-query tile, 2 CTAs/SM, P in TMEM

@@ -25,7 +25,7 @@
 // consumers half a period apart, so a load window is ~half an item period while one SM's share of HBM bandwidth needs ~2/3 of
 // it; MUFU (4096 cycles per item) and the tensor pipe (~4300) are the next floors.  L2-prefetching the next item's boxes
 // (-DHB_A3_L2_PREFETCH) slows the TMEM loads of the max pass 4x and costs 20 %; lock-step tiles (-DHB_A3_NO_TURNS) and dot
-// products at the end of the item (-DHB_A3_DOTS_LATE) are within 2 % of the default.
+// products at the end of the item (AttnParams::dots_late, debug key "attention_dots_late") are within 2 % of the default.
 // TMEM per tile (256 columns): S fp32 [0,256); P (bf16x2) keys 0..127 -> [0,64) (ascending, behind the reader), keys 128..255 ->
 // [192,256) (that thread walks its S columns in DESCENDING order, so it too only overwrites columns it has consumed);
 // O d 0..95 -> [64,160) (column 152 = row sum); extra-query partial output [160,176).
@@ -487,9 +487,8 @@ __global__ void __launch_bounds__(A3_THREADS, 1) vit_attn3_kernel(const __grid_c
       A3_SSTAMP(5);
 
       // ---- while the tensor core runs this tile's P.V: the NEXT item's dot products (its Q / K landed long ago)
-#ifndef HB_A3_DOTS_LATE
-      if (it + 1 < my_items) dots(it + 1);
-#endif
+      const bool dots_late = (p.dots_late >> tile) & 1;   // warp-uniform
+      if (!dots_late && it + 1 < my_items) dots(it + 1);
       A3_SSTAMP(6);
 
       // ---- output: (O + the extra key's rank-1 term) / row sum -> dense bf16 staging tile -> one TMA store per tile
@@ -571,9 +570,7 @@ __global__ void __launch_bounds__(A3_THREADS, 1) vit_attn3_kernel(const __grid_c
           }
         }
       }
-#ifdef HB_A3_DOTS_LATE
-      if (it + 1 < my_items) dots(it + 1);
-#endif
+      if (dots_late && it + 1 < my_items) dots(it + 1);
     }
     if (store_pending) tma_store_wait_all();
   }

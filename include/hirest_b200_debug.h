@@ -24,6 +24,9 @@ extern "C" {
  *                                                              + one finish kernel (bias, residual, LayerNorm, next split operand); 0 = off
  * "profile_layer"              -1 | layer            -1        cudaProfilerStart / Stop around this ViT layer of every encode_image chunk
  *                                                              (ncu --profile-from-start off captures exactly its 5 kernels)
+ * "attention_dots_late"        0..3 (tile bit mask)  0         v3: tile t computes the next item's extra-token dot products after its output
+ *                                                              phase instead of during its P.V MMAs (measured: 0.756 / 0.739 / 0.792 / 0.756 ms
+ *                                                              per layer for masks 0 / 1 / 2 / 3 — the pipeline re-balances, within noise)
  * "attention_prefetch"         0 | 1                 0         v2 only: L2-prefetch the operands of the CTA one wave ahead (measured slower)
  * "ln_fold"                    0 | 1                 1         ViT handles created afterwards fold the block LayerNorms into the QKV / fc1
  *                                                              GEMM epilogues (1) or run separate LayerNorm kernels (0)
