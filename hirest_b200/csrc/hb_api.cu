@@ -36,6 +36,7 @@ int g_cg = 2;
 int g_attn_version = 3;
 int g_small_attn_tc = 1;
 int g_dec_split_kbs = 6;    // caption decoder: k-blocks (64 bf16) per split-K slice of the hidden-width linears; 0 = no split-K
+int g_ln_split_fuse = 1;    // small models: LayerNorm + split-operand conversion in one kernel (ln_split)
 int g_decoder_graphs = 1;   // replay the caption decoder's steps as CUDA graphs (from the second search of a shape on)
 int g_profile_layer = -1;   // debug: cudaProfilerStart/Stop around this ViT layer (ncu --profile-from-start off)   // fp32 small-sequence attention on tensor cores (hb_attn_tc.cu) instead of CUDA cores
 int g_attn_prefetch = 0;   // attention v2: L2-prefetch the operands of the CTA one wave ahead (measured: 1.05 -> 1.14 ms, off)
@@ -293,9 +294,10 @@ struct SplitLinear {
 
 
 // fp32 activations [rows, K] -> split operand in `op` -> 3-term split-bf16 GEMM with L -> out fp32 [rows, N]
+// (act == nullptr: `op` already holds the split operand, written by ln_split below)
 int split_gemm_op(__nv_bfloat16* op, const float* act, long long rows, int K, int gelu, const CUtensorMap& tmA, const SplitLinear& L,
                   float* out, int epi, cudaStream_t s, const float* resid = nullptr, const float* rowadd = nullptr, int remap = 0) {
-  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(act, op, rows, K, gelu, s));
+  if (act != nullptr) HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(act, op, rows, K, gelu, s));
   hb::GemmParams p;
   p.M = static_cast<int>(rows); p.N = L.N; p.K = 3 * K;
   p.bias = L.has_bias ? L.b.as<float>() : nullptr; p.out = out; p.ldo = L.N; p.resid = resid;
@@ -310,6 +312,16 @@ int ln_f32(const float* x, float* y, const F32Vec& w, const F32Vec& b, float eps
   ln.x = x; ln.ldx = D; ln.y = y; ln.ldy = D; ln.w = w.ptr(); ln.b = b.ptr(); ln.eps = eps; ln.rows = static_cast<int>(rows); ln.D = D;
   ln.row_idx = row_idx;
   HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s, hb::layernorm_launch(ln, false, s));
+  return 0;
+}
+
+// LayerNorm whose output feeds a split GEMM: one kernel writes the normalised row as fp32 (y, may be null when only the GEMM
+// reads it) and as the [lo | hi | hi] operand in `op` (splitk_finish_kernel with a single slice), instead of a LayerNorm
+// kernel + a split kernel re-reading its output.  Falls back to the two kernels when the fusion is off or D > 1536.
+bool ln_split_ok(int D) { return g_ln_split_fuse && D % 4 == 0 && D <= 1536; }
+int ln_split(const float* x, float* y, __nv_bfloat16* op, const F32Vec& w, const F32Vec& b, float eps, long long rows, int D, cudaStream_t s) {
+  HB_LAUNCH_P(CAT_LAYERNORM, 0.0, s,
+              hb::splitk_finish_launch(x, 0, 1, nullptr, nullptr, w.ptr(), b.ptr(), eps, 0, y, op, static_cast<int>(rows), D, s));
   return 0;
 }
 
@@ -367,7 +379,7 @@ int hb_init(int device) {
   g_num_sms = prop.multiProcessorCount;
   if (hb::tmap_init() != 0) return fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   if (!g_inited) {   // A/B switches from the environment (hirest_b200_debug.h), once
-    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "decoder_graphs", "decoder_split_k", "attention_dots_late", "profile_layer", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
+    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "decoder_graphs", "decoder_split_k", "ln_split_fuse", "attention_dots_late", "profile_layer", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
                                  "gemm_dynamic_schedule", "gemm_resid_prefetch_chunks"};
     for (const char* key : keys) {
       std::string env = std::string("HB_DEBUG_") + key;
@@ -422,6 +434,8 @@ int hb_debug_set(const char* key, int value) {
     g_dec_split_kbs = value;
   } else if (k == "profile_layer") {
     g_profile_layer = value;
+  } else if (k == "ln_split_fuse") {
+    g_ln_split_fuse = value ? 1 : 0;
   } else if (k == "attention_dots_late") {
     if (value < 0 || value > 3) return fail(HB_ERR_INVALID, "attention_dots_late is a 2-bit tile mask");
     g_attn_dots_late = value;
@@ -762,8 +776,10 @@ static int text_encode_chunk(HbText* m, const int64_t* ids, int Q, float* out, c
     for (int i = 0; i < c.layers; ++i) {
       HbText::Layer& L = *m->layers[i];
       HbText::PLayer& P = *m->players[i];
-      if ((r = ln_f32(x, lnb, L.l1w, L.l1b, c.ln_eps, M, W, s))) return r;
-      if ((r = split_gemm_op(op, lnb, M, W, 0, m->tm_w, P.qkv, qf, hb::EPI_F32, s))) return r;
+      const bool fuse = ln_split_ok(W);
+      if (fuse) { if ((r = ln_split(x, nullptr, op, L.l1w, L.l1b, c.ln_eps, M, W, s))) return r; }
+      else if ((r = ln_f32(x, lnb, L.l1w, L.l1b, c.ln_eps, M, W, s))) return r;
+      if ((r = split_gemm_op(op, fuse ? nullptr : lnb, M, W, 0, m->tm_w, P.qkv, qf, hb::EPI_F32, s))) return r;
       hb::SmallAttnF32Params ap;
       ap.q = qf; ap.k = qf + W; ap.v = qf + 2 * W; ap.out = att;
       ap.B = Q; ap.H = c.heads; ap.Tq = C; ap.Tk = C;
@@ -772,8 +788,9 @@ static int text_encode_chunk(HbText* m, const int64_t* ids, int Q, float* out, c
       ap.scale = 0.125f; ap.mask_mode = 1;   // causal, eva_model.py:224-230
       if ((r = small_attn_f32_auto(ap, m->attn_ws, s))) return r;
       if ((r = split_gemm_op(op, att, M, W, 0, m->tm_w, P.out, x, hb::EPI_F32, s, x))) return r;
-      if ((r = ln_f32(x, lnb, L.l2w, L.l2b, c.ln_eps, M, W, s))) return r;
-      if ((r = split_gemm_op(op, lnb, M, W, 0, m->tm_w, P.fc, mid, hb::EPI_F32, s))) return r;
+      if (fuse) { if ((r = ln_split(x, nullptr, op, L.l2w, L.l2b, c.ln_eps, M, W, s))) return r; }
+      else if ((r = ln_f32(x, lnb, L.l2w, L.l2b, c.ln_eps, M, W, s))) return r;
+      if ((r = split_gemm_op(op, fuse ? nullptr : lnb, M, W, 0, m->tm_w, P.fc, mid, hb::EPI_F32, s))) return r;
       if ((r = split_gemm_op(op, mid, M, 4 * W, /*gelu=*/1, m->tm_4w, P.cproj, x, hb::EPI_F32, s, x))) return r;
     }
     if ((r = ln_f32(x, m->eotf.as<float>(), m->lfw, m->lfb, c.ln_eps, Q, W, s, m->eot_row.as<int>()))) return r;
@@ -1190,10 +1207,14 @@ int hb_moment_forward(HbMoment* m, const float* video, const float* text_feat, c
   if ((r = split_gemm(m, m->f.as<float>(), R, E, 0, m->tm_e, m->emb, m->e_lin.as<float>(), hb::EPI_F32_ROWADD, s, nullptr, m->pos.ptr(), T)))
     return r;
   float* x = m->x.as<float>();
-  if ((r = ln_f32(m->e_lin.as<float>(), x, m->emb_ln_w, m->emb_ln_b, 1e-12f, R, Hd, s))) return r;
-  for (auto& Lp : m->layers) {
-    HbMoment::Layer& L = *Lp;
-    if ((r = split_gemm(m, x, R, Hd, 0, m->tm_hd, L.qkv, m->qkv.as<float>(), hb::EPI_F32, s))) return r;
+  const bool fuse = ln_split_ok(Hd);   // every LayerNorm below feeds the next linear: it also writes that GEMM's split operand
+  __nv_bfloat16* opb = m->op.as<__nv_bfloat16>();
+  if (fuse) { if ((r = ln_split(m->e_lin.as<float>(), x, opb, m->emb_ln_w, m->emb_ln_b, 1e-12f, R, Hd, s))) return r; }
+  else if ((r = ln_f32(m->e_lin.as<float>(), x, m->emb_ln_w, m->emb_ln_b, 1e-12f, R, Hd, s))) return r;
+  for (size_t li = 0; li < m->layers.size(); ++li) {
+    HbMoment::Layer& L = *m->layers[li];
+    const bool last = (li + 1 == m->layers.size());
+    if ((r = split_gemm(m, fuse ? nullptr : x, R, Hd, 0, m->tm_hd, L.qkv, m->qkv.as<float>(), hb::EPI_F32, s))) return r;
     hb::SmallAttnF32Params ap;
     ap.q = m->qkv.as<float>(); ap.k = ap.q + Hd; ap.v = ap.q + 2 * Hd; ap.out = m->att.as<float>();
     ap.B = B; ap.H = c.heads; ap.Tq = T; ap.Tk = T;
@@ -1202,10 +1223,12 @@ int hb_moment_forward(HbMoment* m, const float* video, const float* text_feat, c
     ap.scale = 0.125f; ap.mask_mode = 2; ap.mask_const = -10000.0f;  // all-zeros mask quirk, modeling.py:208
     if ((r = small_attn_f32_auto(ap, m->attn_ws, s))) return r;
     if ((r = split_gemm(m, m->att.as<float>(), R, Hd, 0, m->tm_hd, L.ao, m->t1.as<float>(), hb::EPI_F32, s, x))) return r;
-    if ((r = ln_f32(m->t1.as<float>(), m->h.as<float>(), L.ao_ln_w, L.ao_ln_b, 1e-12f, R, Hd, s))) return r;
-    if ((r = split_gemm(m, m->h.as<float>(), R, Hd, 0, m->tm_hd, L.inter, m->mid.as<float>(), hb::EPI_F32, s))) return r;
+    if (fuse) { if ((r = ln_split(m->t1.as<float>(), m->h.as<float>(), opb, L.ao_ln_w, L.ao_ln_b, 1e-12f, R, Hd, s))) return r; }
+    else if ((r = ln_f32(m->t1.as<float>(), m->h.as<float>(), L.ao_ln_w, L.ao_ln_b, 1e-12f, R, Hd, s))) return r;
+    if ((r = split_gemm(m, fuse ? nullptr : m->h.as<float>(), R, Hd, 0, m->tm_hd, L.inter, m->mid.as<float>(), hb::EPI_F32, s))) return r;
     if ((r = split_gemm(m, m->mid.as<float>(), R, Ff, /*gelu=*/1, m->tm_ffn, L.out, m->t1.as<float>(), hb::EPI_F32, s, m->h.as<float>()))) return r;
-    if ((r = ln_f32(m->t1.as<float>(), x, L.o_ln_w, L.o_ln_b, 1e-12f, R, Hd, s))) return r;
+    if (fuse) { if ((r = ln_split(m->t1.as<float>(), x, last ? nullptr : opb, L.o_ln_w, L.o_ln_b, 1e-12f, R, Hd, s))) return r; }
+    else if ((r = ln_f32(m->t1.as<float>(), x, L.o_ln_w, L.o_ln_b, 1e-12f, R, Hd, s))) return r;
   }
   HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::moment_heads_launch(x, m->head_w.ptr(), m->head_b.ptr(), out_logits, R, Hd, s));
   if (out_feats) HB_CUDA(cudaMemcpyAsync(out_feats, x, static_cast<size_t>(R) * Hd * 4, cudaMemcpyDeviceToDevice, s));
