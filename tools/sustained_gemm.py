@@ -66,6 +66,7 @@ def main():
     ap.add_argument("--cg", type=int, default=2)
     ap.add_argument("--only", default="")
     ap.add_argument("--no-cublas", action="store_true")
+    ap.add_argument("--no-resid", action="store_true", help="fp32-output shapes without the residual read (isolates the epilogue's load side)")
     a = ap.parse_args()
     dev = "cuda:0"
     hb = _lib.init(0)
@@ -82,7 +83,7 @@ def main():
         b = torch.randn(N, device=dev)
         flops = 2.0 * Mx * N * K
         out_t = torch.empty(Mx, N, device=dev, dtype=torch.float32 if epi == 2 else torch.bfloat16)
-        resid = out_t if epi == 2 else None
+        resid = out_t if (epi == 2 and not a.no_resid) else None
         wt = w.t()
         out_c = torch.empty(Mx, N, device=dev, dtype=torch.bfloat16)
         s = _lib.stream_ptr()
