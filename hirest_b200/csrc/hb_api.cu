@@ -1400,6 +1400,7 @@ namespace {
 // GEMM of a decoder linear whose split operand already sits in d->op
 int dec_gemm_raw(HbDecoder* d, long long rows, int K, const CUtensorMap& tmA, const SplitLinear& L, float* out, cudaStream_t s,
                  const float* resid = nullptr) {
+  (void)d;
   hb::GemmParams p;
   p.M = static_cast<int>(rows); p.N = L.N; p.K = 3 * K;
   {  // wide outputs (the vocabulary projection): whole rounds of N tiles over the workers; depends on N only
