@@ -71,13 +71,15 @@ class PendingGather:
     """Handle of an all-gather in flight (see all_gather_embeddings(..., async_op=True)); ``wait()`` makes the current stream wait
     for it and returns the gathered [n_total, E] embeddings in global video order."""
 
-    def __init__(self, work, out, sizes, per):
-        self._work, self._out, self._sizes, self._per = work, out, sizes, per
+    def __init__(self, work, out, sizes, per, out_dtype=None):
+        self._work, self._out, self._sizes, self._per, self._out_dtype = work, out, sizes, per, out_dtype
 
     def wait(self) -> torch.Tensor:
         if self._work is not None:
             self._work.wait()
             self._work = None
+        if self._out_dtype is not None and self._out.dtype != self._out_dtype:
+            self._out = self._out.to(self._out_dtype)   # wire dtype -> the caller's dtype, once
         out, sizes, per = self._out, self._sizes, self._per
         total = sum(sizes)
         if all(n == per for n in sizes[:-1]) or total == 0:
@@ -92,7 +94,8 @@ class PendingGather:
         return torch.cat([out[r * per:r * per + n] for r, n in enumerate(sizes) if n > 0], dim=0)
 
 
-def all_gather_embeddings(local_hat: torch.Tensor, group=None, n_total: Optional[int] = None, async_op: bool = False):
+def all_gather_embeddings(local_hat: torch.Tensor, group=None, n_total: Optional[int] = None, async_op: bool = False,
+                          wire_dtype: Optional[torch.dtype] = None):
     """The one collective of the path: all-gather of the L2-normalised video embeddings over NCCL (gloo in the CPU tests).
 
     Shards may be UNEQUAL (4282 validation videos over 8 ranks = 7 x 536 + 530, or trailing empty shards): every rank pads its
@@ -100,10 +103,16 @@ def all_gather_embeddings(local_hat: torch.Tensor, group=None, n_total: Optional
     ``n_total`` = the global number of videos when the shards are the contiguous blocks of ``shard_range`` (no extra
     communication); without it the per-rank sizes are exchanged first (one tiny all-gather + a host sync).
     ``async_op=True`` returns a PendingGather: the collective runs on the communicator's stream while the caller keeps
-    enqueueing compute (bench.py overlaps the gather of step i with the encoder of step i+1)."""
+    enqueueing compute (bench.py overlaps the gather of step i with the encoder of step i+1).
+    ``wire_dtype=torch.bfloat16`` sends the blocks as bf16 (SURVEY.md §8(e)'s wording: half the bytes of a transfer that is
+    already < 0.01 % of a step) and returns them in ``local_hat``'s dtype; EVERY block, the local one included, then carries
+    bf16-rounded values, so all ranks still score identical embeddings — but not the fp32 ones a single GPU would, which is
+    why the default keeps fp32 on the wire and bench.py's sharded-equals-single-GPU check stays bit-exact."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if wire_dtype is not None:
+            local_hat = local_hat.to(wire_dtype).to(local_hat.dtype)   # same values a multi-rank run would score
         return PendingGather(None, local_hat, [local_hat.shape[0]], local_hat.shape[0]) if async_op else local_hat
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     n_local, E = local_hat.shape
@@ -117,13 +126,14 @@ def all_gather_embeddings(local_hat: torch.Tensor, group=None, n_total: Optional
         dist.all_gather_into_tensor(all_cnt, cnt, group=group)
         sizes = [int(x) for x in all_cnt.tolist()]
     per = max(sizes)
-    block = local_hat.contiguous()
+    wire = wire_dtype or local_hat.dtype
+    block = local_hat.contiguous().to(wire)
     if n_local != per:
-        block = torch.zeros((per, E), dtype=local_hat.dtype, device=local_hat.device)
+        block = torch.zeros((per, E), dtype=wire, device=local_hat.device)
         block[:n_local].copy_(local_hat)
-    out = torch.empty((world * per, E), dtype=local_hat.dtype, device=local_hat.device)
+    out = torch.empty((world * per, E), dtype=wire, device=local_hat.device)
     work = dist.all_gather_into_tensor(out, block, group=group, async_op=async_op)
-    pend = PendingGather(work if async_op else None, out, sizes, per)
+    pend = PendingGather(work if async_op else None, out, sizes, per, local_hat.dtype)
     return pend if async_op else pend.wait()
 
 

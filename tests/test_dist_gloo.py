@@ -54,6 +54,11 @@ def _worker_unequal(rank, world, port, out_dir, Vs):
         if use_async:
             got = got.wait()
         torch.save(got.clone(), os.path.join(out_dir, f"g_{n}_{rank}.pt"))
+    # bf16 on the wire (SURVEY.md section 8(e) wording): every rank gets the bf16-rounded embeddings back in fp32
+    full = torch.randn(7, 16, generator=torch.Generator().manual_seed(1))
+    lo, hi = retrieval.shard_range(7, rank, world)
+    got = retrieval.all_gather_embeddings(full[lo:hi].clone(), n_total=7, wire_dtype=torch.bfloat16)
+    torch.save(got.clone(), os.path.join(out_dir, f"gb_{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -63,6 +68,10 @@ def _check_unequal(tmp_path, world, cases):
         full = torch.randn(V, 16, generator=torch.Generator().manual_seed(1))
         for r in range(world):
             assert torch.equal(torch.load(os.path.join(str(tmp_path), f"g_{n}_{r}.pt")), full), (V, with_total, use_async, r)
+    full = torch.randn(7, 16, generator=torch.Generator().manual_seed(1))
+    for r in range(world):
+        got = torch.load(os.path.join(str(tmp_path), f"gb_{r}.pt"))
+        assert got.dtype == torch.float32 and torch.equal(got, full.bfloat16().float()), r
 
 
 def test_all_gather_with_unequal_and_empty_shards(tmp_path):
