@@ -3,7 +3,7 @@
 # Sources compile in parallel into build/ (git-ignored); extra arguments go to every nvcc compile.
 set -e
 cd "$(dirname "$0")"
-SRC="hb_gemm hb_attn hb_attn2 hb_attn3 hb_attn_tc hb_attn_small hb_elem hb_moment hb_preproc hb_api"
+SRC="hb_gemm hb_attn hb_attn2 hb_attn3 hb_attn_tc hb_attn_small hb_elem hb_moment hb_preproc hb_tokenize hb_api"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden"
 OUT="${HB_OUT:-hirest_b200/libhirest_b200.so}"
 BDIR="${HB_BUILD_DIR:-build}"

@@ -123,6 +123,13 @@ SIGNATURES = {
     "hb_subsample_pool_normalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hb_subsample_pool_normalize_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hb_resample_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "hb_wordpiece_create": (C.c_int, [C.c_char_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "hb_wordpiece_destroy": (None, [C.c_void_p]),
+    "hb_wordpiece_encode_captions": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p]),
+    "hb_bpe_create": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "hb_bpe_destroy": (None, [C.c_void_p]),
+    "hb_bpe_tokenize": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "hb_asr_warp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                               C.c_void_p]),
     "hb_similarity": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int,

@@ -78,6 +78,33 @@ class ClipBpeTokenizer:
         self._unbyte = {s: b for b, s in enumerate(self._byte)}
         self._memo: Dict[str, List[int]] = {}
         self.sot_token, self.eot_token = self.encoder[SOT], self.encoder[EOT]
+        self._merge_lines = "\n".join(" ".join(m) for m in merges)
+        self._native = False   # built on first use (csrc/hb_tokenize.cu: ASCII fast path of the same algorithm)
+
+    def _native_handle(self):
+        if self._native is False:
+            self._native = None
+            try:
+                import ctypes as C
+
+                from . import _lib
+
+                lib = _lib.load()
+                blob = self._merge_lines.encode("utf-8")
+                handle = C.c_void_p()
+                if lib.hb_bpe_create(blob, len(blob), C.byref(handle)) == 0:
+                    self._native = (lib, handle)
+            except (OSError, RuntimeError, AttributeError):
+                self._native = None   # library not built: the Python implementation is complete on its own
+        return self._native
+
+    def __del__(self):
+        h = getattr(self, "_native", None)
+        if h:
+            try:
+                h[0].hb_bpe_destroy(h[1])
+            except Exception:  # noqa: BLE001  (interpreter shutdown)
+                pass
 
     # ------------------------------------------------------------------ BPE
     def _merge_word(self, symbols: List[str]) -> List[str]:
@@ -146,12 +173,31 @@ class ClipBpeTokenizer:
         chunks.append(buf.decode("utf-8", errors="replace"))
         return "".join(chunks)
 
-    def tokenize(self, texts: Union[str, Sequence[str]], context_length: int = 77, truncate: bool = False) -> torch.LongTensor:
-        """``clip.tokenize``: ``[len(texts), context_length]`` int64, ``[SOT] ids [EOT] 0 0 …``."""
+    def tokenize(self, texts: Union[str, Sequence[str]], context_length: int = 77, truncate: bool = False,
+                 native: bool = True) -> torch.LongTensor:
+        """``clip.tokenize``: ``[len(texts), context_length]`` int64, ``[SOT] ids [EOT] 0 0 …``.  ASCII prompts are tokenised by the
+        library's native batch tokeniser in one call when it is available (and ftfy, which could rewrite them, is not installed);
+        prompts it flags (non-ASCII, ``&`` entities, control characters) go through the Python code of this class."""
         if isinstance(texts, str):
             texts = [texts]
-        out = torch.zeros((len(texts), context_length), dtype=torch.long)
-        for i, text in enumerate(texts):
+        n = len(texts)
+        out = torch.zeros((n, context_length), dtype=torch.long)
+        todo = range(n)
+        h = self._native_handle() if (native and n > 0 and context_length >= 2 and _ftfy is None) else None
+        if h is not None:
+            import ctypes as C
+
+            import numpy as np
+
+            lib, handle = h
+            arr = (C.c_char_p * n)(*[t.encode("utf-8") if "\0" not in t else None for t in texts])
+            status = np.ones(n, dtype=np.uint8)
+            if lib.hb_bpe_tokenize(handle, arr, n, int(context_length), int(bool(truncate)), out.data_ptr(), status.ctypes.data) == 0:
+                for i in np.nonzero(status == 2)[0].tolist():
+                    raise RuntimeError(f"Input {texts[i]} is too long for context length {context_length}")
+                todo = np.nonzero(status == 1)[0].tolist()
+        for i in todo:
+            text = texts[i]
             ids = [self.sot_token] + self.encode(text) + [self.eot_token]
             if len(ids) > context_length:
                 if not truncate:

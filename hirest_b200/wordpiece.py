@@ -157,10 +157,58 @@ class WordPieceTokenizer:
         m[:len(inp)] = 1
         return a, b, m
 
-    def encode_captions(self, captions: Sequence[str], max_words: int = 48):
-        """Batch form: three ``int64 [n, max_words]`` arrays."""
-        rows = [self.encode_caption(c, max_words) for c in captions]
-        return tuple(np.stack([r[i] for r in rows]) if rows else np.zeros((0, max_words), np.int64) for i in range(3))
+    def _native_handle(self):
+        """The library's batch tokeniser (csrc/hb_tokenize.cu: ASCII fast path) for the reference's configuration, or None."""
+        h = getattr(self, "_native", False)
+        if h is not False:
+            return h
+        self._native = None
+        if (self.never_split == frozenset(SPECIAL_TOKENS) and self.unk_token == "[UNK]" and self.max_chars_per_word == 100
+                and all(t in self.vocab for t in ("[UNK]", "[CLS]", "[SEP]"))):
+            try:
+                import ctypes as C
+
+                from . import _lib
+
+                lib = _lib.load()
+                toks = [t for t in self.vocab if t and "\0" not in t]
+                blob = b"".join(t.encode("utf-8") + b"\0" for t in toks)
+                ids = np.asarray([self.vocab[t] for t in toks], dtype=np.int64)
+                handle = C.c_void_p()
+                if lib.hb_wordpiece_create(blob, len(blob), ids.ctypes.data, len(toks), int(self.do_lower_case), C.byref(handle)) == 0:
+                    self._native = (lib, handle)
+            except (OSError, RuntimeError, AttributeError):
+                self._native = None   # library not built: the Python implementation below is complete on its own
+        return self._native
+
+    def __del__(self):
+        h = getattr(self, "_native", None)
+        if h:
+            try:
+                h[0].hb_wordpiece_destroy(h[1])
+            except Exception:  # noqa: BLE001  (interpreter shutdown)
+                pass
+
+    def encode_captions(self, captions: Sequence[str], max_words: int = 48, native: bool = True):
+        """Batch form: three ``int64 [n, max_words]`` arrays.  ASCII captions go through the library's native batch tokeniser in one
+        call when it is available; captions it flags (non-ASCII, control characters) and everything else use the code above."""
+        n = len(captions)
+        out = tuple(np.zeros((n, max_words), dtype=np.int64) for _ in range(3))
+        todo = range(n)
+        h = self._native_handle() if (native and n > 0 and max_words >= 2) else None
+        if h is not None:
+            import ctypes as C
+
+            lib, handle = h
+            arr = (C.c_char_p * n)(*[c.encode("utf-8") if "\0" not in c else None for c in captions])
+            flags = np.ones(n, dtype=np.uint8)
+            if lib.hb_wordpiece_encode_captions(handle, arr, n, int(max_words), out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data,
+                                                flags.ctypes.data) == 0:
+                todo = np.nonzero(flags)[0].tolist()
+        for i in todo:
+            a, b, m = self.encode_caption(captions[i], max_words)
+            out[0][i], out[1][i], out[2][i] = a, b, m
+        return out
 
     def decode(self, ids: Sequence[int]) -> str:
         """``modeling.py:615-626``: ids → tokens, cut at the first [SEP] / [PAD], join, merge ``##`` continuations."""

@@ -300,6 +300,32 @@ HB_API int hb_small_attention_f32(const float* q, const float* k, const float* v
                                   int ldk, int ldv, int ldo, int64_t bsq, int64_t bsk, int64_t bsv, int64_t bso, float scale,
                                   int mask_mode, float mask_const, int causal_soft, int use_tensor_cores, void* stream);
 
+/* ---- host-only batch tokenisers (no device work; usable before hb_init) ---------------------------------------------------
+ * ASCII fast path of the two tokenisers on the path; a text with a byte >= 0x7F, a control character other than tab / newline /
+ * carriage return (or, for BPE, an '&': HTML entities) is flagged and left to the caller's Unicode implementation
+ * (hirest_b200/wordpiece.py, tokenizer.py), which gives the same ids for ASCII input.
+ *
+ * WordPiece = clip4caption/modules/tokenization.py BertTokenizer (basic tokenizer + greedy longest-match pieces, never_split =
+ * the five special tokens) as used by hirest_dataset.py:119-121 and clip4cap_get_text (:533-580).
+ * tokens: n_tokens NUL-terminated UTF-8 strings back to back (tokens_bytes in total), ids[i] = id of token i (a repeated token keeps
+ * its last id, like the reference's dict).  [UNK], [CLS], [SEP] must be present. */
+typedef struct HbWordPiece HbWordPiece;
+HB_API int hb_wordpiece_create(const char* tokens, int64_t tokens_bytes, const int64_t* ids, int n_tokens, int do_lower_case,
+                               HbWordPiece** out);
+HB_API void hb_wordpiece_destroy(HbWordPiece* w);
+/* clip4cap_get_text for n captions: input_ids = [CLS] w1 .., target_ids = w1 .. [SEP], mask, each int64 [n, max_words] (pieces
+ * truncated to max_words - 1).  fallback[i] = 1: row i was NOT written (non-ASCII caption), the caller fills it. */
+HB_API int hb_wordpiece_encode_captions(const HbWordPiece* w, const char* const* captions, int n, int max_words, int64_t* input_ids,
+                                        int64_t* target_ids, int64_t* mask, uint8_t* fallback);
+/* CLIP byte-pair encoding = EVA_clip/simple_tokenizer.py + clip.tokenize (hirest_dataset.py:528, inference_video_retrieval.py:203-206).
+ * merges: the merge table's lines 1 .. 48894 ("left right", UTF-8), newline separated, in rank order. */
+typedef struct HbBpe HbBpe;
+HB_API int hb_bpe_create(const char* merges, int64_t merges_bytes, HbBpe** out);
+HB_API void hb_bpe_destroy(HbBpe* b);
+/* out int64 [n, context_length] = [SOT] ids [EOT] 0 0 ..; status[i]: 0 written, 1 not written (caller's Unicode path),
+ * 2 longer than context_length and truncate == 0 (clip.tokenize raises).  Not thread-safe per handle (memoises words). */
+HB_API int hb_bpe_tokenize(HbBpe* b, const char* const* texts, int n, int context_length, int truncate, int64_t* out, uint8_t* status);
+
 #ifdef __cplusplus
 }
 #endif
