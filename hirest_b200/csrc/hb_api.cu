@@ -36,6 +36,7 @@ int g_cg = 2;
 int g_attn_version = 3;
 int g_small_attn_tc = 1;
 int g_dec_split_kbs = 6;    // caption decoder: k-blocks (64 bf16) per split-K slice of the hidden-width linears; 0 = no split-K
+int g_dec_kv_index = 1;     // caption decoder: beam re-order through an index table instead of copying the KV caches (max_words <= 64)
 int g_ln_split_fuse = 1;    // small models: LayerNorm + split-operand conversion in one kernel (ln_split)
 int g_decoder_graphs = 1;   // replay the caption decoder's steps as CUDA graphs (from the second search of a shape on)
 int g_profile_layer = -1;   // debug: cudaProfilerStart/Stop around this ViT layer (ncu --profile-from-start off)   // fp32 small-sequence attention on tensor cores (hb_attn_tc.cu) instead of CUDA cores
@@ -379,7 +380,7 @@ int hb_init(int device) {
   g_num_sms = prop.multiProcessorCount;
   if (hb::tmap_init() != 0) return fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   if (!g_inited) {   // A/B switches from the environment (hirest_b200_debug.h), once
-    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "decoder_graphs", "decoder_split_k", "ln_split_fuse", "attention_dots_late", "profile_layer", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
+    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "decoder_graphs", "decoder_split_k", "decoder_kv_index", "ln_split_fuse", "attention_dots_late", "profile_layer", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
                                  "gemm_dynamic_schedule", "gemm_resid_prefetch_chunks"};
     for (const char* key : keys) {
       std::string env = std::string("HB_DEBUG_") + key;
@@ -434,6 +435,8 @@ int hb_debug_set(const char* key, int value) {
     g_dec_split_kbs = value;
   } else if (k == "profile_layer") {
     g_profile_layer = value;
+  } else if (k == "decoder_kv_index") {
+    g_dec_kv_index = value ? 1 : 0;
   } else if (k == "ln_split_fuse") {
     g_ln_split_fuse = value ? 1 : 0;
   } else if (k == "attention_dots_late") {
@@ -1279,6 +1282,7 @@ struct HbDecoder {
   DevBuf tok, scores, done, nsteps, prev_k, ys, cand_v, cand_i;
   static constexpr int MAX_SPLITS = 16;
   DevBuf skws;             // split-K partial sums [MAX_SPLITS, max rows, hidden] fp32
+  DevBuf kv_idx[2];        // beam re-ordering as an index table int32 [R, max_words] (ping-pong), shared by all layers
   CUtensorMap tm_hd, tm_ffn, tm_enc;
   // CUDA graphs of the decode steps, valid for one (n_inst, beam, enc_len) shape
   std::vector<cudaGraphExec_t> graphs;
@@ -1377,6 +1381,8 @@ int hb_decoder_create(const HbDecoderConfig* cfg, const HbDecoderWeights* w, int
   if ((r = d->cand_v.alloc(R * max_beam * 4))) return r;
   if ((r = d->cand_i.alloc(R * max_beam * 4))) return r;
   if ((r = d->skws.alloc(static_cast<size_t>(HbDecoder::MAX_SPLITS) * R * Hd * 4))) return r;
+  for (int i = 0; i < 2; ++i)
+    if ((r = d->kv_idx[i].alloc(R * static_cast<size_t>(cfg->max_words) * 4))) return r;
   if ((r = d->done.alloc(static_cast<size_t>(max_inst) * 4))) return r;
   if ((r = d->nsteps.alloc(static_cast<size_t>(max_inst) * 4))) return r;
   if ((r = d->prev_k.alloc(static_cast<size_t>(cfg->max_words) * R * 4))) return r;
@@ -1490,22 +1496,27 @@ static int decoder_step_launches(HbDecoder* d, cudaStream_t s) {
                                                       d->emb_ln_b.ptr(), pos, x, R, Hd, s));
   // sk: the hidden-width linears run as split-K GEMM + finish (bias, residual, LayerNorm and the next GEMM's split operand in
   // one kernel); `op_ready`: d->op already holds the split operand of the next linear's input
+  // kvi: the beam re-order is an index table the self-attention reads through (one tiny kernel per step) instead of a copy of
+  // every layer's K / V prefix (2 x R x (pos + 1) x hidden floats per layer per step)
+  const bool kvi = g_dec_kv_index && Tmax <= 64;
   const bool sk = g_dec_split_kbs > 0 && Hd % 4 == 0 && Hd <= 1536;
   const int S_hd = dec_split_count(Hd), S_ff = dec_split_count(Ff);
   bool op_ready = false;
   for (auto& Lp : d->layers) {
     HbDecoder::Layer& L = *Lp;
-    float* kc = L.kc[d->cur].as<float>();
-    float* vc = L.vc[d->cur].as<float>();
+    float* kc = L.kc[kvi ? 0 : d->cur].as<float>();
+    float* vc = L.vc[kvi ? 0 : d->cur].as<float>();
     if (op_ready) { if ((r = dec_gemm_raw(d, R, Hd, d->tm_hd, L.sqkv, d->qkv.as<float>(), s))) return r; }
     else if ((r = dec_gemm(d, x, R, Hd, 0, d->tm_hd, L.sqkv, d->qkv.as<float>(), s))) return r;
-    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::dec_cache_append_launch(d->qkv.as<float>(), kc, vc, pos, R, Tmax, Hd, s));
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::dec_cache_append_launch(d->qkv.as<float>(), kc, vc, kvi ? d->kv_idx[d->cur].as<int>() : nullptr, pos, R,
+                                                               Tmax, Hd, s));
     hb::SmallAttnF32Params ap;  // one query (the new token) over the cached prefix: every cached key is <= the query position
     ap.q = d->qkv.as<float>(); ap.k = kc; ap.v = vc; ap.out = d->att.as<float>();
     ap.B = R; ap.H = c.heads; ap.Tq = 1; ap.Tk = pos + 1;
     ap.ldq = 3 * Hd; ap.ldk = Hd; ap.ldv = Hd; ap.ldo = Hd;
     ap.bsq = 3 * Hd; ap.bsk = ap.bsv = static_cast<long long>(Tmax) * Hd; ap.bso = Hd;
     ap.scale = 0.125f; ap.mask_mode = 0;
+    if (kvi) { ap.kv_row_idx = d->kv_idx[d->cur].as<int>(); ap.ld_idx = Tmax; }
     HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::small_attn_f32_launch(ap, s));
     // self-attention output: s1 = LN(dense(att) + x); cross-attention query: qc = dense(s1)
     if (sk) {
@@ -1562,6 +1573,11 @@ static int decoder_step_launches(HbDecoder* d, cudaStream_t s) {
                                                          pos, d->n_inst, d->beam, c.eos, d->cand_v.as<float>(), d->cand_i.as<int>(), s));
   g_launches.fetch_add(1, std::memory_order_relaxed);   // beam_advance is two kernels
   // beams re-order: new beam j continues old beam prev_k[j]
+  if (kvi) {
+    HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::dec_index_advance_launch(d->kv_idx[d->cur].as<int>(), d->kv_idx[d->cur ^ 1].as<int>(), pk, pos + 1, R,
+                                                                d->beam, Tmax, s));
+    return HB_OK;
+  }
   for (auto& Lp : d->layers) {
     HbDecoder::Layer& L = *Lp;
     HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::dec_cache_reorder_launch(L.kc[d->cur].as<float>(), L.vc[d->cur].as<float>(), L.kc[d->cur ^ 1].as<float>(),

@@ -57,6 +57,10 @@ struct SmallAttnF32Params {
   float mask_const = 0.f;
   int causal_soft = 0;
   int kv_div = 1;  // K/V batch index = b / kv_div (beams of one instance share the encoder keys / values)
+  // Decode kernel only (Tq == 1, Tk <= 64): key t of batch row b lives in K / V batch kv_row_idx[b * ld_idx + t] instead of b — the
+  // caption decoder's beam re-ordering as an index table instead of copying the KV cache (kv_div must be 1)
+  const int* kv_row_idx = nullptr;
+  int ld_idx = 0;
 };
 int small_attn_f32_launch(const SmallAttnF32Params& p, cudaStream_t stream);
 // Same contract on the tensor cores (hb_attn_tc.cu: split-bf16 UMMAs for q.k^T and p.v, fp32 softmax; fp32-accurate).  Needs a

@@ -241,8 +241,14 @@ __global__ void __launch_bounds__(256) decode_attn_f32_kernel(const SmallAttnF32
   if (w >= p.B * p.H) return;
   const int b = w / p.H, h = w - b * p.H;
   const float* qg = p.q + b * p.bsq + h * DH;
-  const float* kg = p.k + (b / p.kv_div) * p.bsk + h * DH;
-  const float* vg = p.v + (b / p.kv_div) * p.bsv + h * DH;
+  // K / V batch of this lane's two keys (and, by shuffle, of every key in the p.v loop): b / kv_div, or the beam index table
+  long long kb[2];
+#pragma unroll
+  for (int jj = 0; jj < 2; ++jj) {
+    const int key = jj * 32 + lane;
+    kb[jj] = (p.kv_row_idx != nullptr) ? static_cast<long long>(p.kv_row_idx[static_cast<long long>(b) * p.ld_idx + (key < p.Tk ? key : 0)])
+                                       : static_cast<long long>(b / p.kv_div);
+  }
   const float2 q2 = *reinterpret_cast<const float2*>(qg + lane * 2);   // lane holds q[2 lane], q[2 lane + 1]
   float s[2];
   float m = -INFINITY;
@@ -250,7 +256,7 @@ __global__ void __launch_bounds__(256) decode_attn_f32_kernel(const SmallAttnF32
   for (int jj = 0; jj < 2; ++jj) {
     const int key = jj * 32 + lane;
     s[jj] = -INFINITY;
-    const float* kr = kg + static_cast<size_t>(key < p.Tk ? key : 0) * p.ldk;
+    const float* kr = p.k + kb[jj] * p.bsk + h * DH + static_cast<size_t>(key < p.Tk ? key : 0) * p.ldk;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
     for (int ch = 0; ch < 16; ++ch) {
@@ -287,7 +293,10 @@ __global__ void __launch_bounds__(256) decode_attn_f32_kernel(const SmallAttnF32
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         vv[u] = make_float2(0.f, 0.f);
-        if (j0 + u < nk) vv[u] = __ldg(reinterpret_cast<const float2*>(vg + static_cast<size_t>(jj * 32 + j0 + u) * p.ldv + lane * 2));
+        if (j0 + u < nk) {   // warp-uniform
+          const long long vb = __shfl_sync(0xffffffffu, kb[jj], j0 + u);
+          vv[u] = __ldg(reinterpret_cast<const float2*>(p.v + vb * p.bsv + h * DH + static_cast<size_t>(jj * 32 + j0 + u) * p.ldv + lane * 2));
+        }
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -307,6 +316,7 @@ __global__ void __launch_bounds__(256) decode_attn_f32_kernel(const SmallAttnF32
 
 int small_attn_f32_launch(const SmallAttnF32Params& p, cudaStream_t stream) {
   if (p.B <= 0 || p.H <= 0 || p.Tq <= 0 || p.Tk <= 0) return -3;
+  if (p.kv_row_idx != nullptr && !(p.Tq == 1 && p.Tk <= 64 && p.mask_mode != 1 && !p.causal_soft && p.kv_div == 1)) return -3;
   if (p.Tq == 1 && p.Tk <= 64 && p.mask_mode != 1 && !p.causal_soft) {
     const long long warps = static_cast<long long>(p.B) * p.H;
     decode_attn_f32_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, stream>>>(p);

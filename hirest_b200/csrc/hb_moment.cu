@@ -418,13 +418,26 @@ __global__ void __launch_bounds__(256) dec_embed_kernel(const long long* __restr
 }
 
 __global__ void __launch_bounds__(256) dec_cache_append_kernel(const float* __restrict__ qkv, float* __restrict__ kc,
-                                                               float* __restrict__ vc, int pos, int R, int Tmax, int Hd) {
+                                                               float* __restrict__ vc, int* __restrict__ row_idx, int pos, int R,
+                                                               int Tmax, int Hd) {
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (t >= static_cast<long long>(R) * Hd) return;
   const long long r = t / Hd;
   const int k = static_cast<int>(t - r * Hd);
   kc[(r * Tmax + pos) * Hd + k] = qkv[r * 3 * Hd + Hd + k];
   vc[(r * Tmax + pos) * Hd + k] = qkv[r * 3 * Hd + 2 * Hd + k];
+  if (row_idx != nullptr && k == 0) row_idx[r * Tmax + pos] = static_cast<int>(r);   // this beam's newest key lives in its own cache row
+}
+
+// Beam re-ordering without moving the KV cache: the history of new beam j is that of old beam prev_k[j], so its index row is a copy
+// of that beam's (idx[row][t] = cache row that holds key t of the row's hypothesis).  One table serves every decoder layer.
+__global__ void __launch_bounds__(256) dec_index_advance_kernel(const int* __restrict__ idx_old, int* __restrict__ idx_new,
+                                                                const int* __restrict__ prev_k, int len, int R, int beam, int Tmax) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= R * len) return;
+  const int r = t / len, k = t - r * len;
+  const int src_r = (r / beam) * beam + prev_k[r];
+  idx_new[r * Tmax + k] = idx_old[src_r * Tmax + k];
 }
 
 __global__ void __launch_bounds__(256) dec_cache_reorder_kernel(const float* __restrict__ ksrc, const float* __restrict__ vsrc,
@@ -754,8 +767,13 @@ int dec_embed_launch(const long long* tok, const float* word_emb, const float* p
   dec_embed_kernel<<<nblocks(R, 8), 256, 0, s>>>(tok, word_emb, pos_emb, lnw, lnb, pos, x, R, Hd);
   return static_cast<int>(cudaGetLastError());
 }
-int dec_cache_append_launch(const float* qkv, float* kc, float* vc, int pos, int R, int Tmax, int Hd, cudaStream_t s) {
-  dec_cache_append_kernel<<<nblocks(static_cast<long long>(R) * Hd, 256), 256, 0, s>>>(qkv, kc, vc, pos, R, Tmax, Hd);
+int dec_cache_append_launch(const float* qkv, float* kc, float* vc, int* row_idx, int pos, int R, int Tmax, int Hd, cudaStream_t s) {
+  dec_cache_append_kernel<<<nblocks(static_cast<long long>(R) * Hd, 256), 256, 0, s>>>(qkv, kc, vc, row_idx, pos, R, Tmax, Hd);
+  return static_cast<int>(cudaGetLastError());
+}
+int dec_index_advance_launch(const int* idx_old, int* idx_new, const int* prev_k, int len, int R, int beam, int Tmax, cudaStream_t s) {
+  if (len <= 0) return 0;
+  dec_index_advance_kernel<<<nblocks(static_cast<long long>(R) * len, 256), 256, 0, s>>>(idx_old, idx_new, prev_k, len, R, beam, Tmax);
   return static_cast<int>(cudaGetLastError());
 }
 int dec_cache_reorder_launch(const float* ksrc, const float* vsrc, float* kdst, float* vdst, const int* prev_k, int len, int R,

@@ -47,8 +47,11 @@ int trim_feats_launch(const float* x, const long long* mask, float* out, int B, 
 // x[r,:] = TF_LN(word_emb[tok[r]] + pos_emb[pos]; w, b, 1e-12)                       (module_decoder.py:309-320)
 int dec_embed_launch(const long long* tok, const float* word_emb, const float* pos_emb, const float* lnw, const float* lnb, int pos,
                      float* x, int R, int Hd, cudaStream_t s);
-// append this step's self-attention key / value (columns [Hd,2Hd) / [2Hd,3Hd) of qkv) at position `pos` of the caches
-int dec_cache_append_launch(const float* qkv, float* kc, float* vc, int pos, int R, int Tmax, int Hd, cudaStream_t s);
+// append this step's self-attention key / value (columns [Hd,2Hd) / [2Hd,3Hd) of qkv) at position `pos` of the caches; with
+// row_idx (int [R, Tmax], may be null) also row_idx[r, pos] = r
+int dec_cache_append_launch(const float* qkv, float* kc, float* vc, int* row_idx, int pos, int R, int Tmax, int Hd, cudaStream_t s);
+// beams re-order as an index table: idx_new[r, 0..len) = idx_old[(r / beam) * beam + prev_k[r], 0..len)
+int dec_index_advance_launch(const int* idx_old, int* idx_new, const int* prev_k, int len, int R, int beam, int Tmax, cudaStream_t s);
 // beams re-order: dst[r, 0..len) = src[(r / beam) * beam + prev_k[r], 0..len) for both caches of one layer
 int dec_cache_reorder_launch(const float* ksrc, const float* vsrc, float* kdst, float* vdst, const int* prev_k, int len, int R,
                              int beam, int Tmax, int Hd, cudaStream_t s);

@@ -24,6 +24,8 @@ extern "C" {
  *                                                              + one finish kernel (bias, residual, LayerNorm, next split operand); 0 = off
  * "profile_layer"              -1 | layer            -1        cudaProfilerStart / Stop around this ViT layer of every encode_image chunk
  *                                                              (ncu --profile-from-start off captures exactly its 5 kernels)
+ * "decoder_kv_index"           0 | 1                 1         caption decoder: beam re-order through an index table read by the self-attention
+ *                                                              (max_words <= 64) instead of copying every layer's KV prefix; same results
  * "ln_split_fuse"              0 | 1                 1         small models: LayerNorm + split-operand conversion in one kernel instead of a
  *                                                              LayerNorm kernel and a split kernel (different reduction order: ~1e-7)
  * "attention_dots_late"        0..3 (tile bit mask)  0         v3: tile t computes the next item's extra-token dot products after its output

@@ -270,14 +270,15 @@ def test_decoder_graph_replay_and_kernel_variants_agree(hb, golden, tmp_path):
             assert m.test_step(b, num_beams=3)["token_ids"] == g["ids"]
             counts.append(hb.hb_launch_count() - n0)
         assert counts[0] == counts[1] == counts[2], counts
-        for key in ("decoder_graphs", "decoder_split_k"):
-            _lib.debug_set(key, 0)
+        for key in ("decoder_graphs", "decoder_split_k", "decoder_kv_index"):
+            _lib.debug_set(key, 0)   # (switches accumulate: the last variant runs with all three off)
             m = fresh()
             for _ in range(2):
                 assert m.test_step(b, num_beams=3)["token_ids"] == g["ids"], key
     finally:
         _lib.debug_set("decoder_graphs", 1)
         _lib.debug_set("decoder_split_k", 6)
+        _lib.debug_set("decoder_kv_index", 1)
 
 
 def test_config4_size_determinism_and_oracle_subset(hb):
