@@ -1492,16 +1492,17 @@ static int decoder_step_launches(HbDecoder* d, cudaStream_t s) {
   const int R = d->n_inst * d->beam, Hd = c.hidden, Ff = c.ffn, pos = d->step, Tmax = c.max_words;
   float* x = d->x.as<float>();
   int r;
-  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::dec_embed_launch(d->tok.as<long long>(), d->word_emb.ptr(), d->pos_emb.ptr(), d->emb_ln_w.ptr(),
-                                                      d->emb_ln_b.ptr(), pos, x, R, Hd, s));
   // sk: the hidden-width linears run as split-K GEMM + finish (bias, residual, LayerNorm and the next GEMM's split operand in
   // one kernel); `op_ready`: d->op already holds the split operand of the next linear's input
+  const bool sk = g_dec_split_kbs > 0 && Hd % 4 == 0 && Hd <= 1536;
+  const bool fuse_op = sk && Tmax <= 64 && d->enc_len <= 64;   // producers of a linear's input also write its split operand
+  HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::dec_embed_launch(d->tok.as<long long>(), d->word_emb.ptr(), d->pos_emb.ptr(), d->emb_ln_w.ptr(),
+                                                      d->emb_ln_b.ptr(), pos, x, fuse_op ? d->op.as<__nv_bfloat16>() : nullptr, R, Hd, s));
   // kvi: the beam re-order is an index table the self-attention reads through (one tiny kernel per step) instead of a copy of
   // every layer's K / V prefix (2 x R x (pos + 1) x hidden floats per layer per step)
   const bool kvi = g_dec_kv_index && Tmax <= 64;
-  const bool sk = g_dec_split_kbs > 0 && Hd % 4 == 0 && Hd <= 1536;
   const int S_hd = dec_split_count(Hd), S_ff = dec_split_count(Ff);
-  bool op_ready = false;
+  bool op_ready = fuse_op;
   for (auto& Lp : d->layers) {
     HbDecoder::Layer& L = *Lp;
     float* kc = L.kc[kvi ? 0 : d->cur].as<float>();
@@ -1517,10 +1518,11 @@ static int decoder_step_launches(HbDecoder* d, cudaStream_t s) {
     ap.bsq = 3 * Hd; ap.bsk = ap.bsv = static_cast<long long>(Tmax) * Hd; ap.bso = Hd;
     ap.scale = 0.125f; ap.mask_mode = 0;
     if (kvi) { ap.kv_row_idx = d->kv_idx[d->cur].as<int>(); ap.ld_idx = Tmax; }
+    if (fuse_op) { ap.op_out = d->op.as<__nv_bfloat16>(); ap.ld_op = Hd; }
     HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::small_attn_f32_launch(ap, s));
     // self-attention output: s1 = LN(dense(att) + x); cross-attention query: qc = dense(s1)
     if (sk) {
-      HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(d->att.as<float>(), d->op.as<__nv_bfloat16>(), R, Hd, 0, s));
+      if (!fuse_op) HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(d->att.as<float>(), d->op.as<__nv_bfloat16>(), R, Hd, 0, s));
       if ((r = dec_gemm_split(d, R, Hd, d->tm_hd, L.so, S_hd, s))) return r;
       if ((r = dec_finish(d, R, L.so, S_hd, x, 0, &L.so_ln_w, &L.so_ln_b, d->s1.as<float>(), true, s))) return r;
       if ((r = dec_gemm_split(d, R, Hd, d->tm_hd, L.eq, S_hd, s))) return r;
@@ -1536,10 +1538,11 @@ static int decoder_step_launches(HbDecoder* d, cudaStream_t s) {
     cp.ldq = Hd; cp.ldk = cp.ldv = 2 * Hd; cp.ldo = Hd;
     cp.bsq = Hd; cp.bsk = cp.bsv = static_cast<long long>(d->enc_len) * 2 * Hd; cp.bso = Hd;
     cp.scale = 0.125f; cp.mask_mode = 2; cp.mask_const = -10000.0f; cp.kv_div = d->beam;
+    if (fuse_op) { cp.op_out = d->op.as<__nv_bfloat16>(); cp.ld_op = Hd; }
     HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::small_attn_f32_launch(cp, s));
     // c1 = LN(dense(att) + s1); feed-forward: x = LN(dense(gelu(dense(c1))) + c1)
     if (sk) {
-      HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(d->att.as<float>(), d->op.as<__nv_bfloat16>(), R, Hd, 0, s));
+      if (!fuse_op) HB_LAUNCH_P(CAT_OTHER, 0.0, s, hb::split3_act_launch(d->att.as<float>(), d->op.as<__nv_bfloat16>(), R, Hd, 0, s));
       if ((r = dec_gemm_split(d, R, Hd, d->tm_hd, L.eo, S_hd, s))) return r;
       if ((r = dec_finish(d, R, L.eo, S_hd, d->s1.as<float>(), 0, &L.eo_ln_w, &L.eo_ln_b, d->c1.as<float>(), true, s))) return r;
       if ((r = dec_gemm_raw(d, R, Hd, d->tm_hd, L.inter, d->mid.as<float>(), s))) return r;

@@ -61,6 +61,10 @@ struct SmallAttnF32Params {
   // caption decoder's beam re-ordering as an index table instead of copying the KV cache (kv_div must be 1)
   const int* kv_row_idx = nullptr;
   int ld_idx = 0;
+  // Decode kernel only: also write the output as the [lo | hi | hi] split-bf16 operand of the following linear,
+  // op_out [B, 3 * ld_op] with ld_op = H * 64 (what split3_act_kernel would produce from `out`)
+  __nv_bfloat16* op_out = nullptr;
+  int ld_op = 0;
 };
 int small_attn_f32_launch(const SmallAttnF32Params& p, cudaStream_t stream);
 // Same contract on the tensor cores (hb_attn_tc.cu: split-bf16 UMMAs for q.k^T and p.v, fp32 softmax; fp32-accurate).  Needs a

@@ -309,14 +309,24 @@ __global__ void __launch_bounds__(256) decode_attn_f32_kernel(const SmallAttnF32
     }
   }
   const float inv = 1.0f / ts;
-  *reinterpret_cast<float2*>(p.out + b * p.bso + h * DH + lane * 2) = make_float2(o0 * inv, o1 * inv);
+  const float y0 = o0 * inv, y1 = o1 * inv;
+  *reinterpret_cast<float2*>(p.out + b * p.bso + h * DH + lane * 2) = make_float2(y0, y1);
+  if (p.op_out != nullptr) {
+    const __nv_bfloat16 h0 = __float2bfloat16(y0), h1 = __float2bfloat16(y1);
+    const __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(y0 - __bfloat162float(h0), y1 - __bfloat162float(h1));
+    __nv_bfloat16* o = p.op_out + static_cast<long long>(b) * 3 * p.ld_op + h * DH + lane * 2;
+    *reinterpret_cast<__nv_bfloat162*>(o) = ll;
+    *reinterpret_cast<__nv_bfloat162*>(o + p.ld_op) = hh;
+    *reinterpret_cast<__nv_bfloat162*>(o + 2 * p.ld_op) = hh;
+  }
 }
 
 }  // namespace
 
 int small_attn_f32_launch(const SmallAttnF32Params& p, cudaStream_t stream) {
   if (p.B <= 0 || p.H <= 0 || p.Tq <= 0 || p.Tk <= 0) return -3;
-  if (p.kv_row_idx != nullptr && !(p.Tq == 1 && p.Tk <= 64 && p.mask_mode != 1 && !p.causal_soft && p.kv_div == 1)) return -3;
+  if ((p.kv_row_idx != nullptr || p.op_out != nullptr) && !(p.Tq == 1 && p.Tk <= 64 && p.mask_mode != 1 && !p.causal_soft && (p.kv_div == 1 || p.kv_row_idx == nullptr))) return -3;
   if (p.Tq == 1 && p.Tk <= 64 && p.mask_mode != 1 && !p.causal_soft) {
     const long long warps = static_cast<long long>(p.B) * p.H;
     decode_attn_f32_kernel<<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, stream>>>(p);

@@ -389,7 +389,8 @@ __global__ void __launch_bounds__(256) trim_feats_kernel(const float* __restrict
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dec_embed_kernel(const long long* __restrict__ tok, const float* __restrict__ word_emb,
                                                         const float* __restrict__ pos_emb, const float* __restrict__ lnw,
-                                                        const float* __restrict__ lnb, int pos, float* __restrict__ x, int R, int Hd) {
+                                                        const float* __restrict__ lnb, int pos, float* __restrict__ x,
+                                                        __nv_bfloat16* __restrict__ op, int R, int Hd) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= R) return;
   const float* e = word_emb + tok[warp] * Hd;
@@ -413,7 +414,15 @@ __global__ void __launch_bounds__(256) dec_embed_kernel(const long long* __restr
 #pragma unroll
   for (int i = 0; i < 32; ++i) {
     const int k = lane + i * 32;
-    if (k < Hd) x[static_cast<long long>(warp) * Hd + k] = lnw[k] * ((v[i] - mean) * rstd) + lnb[k];
+    if (k < Hd) {
+      const float y = lnw[k] * ((v[i] - mean) * rstd) + lnb[k];
+      x[static_cast<long long>(warp) * Hd + k] = y;
+      if (op != nullptr) {   // the [lo | hi | hi] operand of the first layer's QKV GEMM (what split3_act_kernel would write)
+        const __nv_bfloat16 hi = __float2bfloat16(y), lo = __float2bfloat16(y - __bfloat162float(hi));
+        __nv_bfloat16* o = op + static_cast<long long>(warp) * 3 * Hd + k;
+        o[0] = lo; o[Hd] = hi; o[2 * Hd] = hi;
+      }
+    }
   }
 }
 
@@ -762,9 +771,9 @@ int trim_feats_launch(const float* x, const long long* mask, float* out, int B, 
 }
 
 int dec_embed_launch(const long long* tok, const float* word_emb, const float* pos_emb, const float* lnw, const float* lnb, int pos,
-                     float* x, int R, int Hd, cudaStream_t s) {
+                     float* x, __nv_bfloat16* op, int R, int Hd, cudaStream_t s) {
   if (Hd > 1024) return -7;
-  dec_embed_kernel<<<nblocks(R, 8), 256, 0, s>>>(tok, word_emb, pos_emb, lnw, lnb, pos, x, R, Hd);
+  dec_embed_kernel<<<nblocks(R, 8), 256, 0, s>>>(tok, word_emb, pos_emb, lnw, lnb, pos, x, op, R, Hd);
   return static_cast<int>(cudaGetLastError());
 }
 int dec_cache_append_launch(const float* qkv, float* kc, float* vc, int* row_idx, int pos, int R, int Tmax, int Hd, cudaStream_t s) {

@@ -46,7 +46,7 @@ int trim_feats_launch(const float* x, const long long* mask, float* out, int B, 
 // ---- caption decoder (clip4caption/modules/module_decoder.py:294-406, beam.py:70-123, train.py:547-599) ----------------
 // x[r,:] = TF_LN(word_emb[tok[r]] + pos_emb[pos]; w, b, 1e-12)                       (module_decoder.py:309-320)
 int dec_embed_launch(const long long* tok, const float* word_emb, const float* pos_emb, const float* lnw, const float* lnb, int pos,
-                     float* x, int R, int Hd, cudaStream_t s);
+                     float* x, __nv_bfloat16* op /* optional: [lo|hi|hi] split operand of x, [R, 3 Hd] */, int R, int Hd, cudaStream_t s);
 // append this step's self-attention key / value (columns [Hd,2Hd) / [2Hd,3Hd) of qkv) at position `pos` of the caches; with
 // row_idx (int [R, Tmax], may be null) also row_idx[r, pos] = r
 int dec_cache_append_launch(const float* qkv, float* kc, float* vc, int* row_idx, int pos, int R, int Tmax, int Hd, cudaStream_t s);
