@@ -7,6 +7,7 @@
 #include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 
+#include <array>
 #include <atomic>
 #include <cctype>
 #include <cmath>
@@ -1284,16 +1285,22 @@ struct HbDecoder {
   DevBuf skws;             // split-K partial sums [MAX_SPLITS, max rows, hidden] fp32
   DevBuf kv_idx[2];        // beam re-ordering as an index table int32 [R, max_words] (ping-pong), shared by all layers
   CUtensorMap tm_hd, tm_ffn, tm_enc;
-  // CUDA graphs of the decode steps, valid for one (n_inst, beam, enc_len) shape
-  std::vector<cudaGraphExec_t> graphs;
-  std::vector<int64_t> graph_launches;   // kernels per step graph (hb_launch_count stays the number of kernels run)
-  int g_n_inst = -1, g_beam = -1, g_enc_len = -1, searches_with_shape = 0;
+  // CUDA graphs of the decode steps, one set per (n_inst, beam, enc_len) shape: a job's full batches and its ragged last batch
+  // alternate, so the sets of the MAX_SHAPES most recently used shapes are kept
+  struct GraphSet {
+    std::vector<cudaGraphExec_t> exec;     // per step index
+    std::vector<int64_t> launches;         // kernels per step graph (hb_launch_count stays the number of kernels run)
+    int searches = 0;                      // searches begun with this shape before the current one
+    uint64_t last_use = 0;
+    void destroy() { for (auto& e : exec) if (e) { cudaGraphExecDestroy(e); e = nullptr; } }
+  };
+  static constexpr size_t MAX_SHAPES = 8;
+  std::map<std::array<int, 3>, GraphSet> graph_sets;
+  GraphSet* gs = nullptr;                  // the current search's set
+  uint64_t use_clock = 0;
   cudaStream_t cap_stream = nullptr;     // capture happens here: the caller's stream may be the legacy default stream, which cannot capture
-  void drop_graphs() {
-    for (auto& e : graphs) if (e) { cudaGraphExecDestroy(e); e = nullptr; }
-  }
   ~HbDecoder() {
-    drop_graphs();
+    for (auto& kv : graph_sets) kv.second.destroy();
     if (cap_stream) cudaStreamDestroy(cap_stream);
   }
 };
@@ -1461,11 +1468,23 @@ int hb_decoder_begin(HbDecoder* d, const float* enc, int n_inst, int enc_len, in
   if (n_inst <= 0 || n_inst > d->max_inst || beam <= 0 || beam > d->max_beam || enc_len <= 0 || enc_len > d->max_enc)
     return fail(HB_ERR_INVALID, "decoder batch (%d instances, beam %d, %d frames) exceeds the handle's capacity", n_inst, beam, enc_len);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (n_inst != d->g_n_inst || beam != d->g_beam || enc_len != d->g_enc_len) {
-    d->drop_graphs();
-    d->g_n_inst = n_inst; d->g_beam = beam; d->g_enc_len = enc_len; d->searches_with_shape = 0;
-  } else {
-    d->searches_with_shape += 1;
+  {
+    const std::array<int, 3> key{n_inst, beam, enc_len};
+    auto it = d->graph_sets.find(key);
+    if (it == d->graph_sets.end()) {
+      if (d->graph_sets.size() >= HbDecoder::MAX_SHAPES) {   // evict the least recently used shape
+        auto lru = d->graph_sets.begin();
+        for (auto j = d->graph_sets.begin(); j != d->graph_sets.end(); ++j)
+          if (j->second.last_use < lru->second.last_use) lru = j;
+        lru->second.destroy();
+        d->graph_sets.erase(lru);
+      }
+      it = d->graph_sets.emplace(key, HbDecoder::GraphSet()).first;
+    } else {
+      it->second.searches += 1;
+    }
+    it->second.last_use = ++d->use_clock;
+    d->gs = &it->second;   // std::map nodes are stable
   }
   d->n_inst = n_inst; d->beam = beam; d->enc_len = enc_len; d->step = 0; d->cur = 0;
   const int R = n_inst * beam, Hd = d->cfg.hidden;
@@ -1599,10 +1618,11 @@ int hb_decoder_step(HbDecoder* d, void* stream) {
   // CUDA graphs: the first search with a given (n_inst, beam, enc_len) runs eagerly (it also warms every lazily set kernel
   // attribute); from the second search on each step index is captured once and then replayed with one cudaGraphLaunch instead of
   // ~50 kernel launches (launch-bound: a step is ~0.85 ms of 15-us kernels).  Per-launch profiling bypasses the graphs.
-  const bool use_graph = g_decoder_graphs && !g_prof_on && d->searches_with_shape >= 1;
+  const bool use_graph = g_decoder_graphs && !g_prof_on && d->gs != nullptr && d->gs->searches >= 1;
   if (use_graph) {
-    if (d->graphs.size() != static_cast<size_t>(d->cfg.max_words)) d->graphs.assign(d->cfg.max_words, nullptr);
-    cudaGraphExec_t& exec = d->graphs[d->step];
+    HbDecoder::GraphSet& gs = *d->gs;
+    if (gs.exec.size() != static_cast<size_t>(d->cfg.max_words)) { gs.exec.assign(d->cfg.max_words, nullptr); gs.launches.assign(d->cfg.max_words, 0); }
+    cudaGraphExec_t& exec = gs.exec[d->step];
     if (exec == nullptr) {
       cudaGraph_t g = nullptr;
       const int64_t n0 = g_launches.load();
@@ -1610,8 +1630,7 @@ int hb_decoder_step(HbDecoder* d, void* stream) {
       if (!d->cap_stream) HB_CUDA(cudaStreamCreateWithFlags(&d->cap_stream, cudaStreamNonBlocking));
       HB_CUDA(cudaStreamBeginCapture(d->cap_stream, cudaStreamCaptureModeThreadLocal));
       r = decoder_step_launches(d, d->cap_stream);
-      if (d->graph_launches.size() != d->graphs.size()) d->graph_launches.assign(d->graphs.size(), 0);
-      d->graph_launches[d->step] = g_launches.exchange(n0) - n0;   // kernels recorded, not yet run: counted at every replay below
+      gs.launches[d->step] = g_launches.exchange(n0) - n0;   // kernels recorded, not yet run: counted at every replay below
       cudaError_t e = cudaStreamEndCapture(d->cap_stream, &g);
       if (r != HB_OK || e != cudaSuccess) {
         if (g) cudaGraphDestroy(g);
@@ -1623,7 +1642,7 @@ int hb_decoder_step(HbDecoder* d, void* stream) {
       if (e != cudaSuccess) { exec = nullptr; return fail(HB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
     }
     HB_CUDA(cudaGraphLaunch(exec, s));
-    g_launches.fetch_add(d->graph_launches[d->step], std::memory_order_relaxed);
+    g_launches.fetch_add(gs.launches[d->step], std::memory_order_relaxed);
   } else {
     r = decoder_step_launches(d, s);
     if (r != HB_OK) return r;

@@ -281,6 +281,46 @@ def test_decoder_graph_replay_and_kernel_variants_agree(hb, golden, tmp_path):
         _lib.debug_set("decoder_kv_index", 1)
 
 
+def test_decoder_graph_sets_survive_alternating_shapes(hb, golden, tmp_path):
+    """A job's full batches and its ragged last batch alternate between two (instances, beam, frames) shapes: each shape keeps its
+    own step graphs (no re-capture after the second search of a shape: the kernel count per search stays constant), more shapes than
+    the handle keeps evict the least recently used set, and every search still returns the reference's token ids."""
+    clip = FixedText()
+    sd = synthetic.make_moment_state_dict(seed=3)
+    bias = sd["clip4cap_model.decoder.classifier.cls.predictions.bias"].clone()
+    bias[102] += 2.0
+    sd["clip4cap_model.decoder.classifier.cls.predictions.bias"] = bias
+    b = synthetic.make_moment_batch(4, 40, seed=7)
+    b["tasks"] = ["step_captioning"] * 4
+    g = golden["caption_eos"]
+    m = moment.MomentModel(-1, 384, moment.default_args(bert_vocab_path=_write_vocab(tmp_path)), clip_model=clip, max_rows=1024, max_batch=8)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV)
+
+    def search(n):
+        sub = {k: (v[:n] if torch.is_tensor(v) or isinstance(v, list) else v) for k, v in b.items()}
+        clip.feat = b["text_feat"][:n]
+        n0 = hb.hb_launch_count()
+        ids = m.test_step(sub, num_beams=3)["token_ids"]
+        assert ids == g["ids"][:n], n
+        return hb.hb_launch_count() - n0
+
+    counts = {4: [], 3: []}
+    for _ in range(3):
+        for n in (4, 3):
+            counts[n].append(search(n))
+    assert len(set(counts[4])) == 1 and len(set(counts[3])) == 1, counts
+    # more shapes than a handle keeps (8): beam widths 1..5 x two batch sizes, twice over, then the first shapes again
+    for _ in range(2):
+        for beam in (1, 2, 4, 5):
+            for n in (1, 2, 4):
+                sub = {k: (v[:n] if torch.is_tensor(v) or isinstance(v, list) else v) for k, v in b.items()}
+                clip.feat = b["text_feat"][:n]
+                ids = m.test_step(sub, num_beams=beam)["token_ids"]
+                assert len(ids) == n
+    assert search(4) == counts[4][0] and search(3) == counts[3][0]
+
+
 def test_config4_size_determinism_and_oracle_subset(hb):
     """BASELINE configs[3] size (64 clips x 300 frames): two runs are bit-identical, each clip's result is independent of the batch
     it is in, and the first two clips match the CPU oracle's moment-retrieval prediction."""
