@@ -57,17 +57,34 @@ def all_gather_objects(obj, group=None) -> list:
     return out
 
 
-def _run_sharded(items: List[dict], run_batch, batch_size: int, rank: int, world: int, gather) -> List:
+def _run_sharded(items: List[dict], run_batch, batch_size: int, rank: int, world: int, gather, prepare=None, prefetch: bool = True) -> List:
     """Run `run_batch(chunk) -> list of per-item results` over this rank's items, gather every rank's (index, result) pairs and
     return the per-item results in ITEM order (padding duplicates dropped).  (The reference extends the gathered lists in rank
     order, run.py:645-662, which is equivalent for its dictionaries keyed by video and wrong for the caption lists; item order
-    is what the single-process run produces.)"""
+    is what the single-process run produces.)
+
+    With ``prepare`` the work of a chunk is split into ``prepare(chunk) -> batch`` (host collate + host-to-device copies) and
+    ``run_batch(batch)`` (the model call): one worker thread prepares chunk i + 1 while the model runs chunk i — what the
+    reference's ``DataLoader(num_workers=..., pin_memory=True)`` does with processes (hirest_dataset.py:620-630).  Results do not depend on it."""
     mine = shard_indices(len(items), rank, world)
+    chunks = [mine[c0:c0 + batch_size] for c0 in range(0, len(mine), batch_size)]
     local = []
-    for c0 in range(0, len(mine), batch_size):
-        ids = mine[c0:c0 + batch_size]
-        res = run_batch([items[i] for i in ids])
-        local += list(zip(ids, res))
+    if prepare is None:
+        for ids in chunks:
+            local += list(zip(ids, run_batch([items[i] for i in ids])))
+    elif not prefetch:
+        for ids in chunks:
+            local += list(zip(ids, run_batch(prepare([items[i] for i in ids]))))
+    elif chunks:
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            fut = pool.submit(prepare, [items[i] for i in chunks[0]])
+            for k, ids in enumerate(chunks):
+                batch = fut.result()
+                if k + 1 < len(chunks):
+                    fut = pool.submit(prepare, [items[i] for i in chunks[k + 1]])
+                local += list(zip(ids, run_batch(batch)))
     merged = {}
     for part in gather(local):
         for i, r in part:
@@ -77,7 +94,7 @@ def _run_sharded(items: List[dict], run_batch, batch_size: int, rank: int, world
 
 def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beams: int = 5, n_model_frames: int = -1,
                    tokenize=None, rank: int = 0, world: int = 1, group=None, gather=None,
-                   caption_batch_size: Optional[int] = None) -> Dict:
+                   caption_batch_size: Optional[int] = None, prefetch: bool = True) -> Dict:
     """Chain the three tasks over ``videos`` (dicts with ``prompt``, ``fname``, ``video_duration``, ``vis_feats [T,1024]``,
     ``asr_feats [T,384]``, ``clip_text_ids [77]``; order = dataset order).  Videos without ``clip_text_ids`` get them from
     ``tokenize(prompt) -> LongTensor[1, 77]`` (e.g. ``hirest_b200.tokenizer.tokenize``), as ``collate_fn`` does with
@@ -94,7 +111,10 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
     ``caption_batch_size`` (default: ``batch_size``) batches the step-captioning items separately: a step item is at most 20
     trimmed frames, and the 48 decode steps of a beam search are latency-bound, so several hundred steps per search cost little
     more than 64.  A caption does not depend on what else is in its batch (trimmed items carry no padding; every decoder kernel
-    computes a row from that row's inputs only), so this is a throughput knob, not a semantic one."""
+    computes a row from that row's inputs only), so this is a throughput knob, not a semantic one.
+
+    ``prefetch`` (default on): one worker thread collates the next batch and copies its features to the GPU on a side stream while
+    the model runs the current one (``_run_sharded``); off, every batch is prepared inline.  Same results either way."""
     nmf = n_model_frames
     if gather is None:
         gather = (lambda obj: all_gather_objects(obj, group)) if world > 1 else (lambda obj: [obj])
@@ -134,8 +154,13 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
                 # moment_mask == 1, in order), so the item carries just those rows with an all-ones mask instead of the whole video
                 # padded to the longest one in the batch: same trimmed tensor, ~30x fewer bytes collated and copied to the GPU.
                 rows = it["moment_mask"].nonzero(as_tuple=True)[0]
-                it.update(vis_feats=v["vis_feats"][rows], asr_feats=v["asr_feats"][rows],
-                          video_mask=torch.ones(rows.numel(), dtype=torch.long), moment_mask=torch.ones(rows.numel(), dtype=torch.long))
+                k = rows.numel()
+                if k > 0 and int(rows[-1]) - int(rows[0]) + 1 == k:   # a step is one run of frames (dataset :287-289): views, no copy
+                    r0 = int(rows[0])
+                    vis, asr = v["vis_feats"][r0:r0 + k], v["asr_feats"][r0:r0 + k]
+                else:
+                    vis, asr = v["vis_feats"][rows], v["asr_feats"][rows]
+                it.update(vis_feats=vis, asr_feats=asr, video_mask=torch.ones(k, dtype=torch.long), moment_mask=torch.ones(k, dtype=torch.long))
             else:
                 it.update(vis_feats=v["vis_feats"], asr_feats=v["asr_feats"])
             out.append(it)
@@ -154,24 +179,47 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
     except (AttributeError, StopIteration, TypeError):
         dev = None   # not a torch module (tests drive the glue with stand-ins): no device cache
 
-    def run_video_batch(chunk):
+    on_gpu = dev is not None and dev.type == "cuda"
+    side = torch.cuda.Stream(dev) if on_gpu else None   # the worker thread's copies run beside the model's kernels
+
+    def to_device(*tensors):
+        """Host-to-device copies on the side stream; the model's stream waits for them in `ready`."""
+        with torch.cuda.stream(side):
+            out = [t.to(dev, non_blocking=True) for t in tensors]
+            ev = torch.cuda.Event()
+            ev.record(side)
+        return out, ev
+
+    def ready(b):
+        ev = b.pop("_copied", None)
+        if ev is not None:
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(ev)
+            for k in ("vis_feats", "asr_feats"):
+                b[k].record_stream(cur)
+        return b
+
+    def prepare_video_batch(chunk):
         key = tuple(it["fname"] for it in chunk)
         hit = feat_cache.get(key)
         if hit is None:
             b = collate(chunk, nmf)
             nbytes = (b["vis_feats"].numel() + b["asr_feats"].numel()) * 4
-            if dev is not None and dev.type == "cuda" and nbytes <= cache_budget[0]:
+            if on_gpu and nbytes <= cache_budget[0]:
                 cache_budget[0] -= nbytes
-                b["vis_feats"], b["asr_feats"] = b["vis_feats"].to(dev), b["asr_feats"].to(dev)
+                (b["vis_feats"], b["asr_feats"]), b["_copied"] = to_device(b["vis_feats"], b["asr_feats"])
                 feat_cache[key] = {"vis_feats": b["vis_feats"], "asr_feats": b["asr_feats"]}
         else:   # masks and bounds from the items, features from the cache (placeholders keep collate's padding logic in one place)
             light = [dict(it, vis_feats=it["vis_feats"].new_empty((it["vis_feats"].shape[0], 0)),
                           asr_feats=it["asr_feats"].new_empty((it["asr_feats"].shape[0], 0))) for it in chunk]
             b = collate(light, nmf)
             b.update(hit)
-        return model.test_step(b)["prediction"]
+        return b
 
-    preds = _run_sharded(items, run_video_batch, batch_size, rank, world, gather)
+    def run_video_batch(b):
+        return model.test_step(ready(b))["prediction"]
+
+    preds = _run_sharded(items, run_video_batch, batch_size, rank, world, gather, prepare=prepare_video_batch, prefetch=prefetch)
     for it, (s, e) in zip(items, preds):
         d = it["video_duration"]
         mr.setdefault(it["prompt"], {})[it["fname"]] = {
@@ -187,7 +235,7 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
     items = with_features(build_items(annotations(lambda v: state[v["prompt"]][v["fname"]]["bounds"],
                                                   lambda v: state[v["prompt"]][v["fname"]]["steps"]), "moment_segmentation", nmf, end_to_end=True))
     ms: Dict[str, dict] = {}
-    preds = _run_sharded(items, run_video_batch, batch_size, rank, world, gather)
+    preds = _run_sharded(items, run_video_batch, batch_size, rank, world, gather, prepare=prepare_video_batch, prefetch=prefetch)
     feat_cache.clear()
     for it, raw in zip(items, preds):
         d = it["video_duration"]
@@ -204,8 +252,14 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
                                                   lambda v: state[v["prompt"]][v["fname"]]["steps"]), "step_captioning", nmf, end_to_end=True),
                           slice_to_moment=True)
     sc: Dict[str, dict] = {}
-    preds = _run_sharded(items, lambda chunk: model.test_step(collate(chunk, -1), num_beams=num_beams)["prediction"],   # ragged items: pad path
-                         caption_batch_size or batch_size, rank, world, gather)
+    def prepare_step_batch(chunk):
+        b = collate(chunk, -1)   # ragged items: pad path
+        if on_gpu:
+            (b["vis_feats"], b["asr_feats"]), b["_copied"] = to_device(b["vis_feats"], b["asr_feats"])
+        return b
+
+    preds = _run_sharded(items, lambda b: model.test_step(ready(b), num_beams=num_beams)["prediction"],
+                         caption_batch_size or batch_size, rank, world, gather, prepare=prepare_step_batch, prefetch=prefetch)
     for it, sent in zip(items, preds):
         e = sc.setdefault(it["fname"], {"captions": []})
         e["captions"].append({"sentence": sent})

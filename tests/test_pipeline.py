@@ -122,6 +122,54 @@ def test_end_to_end_chain_matches_reference_flow(hb, tmp_path):
     m2 = moment.MomentModel(-1, 384, moment.default_args(bert_vocab_path=vocab_path), clip_model=TableText(table), max_rows=4 * 96, max_batch=64)
     m2.load_state_dict(sd, strict=True)
     assert pipeline.run_end_to_end(m2.to(dev), videos, batch_size=4, num_beams=3, caption_batch_size=64) == got
+    # ... nor on whether the next batch is collated and copied by the worker thread (side stream) or inline
+    assert pipeline.run_end_to_end(m, videos, batch_size=4, num_beams=3, prefetch=False) == got
+
+
+def test_prefetch_thread_changes_nothing_and_propagates_errors():
+    """The worker thread that prepares batch i + 1 while the model runs batch i: same dictionaries as inline preparation, batches
+    reach the model in order, and an exception raised while preparing a batch surfaces in the caller."""
+    g = torch.Generator().manual_seed(3)
+    vids = [{"prompt": f"p{i % 3}", "fname": f"v{i}", "video_duration": 30 + i, "vis_feats": torch.randn(30 + i, 8, generator=g),
+             "asr_feats": torch.randn(30 + i, 4, generator=g), "clip_text_ids": torch.zeros(77, dtype=torch.long)} for i in range(11)]
+
+    class Fake:
+        def __init__(self):
+            self.seen = []
+
+        def test_step(self, b, **kw):
+            task, B = b["tasks"][0], b["vis_feats"].shape[0]
+            self.seen.append((task, tuple(b["video_fnames"])))
+            if task == "moment_retrieval":
+                return {"prediction": [[int(n) // 6, int(n) - 3] for n in b["vis_mask"].sum(1)]}
+            if task == "moment_segmentation":
+                out = []
+                for i in range(B):
+                    idx = b["moment_mask"][i].nonzero()[:, 0]
+                    out.append(list(range(int(idx[0]), int(idx[-1]), 7)) + [int(idx[-1])])
+                return {"prediction": out}
+            return {"prediction": [f"c{float(b['vis_feats'][i].sum()):.4f}" for i in range(B)]}
+
+    a, b = Fake(), Fake()
+    ra = pipeline.run_end_to_end(a, vids, batch_size=4, num_beams=3, caption_batch_size=5, prefetch=True)
+    rb = pipeline.run_end_to_end(b, vids, batch_size=4, num_beams=3, caption_batch_size=5, prefetch=False)
+    assert ra == rb and a.seen == b.seen and len(a.seen) >= 3 + 3 + 2
+
+    bad = [dict(v) for v in vids]
+    bad[8]["vis_feats"] = torch.zeros(bad[8]["vis_feats"].shape[0], 9)   # third batch (items are grouped by prompt): collate fails inside the worker thread
+    c = Fake()
+    with pytest.raises(RuntimeError):
+        pipeline.run_end_to_end(c, bad, batch_size=4, prefetch=True)
+    assert len(c.seen) == 2   # the two good batches ran before the error surfaced
+
+    class Boom(Fake):
+        def test_step(self, b, **kw):
+            if len(self.seen) == 1:
+                raise RuntimeError("model failed")
+            return super().test_step(b, **kw)
+
+    with pytest.raises(RuntimeError, match="model failed"):   # the pending prepared batch is dropped, the pool shuts down
+        pipeline.run_end_to_end(Boom(), vids, batch_size=4, prefetch=True)
 
 
 def test_prompts_are_tokenized_when_ids_are_missing():

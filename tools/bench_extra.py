@@ -322,7 +322,7 @@ def _e2e(args, cfg, model_name, ctx):
 
     def job(vs, batch_size=bs):
         return pipeline.run_end_to_end(model, vs, batch_size=batch_size, num_beams=args.beam, rank=rank, world=world,
-                                       caption_batch_size=cbs)
+                                       caption_batch_size=cbs, prefetch=os.environ.get("HB_CHAIN_PREFETCH", "1") != "0")
 
     ms, clocks, out, launches = _timed(ctx, lambda: job(videos), args.steps, lambda: job(videos[:bs]), 1)
     value = n * args.steps / (ms * 1e-3)

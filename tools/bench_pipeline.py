@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--cpu-videos", type=int, default=2)
     ap.add_argument("--caption-batch", type=int, default=0, help="step items per beam search (0 = --batch)")
     ap.add_argument("--profile", action="store_true", help="cProfile of the timed job (host side), top functions to stderr")
+    ap.add_argument("--ab", type=int, default=0, help="A/B of the prefetch thread: N alternating pairs of whole jobs (inline, prefetch), seconds each")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(17)
@@ -74,6 +75,20 @@ def main():
     # warm-up: the whole job once (engine / decoder builds for every batch shape, CUDA-graph capture of the decode steps)
     pipeline.run_end_to_end(m, videos, batch_size=a.batch, num_beams=a.beam, caption_batch_size=a.caption_batch or None)
     torch.cuda.synchronize()
+    if a.ab > 0:
+        pairs = []
+        for _ in range(a.ab):
+            row = []
+            for pf in (False, True):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                pipeline.run_end_to_end(m, videos, batch_size=a.batch, num_beams=a.beam, caption_batch_size=a.caption_batch or None, prefetch=pf)
+                torch.cuda.synchronize()
+                row.append(round(time.perf_counter() - t0, 4))
+            pairs.append(row)
+        print(json.dumps({"op": "pipeline.run_end_to_end, prefetch thread A/B", "videos": a.videos, "seconds_inline_prefetch": pairs,
+                          "median_inline": sorted(r[0] for r in pairs)[len(pairs) // 2], "median_prefetch": sorted(r[1] for r in pairs)[len(pairs) // 2]}))
+        return
     stage = {}
     orig = m.test_step
 
