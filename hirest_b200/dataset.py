@@ -113,9 +113,11 @@ def build_items(annotations: Dict[str, Dict[str, dict]], task: str, n_model_fram
     return items
 
 
-def collate(items: Sequence[dict], n_model_frames: int = -1, tokenize: Optional[Callable] = None) -> dict:
+def collate(items: Sequence[dict], n_model_frames: int = -1, tokenize: Optional[Callable] = None, feature_alloc: Optional[Callable] = None) -> dict:
     """``collate_fn`` (hirest_dataset.py:409-531): stack (fixed frame count) or zero-pad every per-frame tensor to the longest video of
-    the batch; lists for the rest; ``clip_text_ids`` from the items if present, else ``tokenize(prompts)`` (``clip.tokenize``, :528)."""
+    the batch; lists for the rest; ``clip_text_ids`` from the items if present, else ``tokenize(prompts)`` (``clip.tokenize``, :528).
+    ``feature_alloc(shape, dtype) -> uninitialised tensor`` supplies the storage of the two feature batches (e.g. pinned host memory,
+    what the reference's ``DataLoader(pin_memory=True)`` produces, :624); their padding is then zero-filled explicitly."""
     out: dict = {}
     if "target_text" in items[0]:
         out["target_text"] = [d["target_text"] for d in items]
@@ -126,17 +128,26 @@ def collate(items: Sequence[dict], n_model_frames: int = -1, tokenize: Optional[
         # same tensors without 4 allocations per item — collating 64 x 600-frame videos is 150 MB of copies either way)
         max_len = items[0]["vis_feats"].shape[0] if n_model_frames > 0 else max(d["vis_feats"].shape[0] for d in items)
 
-        def pad_stack(key, dtype):
+        def pad_stack(key, dtype, alloc=None):
             first = items[0][key]
-            out_t = torch.zeros((len(items), max_len) + tuple(first.shape[1:]), dtype=dtype, device=first.device)
+            shape = (len(items), max_len) + tuple(first.shape[1:])
+            # (torch.zeros of a large host tensor maps untouched zero pages, so "zero everything, then copy the rows" writes each
+            # byte once; storage from `alloc` is recycled memory and gets its padding — or, for short items, all of it — cleared)
+            out_t = torch.zeros(shape, dtype=dtype, device=first.device) if alloc is None else alloc(shape, dtype)
+            tails = alloc is not None and max_len * int(first[0].numel() if first.shape[0] else 1) >= (64 << 10)
+            if alloc is not None and not tails:
+                out_t.zero_()
             for i, d in enumerate(items):
                 x = d[key]
-                if n_model_frames > 0 and x.shape[0] != max_len:
-                    raise RuntimeError(f"stack expects each tensor to be equal size, but got {x.shape[0]} and {max_len} rows ({key})")
-                out_t[i, :x.shape[0]] = x
+                n = x.shape[0]
+                if n_model_frames > 0 and n != max_len:
+                    raise RuntimeError(f"stack expects each tensor to be equal size, but got {n} and {max_len} rows ({key})")
+                out_t[i, :n] = x
+                if tails and n < max_len:
+                    out_t[i, n:].zero_()
             return out_t
 
-        out["vis_feats"] = pad_stack("vis_feats", torch.float32)
+        out["vis_feats"] = pad_stack("vis_feats", torch.float32, feature_alloc)
         out["vis_mask"] = pad_stack("video_mask", torch.int64)
         out["moment_mask"] = pad_stack("moment_mask", torch.int64)
         for k in ("moment_retrieval_start_target", "moment_retrieval_end_target"):
@@ -145,7 +156,7 @@ def collate(items: Sequence[dict], n_model_frames: int = -1, tokenize: Optional[
         if "prev_boundary_mask" in items[0]:
             out["prev_boundary_mask"] = pad_stack("prev_boundary_mask", torch.int64)
         if "asr_feats" in items[0]:
-            out["asr_feats"] = pad_stack("asr_feats", torch.float32)
+            out["asr_feats"] = pad_stack("asr_feats", torch.float32, feature_alloc)
     if "moment_segmentation_target" in items[0]:
         out["moment_segmentation_target"] = torch.LongTensor([d["moment_segmentation_target"] for d in items])
     for k in ("moment_bound_timestamps", "moment_bound_frames"):

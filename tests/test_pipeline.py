@@ -126,6 +126,24 @@ def test_end_to_end_chain_matches_reference_flow(hb, tmp_path):
     assert pipeline.run_end_to_end(m, videos, batch_size=4, num_beams=3, prefetch=False) == got
 
 
+def test_collate_into_supplied_storage_clears_the_padding():
+    """feature_alloc (pinned host memory on the GPU path) hands out recycled, uninitialised storage: long items get their padding
+    cleared row by row, short ones the whole batch — either way the batch equals the default zero-padded one."""
+    g = torch.Generator().manual_seed(5)
+
+    def dirty(shape, dtype):
+        return torch.full(shape, float("nan"), dtype=dtype)
+
+    for rows, width in ((range(3, 9), 16), ((40, 70, 55), 2048)):   # short items / items past the per-row clearing threshold
+        items = [{"fname": f"v{i}", "prompt": "p", "video_duration": n, "task": "moment_retrieval",
+                  "vis_feats": torch.randn(n, width, generator=g), "asr_feats": torch.randn(n, 8, generator=g),
+                  "video_mask": torch.ones(n, dtype=torch.long), "moment_mask": torch.ones(n, dtype=torch.long),
+                  "clip_text_ids": torch.zeros(77, dtype=torch.long)} for i, n in enumerate(rows)]
+        a, b = pipeline.collate(items), pipeline.collate(items, feature_alloc=dirty)
+        for k in ("vis_feats", "asr_feats", "vis_mask", "moment_mask"):
+            assert torch.equal(a[k], b[k]), k
+
+
 def test_prefetch_thread_changes_nothing_and_propagates_errors():
     """The worker thread that prepares batch i + 1 while the model runs batch i: same dictionaries as inline preparation, batches
     reach the model in order, and an exception raised while preparing a batch surfaces in the caller."""
