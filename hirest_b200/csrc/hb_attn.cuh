@@ -72,5 +72,6 @@ int small_attn_f32_launch(const SmallAttnF32Params& p, cudaStream_t stream);
 // workspace is too small.
 size_t small_attn_tc_workspace(int B, int H, int Tq, int Tk);
 int small_attn_tc_launch(const SmallAttnF32Params& p, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+void small_attn_tc_set_version(int v);   // 2 (default): two CTAs per SM, [hi | lo] operand images; 1: one CTA per SM, double-buffered
 
 }  // namespace hb

@@ -81,8 +81,11 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 // ---- prologue: fp32 q / k / v -> bf16 split operands -----------------------------------------------------------------------
 //   Qs [B*Tq, H, 192] = [lo | hi | hi]   Ks [B*Tk, H, 192] = [hi | lo | hi]   Vh / Vl [B*Tk, H, 64] = hi / lo
+//   PAIR (kernel v2): Qs / Ks [rows, H, 128] = [hi | lo] — the three product terms pick their slabs through the UMMA descriptors
+template <bool PAIR>
 __global__ void __launch_bounds__(256) attn_split_kernel(const SmallAttnF32Params p, __nv_bfloat16* __restrict__ qs, __nv_bfloat16* __restrict__ ks,
                                                          __nv_bfloat16* __restrict__ vh, __nv_bfloat16* __restrict__ vl) {
+  constexpr int W = PAIR ? 128 : 192;
   const long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;   // one thread per (row, head, 4 dims)
   const long long nq = static_cast<long long>(p.B) * p.Tq * p.H * (DH / 4);
   const long long nk = static_cast<long long>(p.B) * p.Tk * p.H * (DH / 4);
@@ -101,10 +104,15 @@ __global__ void __launch_bounds__(256) attn_split_kernel(const SmallAttnF32Param
     const float4 x = *reinterpret_cast<const float4*>(p.q + b * p.bsq + i * p.ldq + h * DH + d4 * 4);
     uint2 hi, lo;
     split4(x, hi, lo);
-    uint2* dst = reinterpret_cast<uint2*>(qs + (row * p.H + h) * 192 + d4 * 4);
-    dst[0] = lo;
-    dst[16] = hi;    // + 64 bf16
-    dst[32] = hi;    // + 128 bf16
+    uint2* dst = reinterpret_cast<uint2*>(qs + (row * p.H + h) * W + d4 * 4);
+    if constexpr (PAIR) {
+      dst[0] = hi;
+      dst[16] = lo;    // + 64 bf16
+    } else {
+      dst[0] = lo;
+      dst[16] = hi;
+      dst[32] = hi;    // + 128 bf16
+    }
   }
   if (t < nk) {
     const int d4 = static_cast<int>(t % (DH / 4));
@@ -115,10 +123,10 @@ __global__ void __launch_bounds__(256) attn_split_kernel(const SmallAttnF32Param
     const float4 xv = *reinterpret_cast<const float4*>(p.v + b * p.bsv + i * p.ldv + h * DH + d4 * 4);
     uint2 hi, lo;
     split4(xk, hi, lo);
-    uint2* dk = reinterpret_cast<uint2*>(ks + (row * p.H + h) * 192 + d4 * 4);
+    uint2* dk = reinterpret_cast<uint2*>(ks + (row * p.H + h) * W + d4 * 4);
     dk[0] = hi;
     dk[16] = lo;
-    dk[32] = hi;
+    if constexpr (!PAIR) dk[32] = hi;
     split4(xv, hi, lo);
     *reinterpret_cast<uint2*>(vh + (row * p.H + h) * DH + d4 * 4) = hi;
     *reinterpret_cast<uint2*>(vl + (row * p.H + h) * DH + d4 * 4) = lo;
@@ -338,6 +346,226 @@ __global__ void __launch_bounds__(TC_THREADS, 1) small_attn_tc_kernel(const __gr
   if (warp == 8) tmem_dealloc<1>(tmem_base, 512);
 }
 
+// ---- main kernel, v2 (default): two CTAs per SM -------------------------------------------------------------------------------
+// v1 keeps one CTA per SM (208 KiB of smem, all 512 TMEM columns), so a CTA's prologue (barrier init, TMEM allocation, first TMA
+// round trip), its serial S -> softmax -> P.V chain over only ceil(Tk / 128) key tiles and its epilogue are all exposed: 15.6 us
+// per CTA at 64 x 300 tokens for ~5 us of tensor + MUFU work.  v2 shrinks a CTA to 97 KiB and 256 TMEM columns so that two are
+// resident and fill each other's bubbles:
+//   * Q / K are staged as [hi | lo] (2 slabs instead of the 3-slab [lo|hi|hi] / [hi|lo|hi] images): the three product terms are
+//     formed by pointing the A / B descriptors at (q_lo, k_hi), (q_hi, k_lo), (q_hi, k_hi) — same MMAs, same accumulation order,
+//     bit-identical S; a third less operand traffic;
+//   * K and V are single-buffered with separate full / free barriers: K(j+1) is fetched as soon as S(j) has been computed (during
+//     tile j's softmax), V(j+1) as soon as P.V(j) has; S is single-buffered in TMEM (S(j+1) is issued behind P.V(j) on the in-order
+//     tensor pipe, so it cannot overwrite P(j) early).
+constexpr uint32_t Q2_OFF = 0;                 // 2 slabs: hi | lo
+constexpr uint32_t K2_OFF = 2 * SLAB;          // 2 slabs: hi | lo
+constexpr uint32_t V2_OFF = 4 * SLAB;          // V_hi | V_lo
+constexpr uint32_t XM2_OFF = 6 * SLAB;
+constexpr uint32_t BAR2_OFF = XM2_OFF + 1024;
+constexpr uint32_t TC2_SMEM = BAR2_OFF + 256 + 1024;
+enum { C_Q = 0, C_K_FULL, C_K_FREE, C_V_FULL, C_V_FREE, C_S, C_P, C_O, C_N };
+
+__global__ void __launch_bounds__(TC_THREADS, 2) small_attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                                       const __grid_constant__ CUtensorMap tmVh,
+                                                                       const __grid_constant__ CUtensorMap tmVl, const SmallAttnF32Params p,
+                                                                       int q_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t sbase = smem_u32(smem);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR2_OFF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C_N + 1);
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+  const int qt = blockIdx.x % q_tiles;
+  const int bh = blockIdx.x / q_tiles;
+  const int b = bh / p.H, h = bh - b * p.H;
+  const int q0 = qt * 128;
+  int n_kt = (p.Tk + 127) / 128;
+  if (p.mask_mode == 1) n_kt = min(n_kt, (min(p.Tq, q0 + 128) + 127) / 128);   // hard causal: no key beyond the tile's last query
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int i = 0; i < C_N; ++i) mbar_init(bars + i, i == C_P ? 8 : 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<1>(tmem_slot, 256);   // S / P [0, 128), O [128, 192): two CTAs share the SM's 512 columns
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 9) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bars + C_Q, 2 * SLAB);
+      for (int s = 0; s < 2; ++s) tma_load_3d(smem + Q2_OFF + s * SLAB, &tmQ, bars + C_Q, s * 64, h, b * p.Tq + q0);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_kt; ++j) {
+      const int krow = (b / p.kv_div) * p.Tk + j * 128;
+      if (j >= 1) mbar_wait(bars + C_K_FREE, (j - 1) & 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bars + C_K_FULL, 2 * SLAB);
+        for (int s = 0; s < 2; ++s) tma_load_3d(smem + K2_OFF + s * SLAB, &tmK, bars + C_K_FULL, s * 64, h, krow);
+      }
+      __syncwarp();
+      if (j >= 1) mbar_wait(bars + C_V_FREE, (j - 1) & 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(bars + C_V_FULL, 2 * SLAB);
+        tma_load_3d(smem + V2_OFF, &tmVh, bars + C_V_FULL, 0, h, krow);
+        tma_load_3d(smem + V2_OFF + SLAB, &tmVl, bars + C_V_FULL, 0, h, krow);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 8) {
+    // ------------------------------------------------------------------ MMA issue (whole warp walks, one elected lane issues)
+    const uint32_t sb = __shfl_sync(0xffffffffu, sbase, 0);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t idesc_s = umma_idesc_bf16(128, 128);
+    const uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);   // B (= V) MN-major
+    auto issue_s = [&](int j) {
+      mbar_wait(bars + C_K_FULL, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 12; ++ks) {   // terms in v1's order: q_lo.k_hi, q_hi.k_lo, q_hi.k_hi (slab 0 = hi, slab 1 = lo)
+          const int term = ks >> 2;
+          const uint32_t q_slab = (term == 0) ? 1u : 0u, k_slab = (term == 1) ? 1u : 0u;
+          const uint64_t ad = umma_desc_sw128(sb + Q2_OFF + q_slab * SLAB + (ks & 3) * 32);
+          const uint64_t bd = umma_desc_sw128(sb + K2_OFF + k_slab * SLAB + (ks & 3) * 32);
+          umma_bf16<1>(tb, ad, bd, idesc_s, ks > 0 ? 1u : 0u);
+        }
+        umma_commit<1>(bars + C_S);
+        umma_commit<1>(bars + C_K_FREE);
+      }
+      __syncwarp();
+    };
+    mbar_wait(bars + C_Q, 0);
+    issue_s(0);
+    for (int j = 0; j < n_kt; ++j) {
+      mbar_wait(bars + C_P, j & 1);
+      mbar_wait(bars + C_V_FULL, j & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t vhb = sb + V2_OFF, vlb = vhb + SLAB;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {   // 16 keys per step; P chunk c = ks / 2: hi at [32c, 32c+16), lo at [32c+16, 32c+32)
+          const uint32_t a_hi = tb + (ks >> 1) * 32 + (ks & 1) * 8, a_lo = a_hi + 16;
+          const uint64_t b_hi = desc_sw128_mn(vhb + ks * 2048, SLAB), b_lo = desc_sw128_mn(vlb + ks * 2048, SLAB);
+          umma_bf16_ts(tb + 128, a_lo, b_hi, idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+          umma_bf16_ts(tb + 128, a_hi, b_lo, idesc_o, 1u);
+          umma_bf16_ts(tb + 128, a_hi, b_hi, idesc_o, 1u);
+        }
+        umma_commit<1>(bars + C_O);
+        umma_commit<1>(bars + C_V_FREE);
+      }
+      __syncwarp();
+      if (j + 1 < n_kt) issue_s(j + 1);   // behind P.V(j) on the in-order tensor pipe: P(j) is consumed before S(j+1) lands on it
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax: two threads per query row (as v1)
+    const int hf = warp >> 2;           // keys [64 hf, 64 hf + 64) of every tile; O columns [32 hf, 32 hf + 32)
+    const int r = (warp & 3) * 32 + lane;
+    const int i = q0 + r;               // query index inside the sequence
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t t_s = t_row + hf * 64, t_o = t_row + 128 + hf * 32;
+    float* xm = reinterpret_cast<float*>(smem + XM2_OFF);
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_kt; ++j) {
+      const int key0 = j * 128 + hf * 64;
+      mbar_wait(bars + C_S, j & 1);
+      tc_fence_after();
+      auto logit2 = [&](uint32_t raw, int key) -> float {   // see v1
+        float s = __uint_as_float(raw) * p.scale;
+        if (p.mask_mode == 2) {
+          s = s + p.mask_const;
+          if (p.causal_soft && key > i) s = s + (-10000.0f);
+        }
+        if (key >= p.Tk || (p.mask_mode == 1 && key > i)) s = -INFINITY;
+        return s;
+      };
+      float tmax = -INFINITY;
+      {
+        uint32_t v[32];
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld_32x32(t_s + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 32; ++k) tmax = fmaxf(tmax, logit2(v[k], key0 + c * 32 + k));
+        }
+      }
+      xm[hf * 128 + r] = tmax;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      tmax = fmaxf(tmax, xm[(hf ^ 1) * 128 + r]);
+      const float m_new = fmaxf(m_run, tmax);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      float alpha;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(alpha) : "f"((m_run - m_use) * LOG2E));
+      if (j > 0) {
+        mbar_wait(bars + C_O, (j - 1) & 1);
+        tc_fence_after();
+        uint32_t o[32];
+        tmem_ld_32x32(t_o, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+        tmem_st_32x32(t_o, o);
+      }
+      float tsum = 0.f;
+      {
+        uint32_t v[32];
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld_32x32(t_s + c * 32, v);
+          tmem_ld_wait();
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            float p0, p1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"((logit2(v[2 * k], key0 + c * 32 + 2 * k) - m_use) * LOG2E));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"((logit2(v[2 * k + 1], key0 + c * 32 + 2 * k + 1) - m_use) * LOG2E));
+            tsum += p0 + p1;
+            const __nv_bfloat16 h0 = __float2bfloat16(p0), h1 = __float2bfloat16(p1);
+            hi[k] = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
+            lo[k] = pack_bf16x2(p0 - __bfloat162float(h0), p1 - __bfloat162float(h1));
+          }
+          tmem_st_32x16(t_s + c * 32, hi);
+          tmem_st_32x16(t_s + c * 32 + 16, lo);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + C_P);
+      l_run = l_run * alpha + tsum;
+      m_run = m_new;
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // both halves have read xm before the next tile overwrites it
+    }
+    xm[hf * 128 + r] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float inv = 1.0f / (l_run + xm[(hf ^ 1) * 128 + r]);
+    mbar_wait(bars + C_O, (n_kt - 1) & 1);
+    tc_fence_after();
+    float* og = p.out + static_cast<long long>(b) * p.bso + static_cast<long long>(i) * p.ldo + h * DH + hf * 32;
+    uint32_t o[32];
+    tmem_ld_32x32(t_o, o);
+    tmem_ld_wait();
+    if (i < p.Tq) {
+#pragma unroll
+      for (int k = 0; k < 32; k += 4)
+        *reinterpret_cast<float4*>(og + k) = make_float4(__uint_as_float(o[k]) * inv, __uint_as_float(o[k + 1]) * inv,
+                                                         __uint_as_float(o[k + 2]) * inv, __uint_as_float(o[k + 3]) * inv);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 8) tmem_dealloc<1>(tmem_base, 256);
+}
+
 }  // namespace
 
 size_t small_attn_tc_workspace(int B, int H, int Tq, int Tk) {
@@ -345,45 +573,53 @@ size_t small_attn_tc_workspace(int B, int H, int Tq, int Tk) {
   return (rq * 192 + rk * 192 + rk * 64 * 2) * 2 + 4 * 256;
 }
 
+namespace { int g_tc_version = 2; }
+void small_attn_tc_set_version(int v) { g_tc_version = (v == 1) ? 1 : 2; }
+
 int small_attn_tc_launch(const SmallAttnF32Params& p, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   if (p.B <= 0 || p.H <= 0 || p.Tq <= 0 || p.Tk <= 0) return -3;
   if (p.kv_div != 1) return -7;   // shared K / V across beams: decode steps (Tq = 1) stay on the CUDA-core kernel
   if ((p.ldq | p.ldk | p.ldv | p.ldo) % 4 || (p.bsq | p.bsk | p.bsv | p.bso) % 4) return -7;
   if (workspace == nullptr || workspace_bytes < small_attn_tc_workspace(p.B, p.H, p.Tq, p.Tk)) return -8;
+  const bool v2 = g_tc_version == 2;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(small_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(small_attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
   const size_t rq = static_cast<size_t>(p.B) * p.Tq, rk = static_cast<size_t>(p.B) * p.Tk;
+  const size_t W = v2 ? 128 : 192;   // bf16 per (row, head) of the Q / K images (the workspace is sized for the wider one)
   auto align256 = [](size_t x) { return (x + 255) / 256 * 256; };
   uint8_t* w = static_cast<uint8_t*>(workspace);
   __nv_bfloat16* qs = reinterpret_cast<__nv_bfloat16*>(w);
-  w += align256(rq * p.H * 192 * 2);
+  w += align256(rq * p.H * W * 2);
   __nv_bfloat16* ks = reinterpret_cast<__nv_bfloat16*>(w);
-  w += align256(rk * p.H * 192 * 2);
+  w += align256(rk * p.H * W * 2);
   __nv_bfloat16* vh = reinterpret_cast<__nv_bfloat16*>(w);
   w += align256(rk * p.H * 64 * 2);
   __nv_bfloat16* vl = reinterpret_cast<__nv_bfloat16*>(w);
   const long long nthreads = static_cast<long long>(rq > rk ? rq : rk) * p.H * (DH / 4);
-  attn_split_kernel<<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, stream>>>(p, qs, ks, vh, vl);
+  if (v2) attn_split_kernel<true><<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, stream>>>(p, qs, ks, vh, vl);
+  else attn_split_kernel<false><<<static_cast<unsigned>((nthreads + 255) / 256), 256, 0, stream>>>(p, qs, ks, vh, vl);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
   CUtensorMap tq, tk, tvh, tvl;
   const uint32_t box[3] = {64, 1, 128};
   {
-    const uint64_t dq[3] = {192, static_cast<uint64_t>(p.H), rq}, dk[3] = {192, static_cast<uint64_t>(p.H), rk};
-    const uint64_t s192[2] = {192 * 2, static_cast<uint64_t>(p.H) * 192 * 2};
+    const uint64_t dq[3] = {W, static_cast<uint64_t>(p.H), rq}, dk[3] = {W, static_cast<uint64_t>(p.H), rk};
+    const uint64_t sw[2] = {W * 2, static_cast<uint64_t>(p.H) * W * 2};
     const uint64_t dv[3] = {64, static_cast<uint64_t>(p.H), rk};
     const uint64_t s64[2] = {64 * 2, static_cast<uint64_t>(p.H) * 64 * 2};
-    if (int r = make_tmap_bf16_3d(&tq, qs, dq, s192, box)) return r;
-    if (int r = make_tmap_bf16_3d(&tk, ks, dk, s192, box)) return r;
+    if (int r = make_tmap_bf16_3d(&tq, qs, dq, sw, box)) return r;
+    if (int r = make_tmap_bf16_3d(&tk, ks, dk, sw, box)) return r;
     if (int r = make_tmap_bf16_3d(&tvh, vh, dv, s64, box)) return r;
     if (int r = make_tmap_bf16_3d(&tvl, vl, dv, s64, box)) return r;
   }
   const int q_tiles = (p.Tq + 127) / 128;
-  small_attn_tc_kernel<<<p.B * p.H * q_tiles, TC_THREADS, TC_SMEM, stream>>>(tq, tk, tvh, tvl, p, q_tiles);
+  if (v2) small_attn_tc2_kernel<<<p.B * p.H * q_tiles, TC_THREADS, TC2_SMEM, stream>>>(tq, tk, tvh, tvl, p, q_tiles);
+  else small_attn_tc_kernel<<<p.B * p.H * q_tiles, TC_THREADS, TC_SMEM, stream>>>(tq, tk, tvh, tvl, p, q_tiles);
   return static_cast<int>(cudaGetLastError());
 }
 

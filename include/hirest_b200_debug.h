@@ -15,8 +15,9 @@ extern "C" {
  * "gemm_cta_group"             1 | 2                 2         tcgen05 cta_group of the GEMMs (2 = CTA pairs, 256 x 256 tiles)
  * "attention_version"          1 | 2 | 3             3         ViT attention kernel: 3 persistent pipelined CTA per SM (hb_attn3.cu),
  *                                                              2 one CTA per 128-query tile (hb_attn2.cu), 1 one CTA per (frame, head)
- * "small_attention_tc"         0 | 1                 1         fp32 attention of the small sequence models on tensor cores (hb_attn_tc.cu)
- *                                                              instead of CUDA cores (hb_attn_small.cu); same results to ~1e-6
+ * "small_attention_tc"         0 | 1 | 2             2         fp32 attention of the small sequence models on tensor cores (hb_attn_tc.cu;
+ *                                                              2 = two CTAs per SM, 1 = the one-CTA-per-SM kernel, bit-identical results)
+ *                                                              instead of CUDA cores (hb_attn_small.cu, 0); same results to ~1e-6
  * "decoder_graphs"             0 | 1                 1         caption decoder: replay each decode step as a CUDA graph from the second
  *                                                              beam search of a (n_inst, beam, enc_len) shape on; same results
  * "decoder_split_k"            0 | k-blocks          6         caption decoder: the hidden-width linears of a decode step run as split-K GEMMs

@@ -199,6 +199,33 @@ def test_small_attention_f32(hb, tc, mode, Tq, Tk):
     assert r < (3e-4 if mask_mode == 2 else (2e-5 if tc else 2e-6))
 
 
+@pytest.mark.parametrize("mode,Tq,Tk", [("const", 300, 300), ("none", 130, 600), ("causal", 77, 77), ("const_causal", 257, 257), ("none", 16, 40)])
+def test_small_attention_tc_versions_are_bit_identical(hb, mode, Tq, Tk):
+    """The two-CTAs-per-SM kernel (default; [hi | lo] operand images, single-buffered K / V / S) issues the same MMAs in the same
+    order as the one-CTA-per-SM kernel: identical bits, also with every SM holding two CTAs (B x H x query tiles >> 148)."""
+    torch.manual_seed(Tq + Tk)
+    B, H = 16, 12
+    W = H * 64
+    qkv = torch.randn(B, max(Tq, Tk), 3 * W, device=DEV)
+    q, k, v = qkv[:, :Tq, :W], qkv[:, :Tk, W:2 * W], qkv[:, :Tk, 2 * W:]
+    mask_mode = {"none": 0, "causal": 1, "const": 2, "const_causal": 2}[mode]
+    ld, bs = 3 * W, max(Tq, Tk) * 3 * W
+    outs = []
+    try:
+        for version in (1, 2, 2):
+            _lib.debug_set("small_attention_tc", version)
+            out = torch.full((B, Tq, W), float("nan"), device=DEV)
+            _lib.check(hb.hb_small_attention_f32(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, Tq, Tk, ld, ld, ld, W,
+                                                 bs, bs, bs, Tq * W, 0.125, mask_mode, -10000.0 if mask_mode == 2 else 0.0,
+                                                 1 if mode == "const_causal" else 0, 1, _lib.stream_ptr()))
+            torch.cuda.synchronize()
+            outs.append(out)
+    finally:
+        _lib.debug_set("small_attention_tc", 2)
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+
+
 def test_small_attention_rejects_long_sequences(hb):
     t = torch.zeros(1, 800, 64, device=DEV, dtype=torch.bfloat16)
     rc = hb.hb_small_attention(t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), 1, 1, 800, 800, 64, 64, 64, 64, 0, 0, 0, 0,
