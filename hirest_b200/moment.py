@@ -118,6 +118,8 @@ class MomentModel(nn.Module):
                 "EVA_CLIP_g_14", pretrained=getattr(self.args, "eva_clip_path", "./pretrained_weights/eva_clip_psz14.pt"))
         self.clip_model = clip_model
         self.max_rows, self.max_batch = max_rows, max_batch
+        self.ms_early_exit = True     # stop the segmentation loop after an iteration that accepted no step (same predictions)
+        self.ms_iterations_run = 0    # forwards of the last test_moment_segmentation call
         self._engine = None
         self._engine_key = None
         self.freeze_clip()
@@ -278,11 +280,27 @@ class MomentModel(nn.Module):
         steps = torch.zeros((B, n_iter, 2), dtype=torch.int32, device=dev)
         nsteps = torch.zeros((B,), dtype=torch.int32, device=dev)
         lib = _lib.load()
+        # An iteration that accepts no step for any clip leaves both masks as they were, so every later iteration would recompute
+        # exactly the same logits and accept nothing again (the reference still runs all n_iter forwards, modeling.py:391): the loop
+        # stops there.  The accepted-step total of iteration i is read back one iteration late, while iteration i + 1 is already
+        # running, so the host never waits on an idle GPU; at most one no-op iteration is enqueued.
+        totals = torch.zeros(n_iter, dtype=torch.int32).pin_memory() if self.ms_early_exit else None
+        events = []
         for it in range(n_iter):
             logits, _ = self._forward(video, text_feat, asr, vmask, mmask, bmask, reuse_base=(it > 0))
             with torch.cuda.device(dev):
                 _lib.check(lib.hb_moment_ms_step(logits.data_ptr(), mmask.data_ptr(), bmask.data_ptr(), steps.data_ptr(),
                                                  nsteps.data_ptr(), n_iter, B, T, thr, None, _lib.stream_ptr(dev)), "hb_moment_ms_step")
+                if totals is not None:
+                    totals[it:it + 1].copy_(nsteps.sum(dim=0, keepdim=True, dtype=torch.int32), non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    events.append(ev)
+                    if it >= 1:
+                        events[it - 1].synchronize()
+                        if int(totals[it - 1]) == (int(totals[it - 2]) if it >= 2 else 0):
+                            break
+        self.ms_iterations_run = it + 1
         steps_h, n_h = steps.cpu().tolist(), nsteps.cpu().tolist()
         preds = []
         for b in range(B):

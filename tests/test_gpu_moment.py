@@ -76,6 +76,15 @@ def test_moment_retrieval_and_segmentation_predictions_match_reference(model, go
     out = m.test_step(b)
     assert out["prediction"] == golden[case]["ms_pred"]
     assert out["raw_predictions"] == out["prediction"]
+    # the loop stops after an iteration that accepted no step (later iterations would repeat it): same predictions as all 20
+    # forwards; in the 40-frame case iteration 10 is the first that changes nothing (CPU oracle), seen one iteration late
+    early = m.ms_iterations_run
+    try:
+        m.ms_early_exit = False
+        assert m.test_step(b)["prediction"] == golden[case]["ms_pred"] and m.ms_iterations_run == 20
+    finally:
+        m.ms_early_exit = True
+    assert early == (12 if case == "small" else 20), early
 
 
 def test_ms_step_kernel_matches_reference_control_flow(hb):
