@@ -118,6 +118,7 @@ class MomentModel(nn.Module):
                 "EVA_CLIP_g_14", pretrained=getattr(self.args, "eva_clip_path", "./pretrained_weights/eva_clip_psz14.pt"))
         self.clip_model = clip_model
         self.max_rows, self.max_batch = max_rows, max_batch
+        self.dedup_prompts = True     # encode each distinct prompt of a batch once (same features)
         self.ms_early_exit = True     # stop the segmentation loop after an iteration that accepted no step (same predictions)
         self.ms_iterations_run = 0    # forwards of the last test_moment_segmentation call
         self._engine = None
@@ -232,8 +233,18 @@ class MomentModel(nn.Module):
         ids = batch["clip_text_ids"]
         if ids.device.type == "cpu" and hasattr(getattr(self.clip_model, "text", None), "validate_ids"):
             self.clip_model.text.validate_ids(ids)   # host-side range check, as nn.Embedding would raise (no device sync)
-        text_feat = self.clip_model.encode_text(ids.to(dev)).float().contiguous()
-        return video, vmask, asr, text_feat
+        # Rows of one batch often repeat a prompt (every step of a video is captioned under the video's prompt, several videos answer
+        # one query): each distinct token row goes through the text tower once and the features are gathered back.  A row's embedding
+        # does not depend on what else is in the batch (bit-identical, tests/test_gpu_chain.py), so this only removes recomputation.
+        inv = None
+        if self.dedup_prompts and ids.device.type == "cpu" and ids.dim() == 2 and ids.shape[0] > 1:
+            uniq, inverse = torch.unique(ids, dim=0, return_inverse=True)
+            if uniq.shape[0] < ids.shape[0]:
+                ids, inv = uniq, inverse.to(dev)
+        text_feat = self.clip_model.encode_text(ids.to(dev)).float()
+        if inv is not None:
+            text_feat = text_feat.index_select(0, inv)
+        return video, vmask, asr, text_feat.contiguous()
 
     def foward_moment_shared(self, video_feats, text_feat, video_mask=None, moment_mask=None, asr_feats=None, boundary_mask=None):
         """Same (misspelt) name and argument order as modeling.py:155."""

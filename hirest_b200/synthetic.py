@@ -230,6 +230,14 @@ def make_moment_state_dict(seed: int = 3, device="cpu", cfg: dict = MOMENT_CFG) 
     return sd
 
 
+def _placeholder_ids(B: int):
+    """Token rows for batches whose text features come from a stand-in encoder: zeros except a distinct value per sample in slot 1,
+    so the samples count as different prompts (MomentModel encodes repeated prompts of a batch once)."""
+    ids = torch.zeros((B, 77), dtype=torch.int64)
+    ids[:, 1] = torch.arange(B)
+    return ids
+
+
 def make_moment_batch(B: int, T: int, seed: int = 5, ragged: bool = True, cfg: dict = MOMENT_CFG):
     """Synthetic collate output (hirest_dataset.py:409-531): unit-norm frame features (extract_features.py:64), ASR
     features, masks, moment bounds; plus fixed stand-in text features [B, 1024] (what encode_text would return)."""
@@ -248,7 +256,7 @@ def make_moment_batch(B: int, T: int, seed: int = 5, ragged: bool = True, cfg: d
     text_feat = torch.randn((B, cfg["clip_dim"]), generator=g)
     return {"vis_feats": vis, "vis_mask": vis_mask, "asr_feats": asr, "moment_mask": moment_mask,
             "moment_bound_frames": bounds, "text_feat": text_feat, "n_frames": n,
-            "clip_text_ids": torch.zeros((B, 77), dtype=torch.int64)}
+            "clip_text_ids": _placeholder_ids(B)}
 
 
 # ---------------------------------------------------------------------------------------------------

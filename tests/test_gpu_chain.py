@@ -59,6 +59,34 @@ def test_text_tower_precise_matches_reference(clip, golden):
         assert e < TEXT_REL_CAP, (case, e)
 
 
+def test_repeated_prompts_are_encoded_once_with_identical_features(clip, model):
+    """A prompt's embedding does not depend on what else is in the batch (same bits alone, repeated, shuffled among others), so
+    MomentModel encodes each distinct token row of a batch once and gathers: identical text features, 5 rows through the tower
+    instead of 40."""
+    ids = synthetic.make_chain_batch(5, 40, 21)["clip_text_ids"]
+    perm = torch.tensor([3, 0, 0, 4, 1, 3, 2, 2] * 5)
+    rep = ids[perm]
+    full = clip.encode_text(rep.to(DEV))
+    each = clip.encode_text(ids.to(DEV))
+    assert torch.equal(full, each[perm.to(DEV)])
+    for i in range(5):
+        assert torch.equal(clip.encode_text(ids[i:i + 1].to(DEV))[0], each[i])
+    b = synthetic.make_chain_batch(40, 40, 22)
+    b["clip_text_ids"] = rep
+    calls = []
+    orig = clip.encode_text
+    try:
+        clip.encode_text = lambda t: (calls.append(t.shape[0]), orig(t))[1]
+        model.dedup_prompts = True
+        tf_dedup = model._inputs(b)[3]
+        model.dedup_prompts = False
+        tf_all = model._inputs(b)[3]
+    finally:
+        model.dedup_prompts = True
+        del clip.encode_text
+    assert calls == [5, 40] and torch.equal(tf_dedup, tf_all)
+
+
 def test_text_tower_bf16_mode_is_the_looser_one(hb, golden):
     """precise=False keeps the plain-bf16 tower of the north_star wording; it must still be within the bf16 budget."""
     m = eva_clip.EVA_CLIP(**synthetic.CHAIN_CLIP, precise_text=False)
