@@ -381,7 +381,7 @@ int hb_init(int device) {
   g_num_sms = prop.multiProcessorCount;
   if (hb::tmap_init() != 0) return fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   if (!g_inited) {   // A/B switches from the environment (hirest_b200_debug.h), once
-    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "decoder_graphs", "decoder_split_k", "decoder_kv_index", "ln_split_fuse", "attention_dots_late", "profile_layer", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
+    static const char* keys[] = {"gemm_cta_group", "attention_version", "small_attention_tc", "resize_version", "decoder_graphs", "decoder_split_k", "decoder_kv_index", "ln_split_fuse", "attention_dots_late", "profile_layer", "attention_prefetch", "ln_fold", "gemm_balanced_tiles",
                                  "gemm_dynamic_schedule", "gemm_resid_prefetch_chunks"};
     for (const char* key : keys) {
       std::string env = std::string("HB_DEBUG_") + key;
@@ -427,6 +427,9 @@ int hb_debug_set(const char* key, int value) {
   } else if (k == "attention_version") {
     if (value < 1 || value > 3) return fail(HB_ERR_INVALID, "attention version must be 1, 2 or 3");
     g_attn_version = value;
+  } else if (k == "resize_version") {
+    if (value != 1 && value != 2) return fail(HB_ERR_INVALID, "resize_version must be 1 or 2");
+    hb::resize_set_version(value);
   } else if (k == "small_attention_tc") {
     if (value < 0 || value > 2) return fail(HB_ERR_INVALID, "small_attention_tc must be 0, 1 or 2");
     g_small_attn_tc = value ? 1 : 0;
@@ -940,8 +943,10 @@ int hb_resize_crop_u8(const uint8_t* src, int64_t B, int H, int W, int S, uint8_
       if (r == -3) return fail(HB_ERR_INVALID, "invalid frame size %dx%d -> %d (need H, W >= 1 and 1 <= S <= 256)", H, W, S);
       if (r == -6) return fail(HB_ERR_INVALID, "frame %dx%d is too large for the shared-memory row window of the resize kernel", H, W);
       if (r) return fail(HB_ERR_INVALID, "resize plan failed (%d)", r);
-      std::vector<int> packed(hb::resize_plan_table_ints(ne->plan));
+      const size_t n1 = hb::resize_plan_table_ints(ne->plan);
+      std::vector<int> packed(n1 + hb::resize_plan_table_ints_v2(ne->plan));
       hb::resize_plan_pack(ne->plan, packed.data());
+      hb::resize_plan_pack_v2(ne->plan, packed.data() + n1);
       if (int a = ne->tables.alloc(packed.size() * sizeof(int))) return a;
       HB_CUDA(cudaMemcpy(ne->tables.p, packed.data(), packed.size() * sizeof(int), cudaMemcpyHostToDevice));  // first use of this size only
       it = g_resize_plans.emplace(key, std::move(ne)).first;

@@ -15,6 +15,17 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(params=[2, 1], ids=["dp4a_words", "byte_loads"], autouse=True)
+def resize_version(request):
+    """Every test runs on both kernels: v2 (default: planar word loads + dp4a on byte-plane weights) and v1 (byte loads + IMAD)."""
+    from hirest_b200 import _lib
+
+    _lib.load()
+    _lib.debug_set("resize_version", request.param)
+    yield request.param
+    _lib.debug_set("resize_version", 1)
+
+
 def _sha(a):
     return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), np.uint8)
 
