@@ -31,7 +31,7 @@ size_t resize_plan_table_ints(const ResizePlanHost& plan);
 void resize_plan_pack(const ResizePlanHost& plan, int* out);        // hb | hk | vb | vk, as the kernel expects them
 size_t resize_plan_table_ints_v2(const ResizePlanHost& plan);       // 0 when the plan has no v2 form
 void resize_plan_pack_v2(const ResizePlanHost& plan, int* out);     // hw0 | hwt | vw0 | vwt; stored right behind the v1 tables
-void resize_set_version(int v);                                     // 2 (default): word loads + dp4a; 1: byte loads + IMAD
+void resize_set_version(int v);                                     // 1 (default): byte loads + IMAD; 2: word loads + dp4a (cross-check)
 // src [B,H,W,3] uint8 (device) -> dst [B,3,S,S] uint8 (device). d_tables = packed tables on the device.
 int resize_crop_launch(const ResizePlanHost& plan, const int* d_tables, const uint8_t* src, uint8_t* dst, long long B, cudaStream_t s);
 
