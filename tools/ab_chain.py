@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--beam", type=int, default=3)
     a = ap.parse_args()
     dev = torch.device("cuda:0")
-    n, tmin, tmax, bs, cbs = a.videos, 120, 600, 64, 256
+    n, tmin, tmax, bs, cbs = a.videos, 120, 600, 64, 512
     vpath, _ = bench_extra._vocab_file()
     model, _ = bench_extra._chain_model(dev, bs * tmax, cbs, vpath)
     g = torch.Generator().manual_seed(17)

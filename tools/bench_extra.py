@@ -305,7 +305,7 @@ def _e2e(args, cfg, model_name, ctx):
     from hirest_b200 import pipeline, synthetic
 
     n, tmin, tmax, bs = args.videos, 120, 600, 64
-    cbs = 256   # step items per beam search (<= 20 trimmed frames each): the decode loop is latency-bound, captions are batch-independent
+    cbs = 512   # step items per beam search (<= 20 trimmed frames each): the decode loop is latency-bound, captions are batch-independent
     vpath, vlist = _vocab_file()
     model, sd = _chain_model(dev, bs * tmax, cbs, vpath)
     g = torch.Generator().manual_seed(17)
