@@ -168,7 +168,9 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
         return out
 
     # ---- 1. moment retrieval (dataset :153-183, evaluate :704-744) -------------------------------------------------
-    items = with_features(build_items(annotations(lambda v: [0, 0], lambda v: []), "moment_retrieval", nmf, end_to_end=True))
+    # (items carry masks and bounds; the features are attached per batch inside the prepare step, i.e. for this rank's items only
+    # and, with prefetch, by the worker thread)
+    items = build_items(annotations(lambda v: [0, 0], lambda v: []), "moment_retrieval", nmf, end_to_end=True)
     mr: Dict[str, Dict[str, dict]] = {}
     # Retrieval and segmentation see the same videos in the same batches (one item per video, same order, same shards): the padded
     # feature tensors of a batch are collated and copied to the GPU once and reused by the segmentation pass (the reference
@@ -210,6 +212,7 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
     def prepare_video_batch(chunk):
         key = tuple(it["fname"] for it in chunk)
         hit = feat_cache.get(key)
+        chunk = with_features(chunk)
         if hit is None:
             b = collate(chunk, nmf, feature_alloc)
             nbytes = (b["vis_feats"].numel() + b["asr_feats"].numel()) * 4
@@ -240,8 +243,8 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
             "bounds": mr[v["prompt"]][v["fname"]]["bounds"],
             "steps": [{"index": i, "heading": "", "absolute_bounds": [i, i + 1]} for i in range(5)]}
     # ---- 2. moment segmentation (dataset :239-266 test branch, evaluate :746-782) ----------------------------------
-    items = with_features(build_items(annotations(lambda v: state[v["prompt"]][v["fname"]]["bounds"],
-                                                  lambda v: state[v["prompt"]][v["fname"]]["steps"]), "moment_segmentation", nmf, end_to_end=True))
+    items = build_items(annotations(lambda v: state[v["prompt"]][v["fname"]]["bounds"],
+                                    lambda v: state[v["prompt"]][v["fname"]]["steps"]), "moment_segmentation", nmf, end_to_end=True)
     ms: Dict[str, dict] = {}
     preds = _run_sharded(items, run_video_batch, batch_size, rank, world, gather, prepare=prepare_video_batch, prefetch=prefetch)
     feat_cache.clear()
@@ -256,12 +259,11 @@ def run_end_to_end(model, videos: Sequence[dict], batch_size: int = 64, num_beam
                                              for i, b in enumerate(ms[fname]["bounds"])] if fname in ms else []
     # ---- 3. step captioning (dataset :268-312, evaluate :787-830) --------------------------------------------------
     # (a video whose segmentation produced no step contributes nothing; the reference indexes steps[0] and raises)
-    items = with_features(build_items(annotations(lambda v: state[v["prompt"]][v["fname"]]["bounds"],
-                                                  lambda v: state[v["prompt"]][v["fname"]]["steps"]), "step_captioning", nmf, end_to_end=True),
-                          slice_to_moment=True)
+    items = build_items(annotations(lambda v: state[v["prompt"]][v["fname"]]["bounds"],
+                                    lambda v: state[v["prompt"]][v["fname"]]["steps"]), "step_captioning", nmf, end_to_end=True)
     sc: Dict[str, dict] = {}
     def prepare_step_batch(chunk):
-        b = collate(chunk, -1, feature_alloc)   # ragged items: pad path
+        b = collate(with_features(chunk, slice_to_moment=True), -1, feature_alloc)   # ragged items: pad path
         if on_gpu:
             (b["vis_feats"], b["asr_feats"]), b["_copied"] = to_device(b["vis_feats"], b["asr_feats"])
         return b
