@@ -428,7 +428,7 @@ int hb_debug_set(const char* key, int value) {
     if (value < 1 || value > 3) return fail(HB_ERR_INVALID, "attention version must be 1, 2 or 3");
     g_attn_version = value;
   } else if (k == "resize_version") {
-    if (value != 1 && value != 2) return fail(HB_ERR_INVALID, "resize_version must be 1 or 2");
+    if (value < 1 || value > 3) return fail(HB_ERR_INVALID, "resize_version must be 1, 2 or 3");
     hb::resize_set_version(value);
   } else if (k == "small_attention_tc") {
     if (value < 0 || value > 2) return fail(HB_ERR_INVALID, "small_attention_tc must be 0, 1 or 2");

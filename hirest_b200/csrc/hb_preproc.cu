@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) resize_crop_kernel(const KParams p) {
 }
 
 
-// ---- kernel v2 (cross-check, not the default): word loads + dp4a -----------------------------------------------------------------------------------
+// ---- kernels v2 / v3 (cross-checks, not the default): word loads + dp4a / + byte extraction -----------------------------------------------------------------------------------
 // v1 spends one LDS.U8 and one IMAD per (pixel, tap, channel) and is LSU-bound at 7 % of the HBM roofline (360p).  v2 keeps the
 // arithmetic exact and moves four taps per instruction:
 //   * staged source rows are de-interleaved into R / G / B planes in shared memory, so the taps of one output column are
@@ -203,6 +203,8 @@ struct KParams2 {
   const uint32_t* hwt;     // [S][3][nwh]
   const int* vw0;          // [S]
   const uint32_t* vwt;     // [S][3][nwv]
+  const int* hwi;          // [S][4 nwh]  the same taps as plain 22-bit weights, one per byte of the words (kernel v3), 16-byte aligned rows
+  const int* vwi;          // [S][4 nwv]
   int H, W, S, x0, span_bytes, row_pitch, ng4, pw, tw, nwh, nwv, ty;
 };
 
@@ -217,6 +219,17 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // a u
   return d;
 }
 
+// DP4A = false is kernel v3: the same layout and word loads, but each byte of a word is extracted (ALU pipe) and multiplied by its
+// plain 22-bit weight with an IMAD — dp4a issues at a fraction of the IMAD rate on this part (v2 measured dp4a-bound).
+__device__ __forceinline__ int mac4(uint32_t px, const int4& w, int acc) {
+  acc += static_cast<int>(px & 0xffu) * w.x;
+  acc += static_cast<int>((px >> 8) & 0xffu) * w.y;
+  acc += static_cast<int>((px >> 16) & 0xffu) * w.z;
+  acc += static_cast<int>(px >> 24) * w.w;
+  return acc;
+}
+
+template <bool DP4A>
 __global__ void __launch_bounds__(256) resize_crop2_kernel(const KParams2 p) {
   extern __shared__ __align__(16) uint8_t sm[];
   uint8_t* stage = sm;                                                          // [G][row_pitch]  interleaved source rows
@@ -276,32 +289,55 @@ __global__ void __launch_bounds__(256) resize_crop2_kernel(const KParams2 p) {
     __syncthreads();
     // ---- horizontal pass: thread x, 3 channels x 4 rows, four taps per dp4a
     if (active) {
-      int a0[G][3], a1[G][3], a2[G][3];
-#pragma unroll
-      for (int j = 0; j < G; ++j)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { a0[j][c] = 0; a1[j][c] = 0; a2[j][c] = 0; }
-      for (int n = 0; n < p.nwh; ++n) {
-        const uint32_t b0 = __ldg(hwx + n), b1 = __ldg(hwx + p.nwh + n), b2 = __ldg(hwx + 2 * p.nwh + n);
+      if constexpr (DP4A) {
+        int a0[G][3], a1[G][3], a2[G][3];
 #pragma unroll
         for (int j = 0; j < G; ++j)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const uint32_t px = planes[(c * G + j) * p.pw + hw0 + n];
-            a0[j][c] = dp4a_uu(px, b0, a0[j][c]);
-            a1[j][c] = dp4a_uu(px, b1, a1[j][c]);
-            a2[j][c] = dp4a_us(px, b2, a2[j][c]);
-          }
-      }
+          for (int c = 0; c < 3; ++c) { a0[j][c] = 0; a1[j][c] = 0; a2[j][c] = 0; }
+        for (int n = 0; n < p.nwh; ++n) {
+          const uint32_t b0 = __ldg(hwx + n), b1 = __ldg(hwx + p.nwh + n), b2 = __ldg(hwx + 2 * p.nwh + n);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        uint32_t word = 0;
+          for (int j = 0; j < G; ++j)
 #pragma unroll
-        for (int j = 0; j < G; ++j) {
-          const int v = (1 << (PRECISION_BITS - 1)) + a0[j][c] + (a1[j][c] << 8) + (a2[j][c] << 16);
-          word |= static_cast<uint32_t>(clip8(v)) << (8 * j);
+            for (int c = 0; c < 3; ++c) {
+              const uint32_t px = planes[(c * G + j) * p.pw + hw0 + n];
+              a0[j][c] = dp4a_uu(px, b0, a0[j][c]);
+              a1[j][c] = dp4a_uu(px, b1, a1[j][c]);
+              a2[j][c] = dp4a_us(px, b2, a2[j][c]);
+            }
         }
-        tmp[(static_cast<size_t>(c) * p.S + x) * p.tw + g] = word;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          uint32_t word = 0;
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            const int v = (1 << (PRECISION_BITS - 1)) + a0[j][c] + (a1[j][c] << 8) + (a2[j][c] << 16);
+            word |= static_cast<uint32_t>(clip8(v)) << (8 * j);
+          }
+          tmp[(static_cast<size_t>(c) * p.S + x) * p.tw + g] = word;
+        }
+      } else {
+        int acc[G][3];
+#pragma unroll
+        for (int j = 0; j < G; ++j)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[j][c] = 1 << (PRECISION_BITS - 1);
+        const int4* wx = reinterpret_cast<const int4*>(p.hwi + static_cast<size_t>(x) * 4 * p.nwh);
+        for (int n = 0; n < p.nwh; ++n) {
+          const int4 w = __ldg(wx + n);
+#pragma unroll
+          for (int j = 0; j < G; ++j)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc[j][c] = mac4(planes[(c * G + j) * p.pw + hw0 + n], w, acc[j][c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          uint32_t word = 0;
+#pragma unroll
+          for (int j = 0; j < G; ++j) word |= static_cast<uint32_t>(clip8(acc[j][c])) << (8 * j);
+          tmp[(static_cast<size_t>(c) * p.S + x) * p.tw + g] = word;
+        }
       }
     }
     // (the next group's staging only writes `stage`; its de-interleave starts behind the barrier that follows the staging)
@@ -314,21 +350,33 @@ __global__ void __launch_bounds__(256) resize_crop2_kernel(const KParams2 p) {
       const int y = y0 + yy;
       const int wi = (p.vw0[y] - r0a) >> 2;
       const uint32_t* vwy = p.vwt + static_cast<size_t>(y) * 3 * p.nwv;
-      int a0[3] = {0, 0, 0}, a1[3] = {0, 0, 0}, a2[3] = {0, 0, 0};
-      for (int n = 0; n < p.nwv; ++n) {
-        const uint32_t b0 = __ldg(vwy + n), b1 = __ldg(vwy + p.nwv + n), b2 = __ldg(vwy + 2 * p.nwv + n);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const uint32_t px = tmp[(static_cast<size_t>(c) * p.S + x) * p.tw + wi + n];
-          a0[c] = dp4a_uu(px, b0, a0[c]);
-          a1[c] = dp4a_uu(px, b1, a1[c]);
-          a2[c] = dp4a_us(px, b2, a2[c]);
-        }
-      }
       uint8_t* d = p.dst + (static_cast<size_t>(b) * 3 * p.S + y) * p.S + x;
+      if constexpr (DP4A) {
+        int a0[3] = {0, 0, 0}, a1[3] = {0, 0, 0}, a2[3] = {0, 0, 0};
+        for (int n = 0; n < p.nwv; ++n) {
+          const uint32_t b0 = __ldg(vwy + n), b1 = __ldg(vwy + p.nwv + n), b2 = __ldg(vwy + 2 * p.nwv + n);
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-        d[c * plane] = static_cast<uint8_t>(clip8((1 << (PRECISION_BITS - 1)) + a0[c] + (a1[c] << 8) + (a2[c] << 16)));
+          for (int c = 0; c < 3; ++c) {
+            const uint32_t px = tmp[(static_cast<size_t>(c) * p.S + x) * p.tw + wi + n];
+            a0[c] = dp4a_uu(px, b0, a0[c]);
+            a1[c] = dp4a_uu(px, b1, a1[c]);
+            a2[c] = dp4a_us(px, b2, a2[c]);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          d[c * plane] = static_cast<uint8_t>(clip8((1 << (PRECISION_BITS - 1)) + a0[c] + (a1[c] << 8) + (a2[c] << 16)));
+      } else {
+        int acc[3] = {1 << (PRECISION_BITS - 1), 1 << (PRECISION_BITS - 1), 1 << (PRECISION_BITS - 1)};
+        const int4* wy = reinterpret_cast<const int4*>(p.vwi + static_cast<size_t>(y) * 4 * p.nwv);
+        for (int n = 0; n < p.nwv; ++n) {
+          const int4 w = __ldg(wy + n);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) acc[c] = mac4(tmp[(static_cast<size_t>(c) * p.S + x) * p.tw + wi + n], w, acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) d[c * plane] = static_cast<uint8_t>(clip8(acc[c]));
+      }
     }
   }
 }
@@ -356,11 +404,21 @@ bool build_v2_axis(const std::vector<int>& bounds, const std::vector<int>& coeff
   return true;
 }
 
+void build_v3_axis(const std::vector<int>& bounds, const std::vector<int>& coeffs, int ksize, int count, int nw, std::vector<int>& wi) {
+  wi.assign(static_cast<size_t>(count) * 4 * nw, 0);
+  for (int i = 0; i < count; ++i) {
+    const int mis = bounds[2 * i] & 3;
+    for (int k = 0; k < bounds[2 * i + 1]; ++k) wi[static_cast<size_t>(i) * 4 * nw + mis + k] = coeffs[static_cast<size_t>(i) * ksize + k];
+  }
+}
+
 void build_v2(ResizePlanHost* plan) {
   const int S = plan->S;
   plan->v2 = false;
   if (!build_v2_axis(plan->hb, plan->hk, plan->kh, S, false, &plan->nwh, plan->hw0, plan->hwt)) return;
   if (!build_v2_axis(plan->vb, plan->vk, plan->kv, S, true, &plan->nwv, plan->vw0, plan->vwt)) return;
+  build_v3_axis(plan->hb, plan->hk, plan->kh, S, plan->nwh, plan->hwi);
+  build_v3_axis(plan->vb, plan->vk, plan->kv, S, plan->nwv, plan->vwi);
   const int span_px = plan->span_bytes / 3;
   plan->ng4 = (span_px + 3) / 4;
   plan->pw = plan->ng4 + plan->nwh;                                  // reads run up to nwh words past a column's first word
@@ -385,7 +443,7 @@ int g_resize_version = 1;   // v2 is bit-identical but measured 20 % slower (DES
 
 }  // namespace
 
-void resize_set_version(int v) { g_resize_version = (v == 1) ? 1 : 2; }
+void resize_set_version(int v) { g_resize_version = (v >= 1 && v <= 3) ? v : 1; }
 
 void resized_output_size(int H, int W, int S, int* nh, int* nw) {
   // torchvision _compute_resized_output_size(size=[S]): shorter edge -> S, longer -> int(S * long / short)
@@ -430,15 +488,18 @@ int resize_plan_build(ResizePlanHost* plan, int H, int W, int S) {
   return 0;
 }
 
+static size_t v3_offset(const ResizePlanHost& plan);
+
 int resize_crop_launch(const ResizePlanHost& plan, const int* d_tables, const uint8_t* src, uint8_t* dst, long long B, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(resize_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(resize_crop2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(resize_crop2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(resize_crop2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  if (plan.v2 && g_resize_version == 2) {
+  if (plan.v2 && g_resize_version >= 2) {
     const int S = plan.S;
     KParams2 q;
     const int* t2 = d_tables + resize_plan_table_ints(plan);   // the v2 tables follow the v1 tables
@@ -446,6 +507,8 @@ int resize_crop_launch(const ResizePlanHost& plan, const int* d_tables, const ui
     q.hwt = reinterpret_cast<const uint32_t*>(q.hw0 + S);
     q.vw0 = reinterpret_cast<const int*>(q.hwt + static_cast<size_t>(S) * 3 * plan.nwh);
     q.vwt = reinterpret_cast<const uint32_t*>(q.vw0 + S);
+    q.hwi = d_tables + v3_offset(plan);
+    q.vwi = q.hwi + static_cast<size_t>(S) * 4 * plan.nwh;
     q.H = plan.H; q.W = plan.W; q.S = S; q.x0 = plan.x0; q.span_bytes = plan.span_bytes; q.row_pitch = plan.row_pitch2;
     q.ng4 = plan.ng4; q.pw = plan.pw; q.tw = plan.tw; q.nwh = plan.nwh; q.nwv = plan.nwv; q.ty = plan.ty2;
     const int threads = (S + 31) / 32 * 32;
@@ -454,7 +517,8 @@ int resize_crop_launch(const ResizePlanHost& plan, const int* d_tables, const ui
       q.src = src + static_cast<size_t>(b0) * plan.H * plan.W * 3;
       q.dst = dst + static_cast<size_t>(b0) * 3 * S * S;
       dim3 grid(static_cast<unsigned>((S + plan.ty2 - 1) / plan.ty2), static_cast<unsigned>(nb));
-      resize_crop2_kernel<<<grid, threads, plan.smem2, s>>>(q);
+      if (g_resize_version == 2) resize_crop2_kernel<true><<<grid, threads, plan.smem2, s>>>(q);
+      else resize_crop2_kernel<false><<<grid, threads, plan.smem2, s>>>(q);
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return static_cast<int>(e);
     }
@@ -486,8 +550,15 @@ size_t resize_plan_table_ints(const ResizePlanHost& plan) {
   return static_cast<size_t>(plan.S) * (4 + plan.kh + plan.kv);
 }
 
+// ints from the start of the whole table (v1 | v2 | pad | v3) to the v3 weights: a multiple of 4, so that the int4 loads are aligned
+static size_t v3_offset(const ResizePlanHost& plan) {
+  const size_t end_v2 = resize_plan_table_ints(plan) + static_cast<size_t>(plan.S) * (2 + 3 * plan.nwh + 3 * plan.nwv);
+  return (end_v2 + 3) / 4 * 4;
+}
+
 size_t resize_plan_table_ints_v2(const ResizePlanHost& plan) {
-  return plan.v2 ? static_cast<size_t>(plan.S) * (2 + 3 * plan.nwh + 3 * plan.nwv) : 0;
+  if (!plan.v2) return 0;
+  return v3_offset(plan) + static_cast<size_t>(plan.S) * 4 * (plan.nwh + plan.nwv) - resize_plan_table_ints(plan);
 }
 
 void resize_plan_pack_v2(const ResizePlanHost& plan, int* out) {
@@ -500,6 +571,11 @@ void resize_plan_pack_v2(const ResizePlanHost& plan, int* out) {
   std::memcpy(out, plan.vw0.data(), sizeof(int) * S);
   out += S;
   std::memcpy(out, plan.vwt.data(), sizeof(uint32_t) * plan.vwt.size());
+  out += plan.vwt.size();
+  out += v3_offset(plan) - (resize_plan_table_ints(plan) + static_cast<size_t>(S) * (2 + 3 * plan.nwh + 3 * plan.nwv));   // alignment pad
+  std::memcpy(out, plan.hwi.data(), sizeof(int) * plan.hwi.size());
+  out += plan.hwi.size();
+  std::memcpy(out, plan.vwi.data(), sizeof(int) * plan.vwi.size());
 }
 
 void resize_plan_pack(const ResizePlanHost& plan, int* out) {

@@ -23,6 +23,7 @@ struct ResizePlanHost {
   int ty2 = 0, row_pitch2 = 0, smem2 = 0;
   std::vector<int> hw0, vw0;              // [S] first word of a column's taps in the planar row / first source row (multiple of 4) of a row's taps
   std::vector<uint32_t> hwt, vwt;         // [S][3][nwh] / [S][3][nwv]: weight bytes b0 | b1 | b2 (w = b0 + 256 b1 + 65536 b2, b2 signed)
+  std::vector<int> hwi, vwi;              // [S][4 nwh] / [S][4 nwv]: the same taps as plain weights, one per byte of the words (kernel v3)
 };
 
 void resized_output_size(int H, int W, int S, int* nh, int* nw);
@@ -30,8 +31,8 @@ int resize_plan_build(ResizePlanHost* plan, int H, int W, int S);   // 0, -3 inv
 size_t resize_plan_table_ints(const ResizePlanHost& plan);
 void resize_plan_pack(const ResizePlanHost& plan, int* out);        // hb | hk | vb | vk, as the kernel expects them
 size_t resize_plan_table_ints_v2(const ResizePlanHost& plan);       // 0 when the plan has no v2 form
-void resize_plan_pack_v2(const ResizePlanHost& plan, int* out);     // hw0 | hwt | vw0 | vwt; stored right behind the v1 tables
-void resize_set_version(int v);                                     // 1 (default): byte loads + IMAD; 2: word loads + dp4a (cross-check)
+void resize_plan_pack_v2(const ResizePlanHost& plan, int* out);     // hw0 | hwt | vw0 | vwt | pad | hwi | vwi; stored right behind the v1 tables
+void resize_set_version(int v);                                     // 1: byte loads + IMAD; 2: word loads + dp4a; 3: word loads + byte extraction + IMAD
 // src [B,H,W,3] uint8 (device) -> dst [B,3,S,S] uint8 (device). d_tables = packed tables on the device.
 int resize_crop_launch(const ResizePlanHost& plan, const int* d_tables, const uint8_t* src, uint8_t* dst, long long B, cudaStream_t s);
 

@@ -18,8 +18,9 @@ extern "C" {
  * "small_attention_tc"         0 | 1 | 2             2         fp32 attention of the small sequence models on tensor cores (hb_attn_tc.cu;
  *                                                              2 = two CTAs per SM, 1 = the one-CTA-per-SM kernel, bit-identical results)
  *                                                              instead of CUDA cores (hb_attn_small.cu, 0); same results to ~1e-6
- * "resize_version"             1 | 2                 1         hb_resize_crop_u8: 1 = byte loads + IMAD, 2 = planar word loads + dp4a on
- *                                                              byte-plane weights (measured 20 % slower); bit-identical output
+ * "resize_version"             1 | 2 | 3             1         hb_resize_crop_u8: 1 = byte loads + IMAD, 2 = planar word loads + dp4a on
+ *                                                              byte-plane weights, 3 = planar word loads + byte extraction + IMAD
+ *                                                              (both measured 15-40 % slower); bit-identical output
  * "decoder_graphs"             0 | 1                 1         caption decoder: replay each decode step as a CUDA graph from the second
  *                                                              beam search of a (n_inst, beam, enc_len) shape on; same results
  * "decoder_split_k"            0 | k-blocks          6         caption decoder: the hidden-width linears of a decode step run as split-K GEMMs

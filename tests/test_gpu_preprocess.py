@@ -15,9 +15,10 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.fixture(params=[2, 1], ids=["dp4a_words", "byte_loads"], autouse=True)
+@pytest.fixture(params=[3, 2, 1], ids=["words_extract_imad", "words_dp4a", "byte_loads"], autouse=True)
 def resize_version(request):
-    """Every test runs on both kernels: v2 (default: planar word loads + dp4a on byte-plane weights) and v1 (byte loads + IMAD)."""
+    """Every test runs on all three kernels: v1 (byte loads + IMAD), v2 (planar word loads + dp4a on byte-plane weights) and v3 (planar
+    word loads + byte extraction + IMAD)."""
     from hirest_b200 import _lib
 
     _lib.load()

@@ -1,4 +1,4 @@
-// Host-side check of the resize kernel v2 tables and arithmetic (no GPU needed): emulates resize_crop2_kernel's data flow on the
+// Host-side check of the resize kernels v2 / v3 tables and arithmetic (no GPU needed): emulates resize_crop2_kernel's data flow on the
 // CPU — aligned-word staging, the byte_perm de-interleave, byte-plane weights + dp4a, the transposed 4-rows-per-word window —
 // from the plan's v2 tables, and compares every output byte with the plain two-pass evaluation of the v1 tables (Pillow's
 // arithmetic).   nvcc -std=c++17 -o tools/_build/preproc_host_check tools/preproc_host_check.cu build/hb_preproc.o
@@ -101,6 +101,12 @@ static int check(int H, int W, int S) {
               a2 = dp4a_us(px, p.hwt[(static_cast<size_t>(x) * 3 + 2) * p.nwh + n], a2);
             }
             const int v = static_cast<int>(static_cast<uint32_t>(1 << 21) + static_cast<uint32_t>(a0) + (static_cast<uint32_t>(a1) << 8) + (static_cast<uint32_t>(a2) << 16));
+            uint32_t v3 = 1u << 21;   // kernel v3: the same words, plain weights per byte
+            for (int n = 0; n < p.nwh; ++n) {
+              const uint32_t px = planes[(c * G + j) * p.pw + p.hw0[x] + n];
+              for (int i = 0; i < 4; ++i) v3 += ((px >> (8 * i)) & 0xff) * static_cast<uint32_t>(p.hwi[(static_cast<size_t>(x) * p.nwh + n) * 4 + i]);
+            }
+            if (static_cast<int>(v3) != v) { std::printf("%dx%d: v3 horizontal sum differs at x=%d\n", H, W, x); return 1; }
             word |= static_cast<uint32_t>(clip8(v)) << (8 * j);
           }
           tmp[(static_cast<size_t>(c) * S + x) * p.tw + g] = word;
@@ -119,6 +125,12 @@ static int check(int H, int W, int S) {
             a2 = dp4a_us(px, p.vwt[(static_cast<size_t>(y) * 3 + 2) * p.nwv + n], a2);
           }
           const int v = static_cast<int>(static_cast<uint32_t>(1 << 21) + static_cast<uint32_t>(a0) + (static_cast<uint32_t>(a1) << 8) + (static_cast<uint32_t>(a2) << 16));
+          uint32_t v3 = 1u << 21;
+          for (int n = 0; n < p.nwv; ++n) {
+            const uint32_t px = tmp[(static_cast<size_t>(c) * S + x) * p.tw + wi + n];
+            for (int i = 0; i < 4; ++i) v3 += ((px >> (8 * i)) & 0xff) * static_cast<uint32_t>(p.vwi[(static_cast<size_t>(y) * p.nwv + n) * 4 + i]);
+          }
+          if (static_cast<int>(v3) != v) { std::printf("%dx%d: v3 vertical sum differs at y=%d\n", H, W, y); return 1; }
           got[(static_cast<size_t>(c) * S + y) * S + x] = static_cast<uint8_t>(clip8(v));
         }
     }
