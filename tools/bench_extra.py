@@ -324,7 +324,9 @@ def _e2e(args, cfg, model_name, ctx):
         return pipeline.run_end_to_end(model, vs, batch_size=batch_size, num_beams=args.beam, rank=rank, world=world,
                                        caption_batch_size=cbs, prefetch=os.environ.get("HB_CHAIN_PREFETCH", "1") != "0")
 
-    ms, clocks, out, launches = _timed(ctx, lambda: job(videos), args.steps, lambda: job(videos[:bs]), 1)
+    # warm-up = the whole job twice: the first pass of a (batch, beam, frames) shape runs its decode steps eagerly and the second
+    # captures them into CUDA graphs (hb_decoder_step); pinned staging blocks and engine workspaces reach their final sizes
+    ms, clocks, out, launches = _timed(ctx, lambda: job(videos), args.steps, lambda: job(videos), 2)
     value = n * args.steps / (ms * 1e-3)
     n_steps = sum(len(x["steps"]) for p in out["final"].values() for x in p.values())
     check = {"steps_captioned": n_steps, "videos_in_result": sum(len(p) for p in out["final"].values())}
@@ -360,7 +362,7 @@ def _e2e(args, cfg, model_name, ctx):
                          "run.py:383-490"}
     peaks = ctx["peaks"]
     return {"metric": "videos/sec, moment retrieval -> segmentation -> step captioning chain (beam 3)", "value": value, "unit": "videos/s",
-            "n_gpus": world, "steps": args.steps, "warmup": 1, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "n_gpus": world, "steps": args.steps, "warmup": 2, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16x3 (split-bf16 GEMMs, fp32-accurate)", "data": "synthetic",
             "config": {"workload": f"BASELINE configs[4]: {n} synthetic videos of {tmin}-{tmax} frames, in-memory MR -> MS -> SC chain "
                                    f"(pipeline.run_end_to_end, batch {bs} videos / {cbs} step items, beam {args.beam}, max 48 words), host collate + H2D inside",
